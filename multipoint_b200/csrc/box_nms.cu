@@ -1,0 +1,552 @@
+// Row 4 / 4b of the hot path: utils.box_nms (multipoint/utils/utils.py:78-122, on top of
+// torchvision.ops.nms / batched_nms) and the torch.nonzero keypoint idiom
+// (predict_align_image_pair.py:170-171, evaluation.py:157-158, export_keypoints.py:100).
+//
+// The reference thresholds, sorts all candidates and runs torchvision's O(N^2) greedy IoU scan
+// (seconds per image on the CPU path its configs force).  Boxes are size x size squares centred
+// on integer pixels, so "j is suppressed by a kept i" depends only on the offset (dy,dx): the
+// host evaluates torchvision's fp32 IoU expression once per offset into a footprint bitmask.
+// Greedy NMS is then the unique fixed point of
+//     kept(p)       <=> no higher-priority neighbour in the footprint is kept
+//     priority      =   (score desc, row-major index asc)      [stable sort of the reference]
+// which is computed in parallel with three-valued logic: an undecided pixel becomes suppressed as
+// soon as one higher-priority neighbour is kept, and kept once all of them are decided not-kept.
+// Decisions are only taken on settled facts, so any evaluation order reaches the same result.
+//
+// Kernels (HBM-bound: 4 B read + 4 B written per pixel, plus 8 B per survivor):
+//  1. nms_tile_kernel    one CTA per TH x TW tile with an E-pixel apron staged in shared memory;
+//                        iterates to the local fixed point, writes the dense result once.  Pixels
+//                        whose dependency chain leaves the apron (<0.1 % at E=8) are written as
+//                        -score and queued on a per-image worklist.
+//  2. nms_fixup_kernel   one CTA per image; resolves the worklist against the dense map in L2.
+//                        Exits immediately when the list is empty.
+//  3. nms_select_kernel  one CTA per image; optional top-k by radix select on (score desc, index
+//                        asc), then ordered (row-major) compaction of the survivors through a
+//                        bitmap into int64 (y,x) keypoints.
+#include <math.h>
+
+#include "mp_common.cuh"
+
+namespace mp {
+
+struct NmsFootprint {
+    int R;
+    uint32_t rows[31];  // rows[dy+R] bit (dx+R) set <=> offset (dy,dx) suppresses
+};
+
+constexpr int NMS_THREADS = 256;
+
+// ------------------------------------------------------------------------------------------
+// block-wide exclusive scan of one int per thread (NMS_THREADS threads); returns the offset of
+// this thread and the block total through `total`.
+__device__ __forceinline__ int block_exclusive_scan(int val, int *warp_sums, int &total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nwarps = blockDim.x >> 5;
+    int inc = val;
+#pragma unroll
+    for (int s = 1; s < 32; s <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, s);
+        if (lane >= s) inc += t;
+    }
+    __syncthreads();  // warp_sums may still be read from a previous call
+    if (lane == 31) warp_sums[warp] = inc;
+    __syncthreads();
+    int base = 0;
+    total = 0;
+    for (int w = 0; w < nwarps; ++w) {
+        const int s = warp_sums[w];
+        if (w < warp) base += s;
+        total += s;
+    }
+    return base + inc - val;
+}
+
+// Decide one undecided pixel at smem/gmem position given a neighbour fetch functor.
+// Returns +score (kept), 0 (suppressed) or the unchanged negative value (still undecided).
+template <typename Fetch>
+__device__ __forceinline__ float nms_decide(float val, const NmsFootprint &fp, Fetch fetch) {
+    const float s = -val;
+    const int R = fp.R;
+    bool blocked = false;
+    for (int dy = -R; dy <= R; ++dy) {
+        uint32_t row = fp.rows[dy + R];
+        while (row) {
+            const int bit = __ffs(row) - 1;
+            row &= row - 1;
+            const int dx = bit - R;
+            const float nv = fetch(dy, dx);
+            if (nv == 0.f) continue;
+            const float sn = fabsf(nv);
+            const bool higher = sn > s || (sn == s && (dy < 0 || (dy == 0 && dx < 0)));
+            if (!higher) continue;
+            if (nv > 0.f) return 0.f;  // a kept higher-priority neighbour suppresses us
+            blocked = true;            // an undecided one: wait
+        }
+    }
+    return blocked ? val : s;
+}
+
+template <int TH, int TW, int E, bool VEC>
+__global__ void __launch_bounds__(NMS_THREADS)
+nms_tile_kernel(const float *__restrict__ prob, float *__restrict__ out, int H, int W, float thr,
+                const NmsFootprint fp, uint2 *__restrict__ survivors, int *__restrict__ surv_count,
+                uint32_t *__restrict__ worklist, int *__restrict__ work_count, int cap) {
+    constexpr int EH = TH + 2 * E, EW = TW + 2 * E;
+    static_assert(EW % 4 == 0 && E % 4 == 0 && TW % 4 == 0, "float4 staging needs 4-px alignment");
+    static_assert(EH * EW < 65536, "list entries are uint16");
+    extern __shared__ __align__(16) float smem[];
+    float *v = smem;                                                // [EH][EW] signed state
+    uint16_t *list = reinterpret_cast<uint16_t *>(v + EH * EW);     // undecided positions
+    __shared__ int n_list;
+    __shared__ int warp_sums[NMS_THREADS / 32];
+    __shared__ int bases[2];
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int b = blockIdx.z;
+    const int ty0 = blockIdx.y * TH, tx0 = blockIdx.x * TW;
+    const int gy0 = ty0 - E, gx0 = tx0 - E;
+    const float *img = prob + (size_t)b * H * W;
+    const int R = fp.R;
+    if (tid == 0) n_list = 0;
+    __syncthreads();
+
+    // ---- 1. stage the tile + apron; threshold; encode: 0 = nothing, -s = undecided ----
+    constexpr int QW = EW / 4;
+    for (int i0 = 0; i0 < EH * QW; i0 += NMS_THREADS) {
+        const int i = i0 + tid;
+        const bool act = i < EH * QW;
+        const int ey = act ? i / QW : 0, q = act ? i - ey * QW : 0;
+        const int gy = gy0 + ey, gx = gx0 + 4 * q;
+        float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (act && gy >= 0 && gy < H) {
+            if (VEC) {
+                if (gx >= 0 && gx < W) val = ld_stream_f4(reinterpret_cast<const float4 *>(img + (size_t)gy * W + gx));
+            } else {
+                const float *rowp = img + (size_t)gy * W;
+                if (gx + 0 >= 0 && gx + 0 < W) val.x = rowp[gx + 0];
+                if (gx + 1 >= 0 && gx + 1 < W) val.y = rowp[gx + 1];
+                if (gx + 2 >= 0 && gx + 2 < W) val.z = rowp[gx + 2];
+                if (gx + 3 >= 0 && gx + 3 < W) val.w = rowp[gx + 3];
+            }
+        }
+        float c[4] = {val.x, val.y, val.z, val.w};
+        const bool rows_ok = act && ey >= R && ey < EH - R;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const bool cand = c[j] > thr;  // strict, fp32 (utils.py:97); NaN is not a candidate
+            c[j] = cand ? -c[j] : 0.f;
+            const int ex = 4 * q + j;
+            const bool push = cand && rows_ok && ex >= R && ex < EW - R;
+            const unsigned m = __ballot_sync(0xffffffffu, push);
+            if (m) {
+                int base = 0;
+                if (lane == (__ffs(m) - 1)) base = atomicAdd(&n_list, __popc(m));
+                base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+                if (push) list[base + __popc(m & ((1u << lane) - 1))] = (uint16_t)(ey * EW + ex);
+            }
+        }
+        if (act) *reinterpret_cast<float4 *>(v + ey * EW + 4 * q) = make_float4(c[0], c[1], c[2], c[3]);
+    }
+    __syncthreads();
+
+    // ---- 2. iterate to the local fixed point ----
+    const int n = n_list;
+    while (true) {
+        bool changed = false;
+        for (int i = tid; i < n; i += NMS_THREADS) {
+            const int e = list[i];
+            const float val = v[e];
+            if (val >= 0.f) continue;
+            const float *centre = v + e;
+            const float nv = nms_decide(val, fp, [&](int dy, int dx) { return centre[dy * EW + dx]; });
+            if (nv != val) {
+                v[e] = nv;
+                changed = true;
+            }
+        }
+        if (!__syncthreads_or(changed)) break;
+    }
+
+    // ---- 3. write the interior once; queue survivors and unresolved pixels ----
+    constexpr int IQ = TW / 4;
+    constexpr int PER_THREAD = (TH * IQ + NMS_THREADS - 1) / NMS_THREADS;
+    int kept = 0, unres = 0;
+#pragma unroll
+    for (int k = 0; k < PER_THREAD; ++k) {
+        const int i = tid + k * NMS_THREADS;
+        if (i >= TH * IQ) break;
+        const int iy = i / IQ, q = i - iy * IQ;
+        const int gy = ty0 + iy, gx = tx0 + 4 * q;
+        if (gy >= H || gx >= W) continue;
+        const float4 val = *reinterpret_cast<const float4 *>(v + (E + iy) * EW + E + 4 * q);
+        const float c[4] = {val.x, val.y, val.z, val.w};
+        if (VEC) {
+            st_stream_f4(reinterpret_cast<float4 *>(out + ((size_t)b * H + gy) * W + gx), val);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (gx + j < W) out[((size_t)b * H + gy) * W + gx + j] = c[j];
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (gx + j >= W) continue;
+            kept += c[j] > 0.f;
+            unres += c[j] < 0.f;
+        }
+    }
+    int tot_kept, tot_unres;
+    int off_kept = block_exclusive_scan(kept, warp_sums, tot_kept);
+    int off_unres = block_exclusive_scan(unres, warp_sums, tot_unres);
+    if (tid == 0) {
+        bases[0] = tot_kept ? atomicAdd(surv_count + b, tot_kept) : 0;
+        bases[1] = tot_unres ? atomicAdd(work_count + b, tot_unres) : 0;
+    }
+    __syncthreads();
+    if (tot_kept == 0 && tot_unres == 0) return;
+    off_kept += bases[0];
+    off_unres += bases[1];
+    uint2 *surv = survivors + (size_t)b * cap;
+    uint32_t *work = worklist + (size_t)b * cap;
+#pragma unroll
+    for (int k = 0; k < PER_THREAD; ++k) {
+        const int i = tid + k * NMS_THREADS;
+        if (i >= TH * IQ) break;
+        const int iy = i / IQ, q = i - iy * IQ;
+        const int gy = ty0 + iy, gx = tx0 + 4 * q;
+        if (gy >= H || gx >= W) continue;
+        const float *c = v + (E + iy) * EW + E + 4 * q;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (gx + j >= W) continue;
+            const uint32_t idx = (uint32_t)(gy * W + gx + j);
+            if (c[j] > 0.f) surv[off_kept++] = make_uint2(idx, __float_as_uint(c[j]));
+            else if (c[j] < 0.f) work[off_unres++] = idx;
+        }
+    }
+}
+
+// One CTA per image: resolve the pixels whose dependency chain left their tile's apron.
+__global__ void __launch_bounds__(1024)
+nms_fixup_kernel(float *__restrict__ out, int H, int W, const NmsFootprint fp, uint2 *__restrict__ survivors,
+                 int *__restrict__ surv_count, const uint32_t *__restrict__ worklist,
+                 const int *__restrict__ work_count, int cap) {
+    const int b = blockIdx.x;
+    const int n = work_count[b];
+    if (n == 0) return;
+    float *img = out + (size_t)b * H * W;
+    const uint32_t *work = worklist + (size_t)b * cap;
+    uint2 *surv = survivors + (size_t)b * cap;
+    while (true) {
+        bool changed = false, pending = false;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const int idx = (int)work[i];
+            const float val = __ldcg(img + idx);
+            if (val >= 0.f) continue;
+            const int y = idx / W, x = idx - y * W;
+            const float nv = nms_decide(val, fp, [&](int dy, int dx) {
+                const int yy = y + dy, xx = x + dx;
+                return (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldcg(img + yy * W + xx) : 0.f;
+            });
+            if (nv != val) {
+                __stcg(img + idx, nv);
+                changed = true;
+                if (nv > 0.f) surv[atomicAdd(surv_count + b, 1)] = make_uint2((uint32_t)idx, __float_as_uint(nv));
+            } else {
+                pending = true;
+            }
+        }
+        __threadfence_block();
+        const bool any_pending = __syncthreads_or(pending);
+        const bool any_changed = __syncthreads_or(changed);
+        if (!any_pending || !any_changed) break;  // !changed with pending cannot happen (progress is guaranteed)
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// ordered emission from a per-image bitmap: bit i of word w <=> pixel 32*w+i is a keypoint.
+// (no __restrict__ / read-only loads here: the bitmap and the score map were written earlier in
+// the same kernel by other threads of this CTA)
+__device__ void emit_from_bitmap(const uint32_t *bitmap, int words, int W, const float *score_src,
+                                 int64_t *__restrict__ kp, float *__restrict__ kp_scores, int32_t *__restrict__ kp_count,
+                                 int kp_cap, int *warp_sums) {
+    const int per = (words + blockDim.x - 1) / blockDim.x;
+    const int w0 = min(words, (int)threadIdx.x * per), w1 = min(words, w0 + per);
+    int cnt = 0;
+    for (int w = w0; w < w1; ++w) cnt += __popc(__ldcg(bitmap + w));
+    int total;
+    int off = block_exclusive_scan(cnt, warp_sums, total);
+    if (threadIdx.x == 0 && kp_count) *kp_count = total;
+    if (kp == nullptr) return;
+    for (int w = w0; w < w1; ++w) {
+        uint32_t bits = __ldcg(bitmap + w);
+        while (bits) {
+            const int i = __ffs(bits) - 1;
+            bits &= bits - 1;
+            if (off < kp_cap) {
+                const int idx = 32 * w + i;
+                kp[2 * (size_t)off] = idx / W;
+                kp[2 * (size_t)off + 1] = idx % W;
+                if (kp_scores) kp_scores[off] = __ldcg(score_src + idx);
+            }
+            ++off;
+        }
+    }
+}
+
+// One CTA per image: top-k (optional) + ordered compaction.
+__global__ void __launch_bounds__(1024)
+nms_select_kernel(float *__restrict__ out, int H, int W, int keep_top_k, const uint2 *__restrict__ survivors,
+                  const int *__restrict__ surv_count, int cap, uint32_t *__restrict__ bitmaps, int words,
+                  int64_t *__restrict__ keypoints, float *__restrict__ kp_scores, int32_t *__restrict__ kp_counts,
+                  int kp_cap) {
+    __shared__ int hist[256];
+    __shared__ int warp_sums[32];
+    __shared__ unsigned long long prefix_s;
+    __shared__ int remaining_s;
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int n = surv_count[b];
+    const uint2 *surv = survivors + (size_t)b * cap;
+    float *img = out + (size_t)b * H * W;
+    const bool want_kp = keypoints != nullptr || kp_counts != nullptr;
+    uint32_t *bitmap = bitmaps ? bitmaps + (size_t)b * words : nullptr;
+
+    // key = (~score_bits, index): ascending key <=> descending score, then ascending index.
+    // positive floats order like their bit patterns.
+    unsigned long long kth = ~0ull;  // keep everything with key <= kth
+    if (keep_top_k > 0 && n > keep_top_k) {
+        // MSB-first radix select of the keep_top_k-th smallest key, 8 bits per pass
+        if (tid == 0) { prefix_s = 0; remaining_s = keep_top_k; }
+        for (int pass = 7; pass >= 0; --pass) {
+            if (tid < 256) hist[tid] = 0;
+            __syncthreads();
+            const unsigned long long prefix = prefix_s;
+            const int shift = pass * 8;
+            for (int i = tid; i < n; i += blockDim.x) {
+                const uint2 e = surv[i];
+                const unsigned long long key = ((unsigned long long)(~e.y) << 32) | e.x;
+                if (pass == 7 || (key >> (shift + 8)) == (prefix >> (shift + 8)))
+                    atomicAdd(&hist[(int)((key >> shift) & 0xff)], 1);
+            }
+            __syncthreads();
+            if (tid == 0) {
+                int rem = remaining_s, d = 0;
+                for (; d < 256; ++d) {
+                    if (hist[d] >= rem) break;
+                    rem -= hist[d];
+                }
+                prefix_s = prefix | ((unsigned long long)d << shift);
+                remaining_s = rem;
+            }
+            __syncthreads();
+        }
+        kth = prefix_s;
+    }
+    if (want_kp) {
+        for (int w = tid; w < words; w += blockDim.x) bitmap[w] = 0;
+        __syncthreads();
+    }
+    for (int i = tid; i < n; i += blockDim.x) {
+        const uint2 e = surv[i];
+        const unsigned long long key = ((unsigned long long)(~e.y) << 32) | e.x;
+        if (key <= kth) {
+            if (want_kp) atomicOr(&bitmap[e.x >> 5], 1u << (e.x & 31));
+        } else {
+            img[e.x] = 0.f;  // cut by top-k (utils.py:109-116)
+        }
+    }
+    if (!want_kp) return;
+    __syncthreads();
+    emit_from_bitmap(bitmap, words, W, img, keypoints ? keypoints + (size_t)b * kp_cap * 2 : nullptr,
+                     kp_scores ? kp_scores + (size_t)b * kp_cap : nullptr, kp_counts ? kp_counts + b : nullptr,
+                     kp_cap, warp_sums);
+}
+
+// ---- row 4b: torch.nonzero((p > thr).float() [* mask]) ----
+__global__ void threshold_bitmap_kernel(const float *__restrict__ prob, const uint8_t *__restrict__ mask, int HW,
+                                        float thr, uint32_t *__restrict__ bitmaps, int words) {
+    const int b = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;  // blockDim.x is a multiple of 32
+    bool on = false;
+    if (i < HW) {
+        const float p = prob[(size_t)b * HW + i];
+        // ((p > thr).float() * mask) != 0
+        on = p > thr && (mask == nullptr || mask[(size_t)b * HW + i] != 0);
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, on);
+    if ((threadIdx.x & 31) == 0 && (i >> 5) < words) bitmaps[(size_t)b * words + (i >> 5)] = m;
+}
+
+__global__ void __launch_bounds__(1024)
+emit_keypoints_kernel(const float *__restrict__ prob, int H, int W, const uint32_t *__restrict__ bitmaps, int words,
+                      int64_t *__restrict__ keypoints, float *__restrict__ kp_scores, int32_t *__restrict__ kp_counts,
+                      int kp_cap) {
+    __shared__ int warp_sums[32];
+    const int b = blockIdx.x;
+    emit_from_bitmap(bitmaps + (size_t)b * words, words, W, prob + (size_t)b * H * W,
+                     keypoints ? keypoints + (size_t)b * kp_cap * 2 : nullptr,
+                     kp_scores ? kp_scores + (size_t)b * kp_cap : nullptr, kp_counts ? kp_counts + b : nullptr, kp_cap,
+                     warp_sums);
+}
+
+// torchvision's CPU nms test `inter / (area_i + area_j - inter) > iou` in fp32 with the quotient
+// compared against the double threshold, for two size x size boxes at offset (dy,dx).
+static bool footprint_hit(double size, double iou, int dy, int dx) {
+    const float half = (float)(size * 0.5);
+    const float a1 = 0.f - half, a2 = 0.f + half;
+    const float area = (a2 - a1) * (a2 - a1);
+    const float by1 = (float)dy - half, by2 = (float)dy + half;
+    const float bx1 = (float)dx - half, bx2 = (float)dx + half;
+    const float yy1 = a1 > by1 ? a1 : by1, xx1 = a1 > bx1 ? a1 : bx1;
+    const float yy2 = a2 < by2 ? a2 : by2, xx2 = a2 < bx2 ? a2 : bx2;
+    float w = yy2 - yy1; if (w < 0.f) w = 0.f;
+    float h = xx2 - xx1; if (h < 0.f) h = 0.f;
+    const float inter = w * h;
+    const float ovr = inter / (area + area - inter);
+    return (double)ovr > iou;
+}
+
+struct NmsLayout {
+    int cap, words;
+    size_t survivors, worklist, counts, bitmaps, total;
+    NmsLayout(int B, int H, int W) {
+        cap = H * W;
+        words = (H * W + 31) / 32;
+        size_t off = 0;
+        counts = off;    off = align_up(off + sizeof(int) * 2 * (size_t)B, 256);
+        survivors = off; off = align_up(off + sizeof(uint2) * (size_t)B * cap, 256);
+        worklist = off;  off = align_up(off + sizeof(uint32_t) * (size_t)B * cap, 256);
+        bitmaps = off;   off = align_up(off + sizeof(uint32_t) * (size_t)B * words, 256);
+        total = off;
+    }
+};
+
+template <int TH, int TW, int E>
+static int launch_tile(const float *prob, float *out, int B, int H, int W, float thr, const NmsFootprint &fp,
+                       uint2 *surv, int *surv_count, uint32_t *work, int *work_count, int cap, bool vec,
+                       cudaStream_t s) {
+    constexpr int EH = TH + 2 * E, EW = TW + 2 * E;
+    constexpr size_t smem = (size_t)EH * EW * (sizeof(float) + sizeof(uint16_t));
+    dim3 grid((W + TW - 1) / TW, (H + TH - 1) / TH, B);
+    if (vec) {
+        auto k = nms_tile_kernel<TH, TW, E, true>;
+        MP_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<grid, NMS_THREADS, smem, s>>>(prob, out, H, W, thr, fp, surv, surv_count, work, work_count, cap);
+    } else {
+        auto k = nms_tile_kernel<TH, TW, E, false>;
+        MP_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<grid, NMS_THREADS, smem, s>>>(prob, out, H, W, thr, fp, surv, surv_count, work, work_count, cap);
+    }
+    MP_LAUNCH_OK();
+    return MP_OK;
+}
+
+}  // namespace mp
+
+extern "C" size_t mp_box_nms_workspace_bytes(int B, int H, int W) {
+    if (B <= 0 || H <= 0 || W <= 0) return 256;
+    return mp::NmsLayout(B, H, W).total;
+}
+
+extern "C" int mp_box_nms_f32(const float *prob, int B, int H, int W, double size, double min_prob,
+                              double iou, int keep_top_k, float *prob_nms, int64_t *keypoints,
+                              float *kp_scores, int32_t *kp_counts, int kp_cap, void *workspace,
+                              size_t workspace_bytes, mp_stream_t stream) {
+    using namespace mp;
+    MP_CHECK_ARG(B >= 0 && H > 0 && W > 0, "mp_box_nms_f32: bad shape B=%d H=%d W=%d", B, H, W);
+    MP_CHECK_ARG((long long)H * W < (1ll << 31), "mp_box_nms_f32: image too large");
+    MP_CHECK_ARG(size > 0 && iou >= 0, "mp_box_nms_f32: size and iou must be positive");
+    MP_CHECK_ARG(kp_cap >= 0 && keep_top_k >= 0, "mp_box_nms_f32: negative capacity / top-k");
+    if (!(min_prob >= 0.0)) {
+        set_error("mp_box_nms_f32: min_prob=%g < 0 is not supported (see multipoint_b200.h)", min_prob);
+        return MP_ERR_UNSUPPORTED;
+    }
+    if (B == 0) return MP_OK;
+    MP_CHECK_ARG(prob && prob_nms, "mp_box_nms_f32: null pointer");
+    MP_CHECK_ARG(keypoints == nullptr || kp_counts != nullptr, "mp_box_nms_f32: keypoints need kp_counts");
+
+    // footprint: reach and translation invariance
+    const float half = (float)(size * 0.5);
+    if (half * 2048.f != floorf(half * 2048.f) || H > 8192 || W > 8192) {
+        set_error("mp_box_nms_f32: size=%g is not a multiple of 1/1024 (or image > 8192): the fp32 IoU "
+                  "of the reference is then position dependent; unsupported", size);
+        return MP_ERR_UNSUPPORTED;
+    }
+    NmsFootprint fp;
+    memset(&fp, 0, sizeof(fp));
+    const int Rmax = (int)ceil(size);
+    int R = 0;
+    for (int dy = -Rmax; dy <= Rmax; ++dy)
+        for (int dx = -Rmax; dx <= Rmax; ++dx)
+            if ((dy || dx) && footprint_hit(size, iou, dy, dx)) R = max(R, max(abs(dy), abs(dx)));
+    if (R > 15) {
+        set_error("mp_box_nms_f32: box size %g reaches %d px; at most 15 supported", size, R);
+        return MP_ERR_UNSUPPORTED;
+    }
+    fp.R = R;
+    for (int dy = -R; dy <= R; ++dy)
+        for (int dx = -R; dx <= R; ++dx)
+            if ((dy || dx) && footprint_hit(size, iou, dy, dx)) fp.rows[dy + R] |= 1u << (dx + R);
+
+    const NmsLayout L(B, H, W);
+    if (workspace == nullptr || workspace_bytes < L.total) {
+        set_error("mp_box_nms_f32: workspace %zu B < required %zu B", workspace_bytes, L.total);
+        return MP_ERR_WORKSPACE;
+    }
+    char *ws = (char *)workspace;
+    int *counts = (int *)(ws + L.counts);
+    int *surv_count = counts, *work_count = counts + B;
+    uint2 *surv = (uint2 *)(ws + L.survivors);
+    uint32_t *work = (uint32_t *)(ws + L.worklist);
+    uint32_t *bitmaps = (uint32_t *)(ws + L.bitmaps);
+    cudaStream_t s = (cudaStream_t)stream;
+    MP_CUDA_OK(cudaMemsetAsync(counts, 0, sizeof(int) * 2 * (size_t)B, s));
+
+    const float thr = (float)min_prob;
+    const bool vec = (W % 4 == 0) && (((uintptr_t)prob & 15) == 0) && (((uintptr_t)prob_nms & 15) == 0);
+    int rc;
+    if (R <= 8)
+        rc = launch_tile<32, 128, 8>(prob, prob_nms, B, H, W, thr, fp, surv, surv_count, work, work_count, L.cap, vec, s);
+    else
+        rc = launch_tile<32, 128, 16>(prob, prob_nms, B, H, W, thr, fp, surv, surv_count, work, work_count, L.cap, vec, s);
+    if (rc != MP_OK) return rc;
+
+    nms_fixup_kernel<<<B, 1024, 0, s>>>(prob_nms, H, W, fp, surv, surv_count, work, work_count, L.cap);
+    MP_LAUNCH_OK();
+
+    if (keep_top_k > 0 || keypoints != nullptr || kp_counts != nullptr) {
+        nms_select_kernel<<<B, 1024, 0, s>>>(prob_nms, H, W, keep_top_k, surv, surv_count, L.cap, bitmaps, L.words,
+                                             keypoints, kp_scores, kp_counts, kp_cap);
+        MP_LAUNCH_OK();
+    }
+    return MP_OK;
+}
+
+extern "C" size_t mp_extract_keypoints_workspace_bytes(int B, int H, int W) {
+    if (B <= 0 || H <= 0 || W <= 0) return 256;
+    return mp::align_up(sizeof(uint32_t) * (size_t)B * (((size_t)H * W + 31) / 32), 256);
+}
+
+extern "C" int mp_extract_keypoints_f32(const float *prob, const uint8_t *mask, int B, int H, int W,
+                                        double threshold, int64_t *keypoints, float *kp_scores,
+                                        int32_t *kp_counts, int kp_cap, void *workspace,
+                                        size_t workspace_bytes, mp_stream_t stream) {
+    using namespace mp;
+    MP_CHECK_ARG(B >= 0 && H > 0 && W > 0 && kp_cap >= 0, "mp_extract_keypoints_f32: bad shape");
+    MP_CHECK_ARG((long long)H * W < (1ll << 31), "mp_extract_keypoints_f32: image too large");
+    if (B == 0) return MP_OK;
+    MP_CHECK_ARG(prob && kp_counts, "mp_extract_keypoints_f32: null pointer");
+    const int HW = H * W, words = (HW + 31) / 32;
+    const size_t need = mp_extract_keypoints_workspace_bytes(B, H, W);
+    if (workspace == nullptr || workspace_bytes < need) {
+        set_error("mp_extract_keypoints_f32: workspace %zu B < required %zu B", workspace_bytes, need);
+        return MP_ERR_WORKSPACE;
+    }
+    uint32_t *bitmaps = (uint32_t *)workspace;
+    cudaStream_t s = (cudaStream_t)stream;
+    dim3 grid((HW + 255) / 256, B);
+    threshold_bitmap_kernel<<<grid, 256, 0, s>>>(prob, mask, HW, (float)threshold, bitmaps, words);
+    MP_LAUNCH_OK();
+    emit_keypoints_kernel<<<B, 1024, 0, s>>>(prob, H, W, bitmaps, words, keypoints, kp_scores, kp_counts, kp_cap);
+    MP_LAUNCH_OK();
+    return MP_OK;
+}

@@ -1,0 +1,573 @@
+// Rows 6-8 of the hot path: utils.get_matches (multipoint/utils/matching.py:4-99):
+// cv2.BFMatcher(NORM_L2, crossCheck) (:7,31), NNMatcher (:35-72), the knn ratio test (:21-28)
+// and ThresholdMatcher (:74-99).  The reference copies both descriptor sets to the host and runs
+// OpenCV / numpy there; here the whole matcher stays on the device.
+//
+// Pipeline (per call, P independent image pairs):
+//   prep      row norms (L2 metric) and the largest norm per set (error bound), split of the
+//             fp32 descriptors into bf16 hi/mid planes for the tensor path
+//   top-2     for every row the best and second-best similarity key over the other set:
+//             MP_ALGO_TENSOR -> match_tc.cu (tcgen05 split-bf16 GEMM, fused arg-top-2 epilogue)
+//             MP_ALGO_SIMT   -> fp32 CUDA-core tiles below (device-side reference)
+//             key = a.b (NN metric) or a.b - |b|^2/2 (L2 metric: argmin |a-b|^2 over b)
+//   flag      rows whose top-2 margin is below twice the error bound of the approximate key
+//   recheck   flagged rows recomputed over the whole other set in fp64 -> the index is the exact
+//             argmin with ties to the lowest index, as np.argmin / OpenCV's strict '<' scan give
+//   select    mutual / threshold / ratio test and ordered compaction into (query, train, dist);
+//             dist is recomputed per kept pair (fp64 accumulate, rounded once to fp32) in the
+//             reference's own formulation.
+#include <math.h>
+
+#include "match_internal.cuh"
+
+namespace mp {
+
+// ------------------------------------------------------------------ prep
+// One warp per descriptor row: squared norm, per-(pair,side) max norm, optional bf16 split.
+__global__ void __launch_bounds__(256)
+match_prep_kernel(const float *__restrict__ d, const int32_t *__restrict__ counts, int N, int D, int P,
+                  float *__restrict__ norms, unsigned *__restrict__ max_norm_bits,
+                  __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ mid) {
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= (long long)P * N) return;
+    const int p = (int)(row / N), i = (int)(row - (long long)p * N);
+    const bool valid = counts == nullptr || i < counts[p];
+    const float *src = d + (size_t)row * D;
+    float ss = 0.f;
+    for (int c = lane; c < D; c += 32) {
+        const float v = valid ? src[c] : 0.f;
+        ss += v * v;
+        if (hi != nullptr) {
+            const __nv_bfloat16 h = __float2bfloat16_rn(v);
+            const __nv_bfloat16 m = __float2bfloat16_rn(v - __bfloat162float(h));
+            hi[(size_t)row * D + c] = h;
+            mid[(size_t)row * D + c] = m;
+        }
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, s);
+    if (lane == 0) {
+        norms[row] = ss;
+        if (valid) atomicMax(max_norm_bits + p, __float_as_uint(sqrtf(ss)));
+    }
+}
+
+// ------------------------------------------------------------------ SIMT top-2
+// 128 rows per CTA (one per thread), 32 columns of the other set per step, K chunks of 16
+// through shared memory.  Columns are visited in ascending order with strict '>' updates, so
+// equal keys resolve to the lowest index.
+constexpr int ST_ROWS = 128, ST_COLS = 32, ST_K = 16;
+
+__global__ void __launch_bounds__(ST_ROWS)
+match_top2_simt_kernel(const float *__restrict__ a, const int32_t *__restrict__ na, int NA,
+                       const float *__restrict__ b, const int32_t *__restrict__ nb, int NB, int D,
+                       const float *__restrict__ norms_b, int use_bias, Top2 *__restrict__ top) {
+    __shared__ float As[ST_ROWS][ST_K + 1];
+    __shared__ float Bs[ST_COLS][ST_K + 1];
+    const int p = blockIdx.y, tid = threadIdx.x;
+    const int row0 = blockIdx.x * ST_ROWS, row = row0 + tid;
+    const int n_a = na ? min(na[p], NA) : NA, n_b = nb ? min(nb[p], NB) : NB;
+    if (row0 >= n_a) {  // whole CTA beyond this pair's valid rows: empty results
+        if (row < NA) {
+            Top2 e;
+            e.best = -INFINITY; e.second = -INFINITY; e.best_idx = -1; e.second_idx = -1;
+            top[(size_t)p * NA + row] = e;
+        }
+        return;
+    }
+    const float *ap = a + (size_t)p * NA * D;
+    const float *bp = b + (size_t)p * NB * D;
+    Top2 t;
+    t.best = -INFINITY; t.second = -INFINITY; t.best_idx = -1; t.second_idx = -1;
+    for (int c0 = 0; c0 < n_b; c0 += ST_COLS) {
+        float acc[ST_COLS];
+#pragma unroll
+        for (int j = 0; j < ST_COLS; ++j) acc[j] = 0.f;
+        for (int k0 = 0; k0 < D; k0 += ST_K) {
+            __syncthreads();
+            for (int e = tid; e < ST_ROWS * ST_K; e += ST_ROWS) {
+                const int r = e / ST_K, k = e - r * ST_K;
+                As[r][k] = (row0 + r < n_a && k0 + k < D) ? ap[(size_t)(row0 + r) * D + k0 + k] : 0.f;
+            }
+            for (int e = tid; e < ST_COLS * ST_K; e += ST_ROWS) {
+                const int c = e / ST_K, k = e - c * ST_K;
+                Bs[c][k] = (c0 + c < n_b && k0 + k < D) ? bp[(size_t)(c0 + c) * D + k0 + k] : 0.f;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < ST_K; ++k) {
+                const float av = As[tid][k];
+#pragma unroll
+                for (int j = 0; j < ST_COLS; ++j) acc[j] = fmaf(av, Bs[j][k], acc[j]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < ST_COLS; ++j) {
+            const int col = c0 + j;
+            if (col >= n_b) break;
+            float key = acc[j];
+            if (use_bias) key -= 0.5f * norms_b[(size_t)p * NB + col];
+            top2_update(t, key, col);
+        }
+    }
+    if (row < NA) {
+        if (row >= n_a) { t.best = -INFINITY; t.second = -INFINITY; t.best_idx = -1; t.second_idx = -1; }
+        top[(size_t)p * NA + row] = t;
+    }
+}
+
+// ------------------------------------------------------------------ flag near-ties
+__global__ void match_flag_kernel(const Top2 *__restrict__ top, int N, int P, const unsigned *__restrict__ max_a,
+                                  const unsigned *__restrict__ max_b, int metric, float eps_rel, int side,
+                                  int32_t *__restrict__ idx_out, uint2 *__restrict__ flagged, int *__restrict__ n_flagged) {
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= (long long)P * N) return;
+    const int p = (int)(g / N);
+    const Top2 t = top[g];
+    idx_out[g] = t.best_idx;
+    if (t.best_idx < 0) return;
+    const float ma = __uint_as_float(max_a[p]), mb = __uint_as_float(max_b[p]);
+    const float eps = eps_rel * fmaxf(ma * mb, 1e-30f);
+    bool flag = (t.second_idx >= 0) && !(t.best - t.second >= 2.f * eps);  // also catches NaN keys
+    if (metric == MP_METRIC_NN && t.best >= 1.f - eps && t.second_idx >= 0) flag = true;  // clip(.,-1,1) ties
+    if (flag) flagged[atomicAdd(n_flagged, 1)] = make_uint2((uint32_t)(p * 2 + side), (uint32_t)(g - (long long)p * N));
+}
+
+// ------------------------------------------------------------------ exact recheck
+// One CTA per flagged row: fp64 key against every row of the other set; first minimum wins.
+//   NN: key = -clip(a.b, -1, 1)      L2: key = sum (a-b)^2       (monotone in the distance)
+__global__ void __launch_bounds__(256)
+match_recheck_kernel(const float *__restrict__ d1, const int32_t *__restrict__ n1, int N1,
+                     const float *__restrict__ d2, const int32_t *__restrict__ n2, int N2, int D, int metric,
+                     const uint2 *__restrict__ flagged, const int *__restrict__ n_flagged,
+                     int32_t *__restrict__ idx12, int32_t *__restrict__ idx21) {
+    extern __shared__ double arow[];  // [D]
+    __shared__ double red_key[256];
+    __shared__ int red_idx[256];
+    const int total = *n_flagged;
+    for (int item = blockIdx.x; item < total; item += gridDim.x) {
+        const uint2 f = flagged[item];
+        const int p = (int)(f.x >> 1), side = (int)(f.x & 1), row = (int)f.y;
+        const float *a = side == 0 ? d1 + ((size_t)p * N1 + row) * D : d2 + ((size_t)p * N2 + row) * D;
+        const float *b = side == 0 ? d2 + (size_t)p * N2 * D : d1 + (size_t)p * N1 * D;
+        const int nb = side == 0 ? (n2 ? min(n2[p], N2) : N2) : (n1 ? min(n1[p], N1) : N1);
+        __syncthreads();
+        for (int c = threadIdx.x; c < D; c += blockDim.x) arow[c] = (double)a[c];
+        __syncthreads();
+        double best = INFINITY;
+        int bidx = 0x7fffffff;
+        for (int j = threadIdx.x; j < nb; j += blockDim.x) {
+            const float *bj = b + (size_t)j * D;
+            double key;
+            if (metric == MP_METRIC_NN) {
+                double dot = 0.0;
+                for (int c = 0; c < D; ++c) dot += arow[c] * (double)bj[c];
+                key = -fmin(1.0, fmax(-1.0, dot));
+            } else {
+                double s = 0.0;
+                for (int c = 0; c < D; ++c) { const double df = arow[c] - (double)bj[c]; s += df * df; }
+                key = s;
+            }
+            if (key < best) { best = key; bidx = j; }  // ascending j per thread: first minimum
+        }
+        red_key[threadIdx.x] = best;
+        red_idx[threadIdx.x] = bidx;
+        __syncthreads();
+        for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+            if (threadIdx.x < s) {
+                const double ok = red_key[threadIdx.x + s];
+                const int oi = red_idx[threadIdx.x + s];
+                if (ok < red_key[threadIdx.x] || (ok == red_key[threadIdx.x] && oi < red_idx[threadIdx.x])) {
+                    red_key[threadIdx.x] = ok;
+                    red_idx[threadIdx.x] = oi;
+                }
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            int32_t *dst = side == 0 ? idx12 + (size_t)p * N1 : idx21 + (size_t)p * N2;
+            dst[row] = red_idx[0] == 0x7fffffff ? -1 : red_idx[0];
+        }
+    }
+}
+
+// ------------------------------------------------------------------ outputs of mp_nearest_f32
+__global__ void match_export_kernel(const Top2 *__restrict__ top, const float *__restrict__ norms_other, int N, int NO,
+                                    int P, int use_bias, float *__restrict__ best, float *__restrict__ second) {
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= (long long)P * N) return;
+    const int p = (int)(g / N);
+    const Top2 t = top[g];
+    // undo the L2 bias so the caller sees plain similarities a.b
+    float b = t.best, s = t.second;
+    if (use_bias) {
+        if (t.best_idx >= 0) b += 0.5f * norms_other[(size_t)p * NO + t.best_idx];
+        if (t.second_idx >= 0) s += 0.5f * norms_other[(size_t)p * NO + t.second_idx];
+    }
+    if (best) best[g] = b;
+    if (second) second[g] = s;
+}
+
+// ------------------------------------------------------------------ select
+// the reference's distance for one pair, fp64 accumulate, rounded once to fp32
+__device__ __forceinline__ float pair_distance(const float *a, const float *b, int D, int metric, int lane) {
+    double acc = 0.0;
+    if (metric == MP_METRIC_NN) {
+        for (int c = lane; c < D; c += 32) acc += (double)a[c] * (double)b[c];
+    } else {
+        for (int c = lane; c < D; c += 32) { const double df = (double)a[c] - (double)b[c]; acc += df * df; }
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+    if (metric == MP_METRIC_NN) {
+        float dot = (float)acc;
+        dot = fminf(1.f, fmaxf(-1.f, dot));
+        return sqrtf(2.f - 2.f * dot);  // matching.py:51
+    }
+    return sqrtf((float)acc);
+}
+
+// one warp per query row: decide keep, compute the distance
+__global__ void __launch_bounds__(256)
+match_decide_kernel(const float *__restrict__ d1, const int32_t *__restrict__ n1, int N1,
+                    const float *__restrict__ d2, int N2, int P, int D, int metric, int kind, int cross_check,
+                    float threshold, float ratio, const int32_t *__restrict__ idx12, const int32_t *__restrict__ idx21,
+                    const Top2 *__restrict__ top12, int32_t *__restrict__ train_tmp, float *__restrict__ dist_tmp) {
+    const int lane = threadIdx.x & 31;
+    const long long g = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (g >= (long long)P * N1) return;
+    const int p = (int)(g / N1), i = (int)(g - (long long)p * N1);
+    const int n_a = n1 ? min(n1[p], N1) : N1;
+    int j = -1;
+    float dist = 0.f;
+    if (i < n_a) {
+        j = idx12[g];
+        if (j >= 0) {
+            const float *a = d1 + (size_t)g * D;
+            dist = pair_distance(a, d2 + ((size_t)p * N2 + j) * D, D, metric, lane);
+            if (kind == MP_MATCH_MUTUAL) {
+                if (cross_check && idx21[(size_t)p * N2 + j] != i) j = -1;
+                if (threshold >= 0.f && !(dist < threshold)) j = -1;
+            } else {
+                // knnMatch(k=2) + Lowe ratio (matching.py:21-28); needs a second neighbour
+                const Top2 t = top12[g];
+                int j2 = (t.best_idx == j) ? t.second_idx : t.best_idx;
+                if (j2 < 0) {
+                    j = -1;
+                } else {
+                    const float dist2 = pair_distance(a, d2 + ((size_t)p * N2 + j2) * D, D, metric, lane);
+                    if (!(dist < ratio * dist2)) j = -1;
+                }
+            }
+        }
+    }
+    if (lane == 0) {
+        train_tmp[g] = j;
+        dist_tmp[g] = dist;
+    }
+}
+
+// one CTA per pair: ordered compaction (ascending query index)
+__global__ void __launch_bounds__(1024)
+match_compact_kernel(const int32_t *__restrict__ train_tmp, const float *__restrict__ dist_tmp, int N1,
+                     int32_t *__restrict__ query, int32_t *__restrict__ train, float *__restrict__ dist,
+                     int32_t *__restrict__ counts) {
+    __shared__ int warp_sums[32];
+    __shared__ int running;
+    const int p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) running = 0;
+    __syncthreads();
+    for (int i0 = 0; i0 < N1; i0 += 1024) {
+        const int i = i0 + tid;
+        const int j = i < N1 ? train_tmp[(size_t)p * N1 + i] : -1;
+        const int keep = j >= 0;
+        int inc = keep;
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, inc, s);
+            if (lane >= s) inc += t;
+        }
+        if (lane == 31) warp_sums[warp] = inc;
+        __syncthreads();
+        int base = running;
+        for (int w = 0; w < warp; ++w) base += warp_sums[w];
+        if (keep) {
+            const size_t o = (size_t)p * N1 + base + inc - 1;
+            query[o] = i;
+            train[o] = j;
+            dist[o] = dist_tmp[(size_t)p * N1 + i];
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int tot = 0;
+            for (int w = 0; w < 32; ++w) tot += warp_sums[w];
+            running += tot;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) counts[p] = running;
+}
+
+// ------------------------------------------------------------------ ThresholdMatcher
+// fp32 tiles like the SIMT top-2, two passes: count per row, then fill in row-major order.
+__global__ void __launch_bounds__(256)
+threshold_rows_kernel(const float *__restrict__ d1, int N1, const float *__restrict__ d2, int N2, int D,
+                      float threshold, const long long *__restrict__ row_offsets, long long *__restrict__ row_counts,
+                      int32_t *__restrict__ query, int32_t *__restrict__ train, float *__restrict__ dist, long long cap) {
+    // one warp per query row; lanes stride over train rows; ballot keeps row-major order
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (i >= N1) return;
+    const float *a = d1 + (size_t)i * D;
+    long long n = 0;
+    const long long base = row_offsets ? row_offsets[i] : 0;
+    for (int j0 = 0; j0 < N2; j0 += 32) {
+        const int j = j0 + lane;
+        float dv = INFINITY;
+        if (j < N2) {
+            const float *b = d2 + (size_t)j * D;
+            double acc = 0.0;
+            for (int c = 0; c < D; ++c) acc += (double)a[c] * (double)b[c];
+            float dot = fminf(1.f, fmaxf(-1.f, (float)acc));
+            dv = sqrtf(2.f - 2.f * dot);
+        }
+        const bool hit = dv < threshold;
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (row_offsets && hit) {
+            const long long o = base + n + __popc(m & ((1u << lane) - 1));
+            if (o < cap) { query[o] = i; train[o] = j; dist[o] = dv; }
+        }
+        n += __popc(m);
+    }
+    if (!row_offsets && lane == 0) row_counts[i] = n;
+}
+
+__global__ void __launch_bounds__(1024)
+exclusive_scan_ll_kernel(const long long *__restrict__ in, long long *__restrict__ out, int n, long long *__restrict__ total) {
+    __shared__ long long warp_sums[32];
+    __shared__ long long running;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) running = 0;
+    __syncthreads();
+    for (int i0 = 0; i0 < n; i0 += 1024) {
+        const int i = i0 + tid;
+        const long long v = i < n ? in[i] : 0;
+        long long inc = v;
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1) {
+            const long long t = __shfl_up_sync(0xffffffffu, inc, s);
+            if (lane >= s) inc += t;
+        }
+        if (lane == 31) warp_sums[warp] = inc;
+        __syncthreads();
+        long long base = running;
+        for (int w = 0; w < warp; ++w) base += warp_sums[w];
+        if (i < n) out[i] = base + inc - v;
+        __syncthreads();
+        if (tid == 0) {
+            long long tot = 0;
+            for (int w = 0; w < 32; ++w) tot += warp_sums[w];
+            running += tot;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) *total = running;
+}
+
+// ------------------------------------------------------------------ host orchestration
+MatchLayout::MatchLayout(int P, int N1, int N2, int D) {
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+    const size_t r1 = (size_t)P * N1, r2 = (size_t)P * N2;
+    scalars = take(sizeof(unsigned) * (2 * (size_t)P + 4));
+    norms1 = take(sizeof(float) * r1);
+    norms2 = take(sizeof(float) * r2);
+    top12 = take(sizeof(Top2) * r1);
+    top21 = take(sizeof(Top2) * r2);
+    idx12 = take(sizeof(int32_t) * r1);
+    idx21 = take(sizeof(int32_t) * r2);
+    flagged = take(sizeof(uint2) * (r1 + r2));
+    train_tmp = take(sizeof(int32_t) * r1);
+    dist_tmp = take(sizeof(float) * r1);
+    hi1 = take(sizeof(__nv_bfloat16) * r1 * D);
+    mid1 = take(sizeof(__nv_bfloat16) * r1 * D);
+    hi2 = take(sizeof(__nv_bfloat16) * r2 * D);
+    mid2 = take(sizeof(__nv_bfloat16) * r2 * D);
+    total = off;
+}
+
+// Fills ws.idx12 / ws.idx21 (exact) and ws.top12 / ws.top21 (approximate keys).
+static int run_nearest(const float *d1, const int32_t *n1, int N1, const float *d2, const int32_t *n2, int N2,
+                       int P, int D, int metric, int algo, const MatchLayout &L, char *ws, cudaStream_t s) {
+    unsigned *scal = (unsigned *)(ws + L.scalars);
+    unsigned *max1 = scal, *max2 = scal + P;
+    int *n_flagged = (int *)(scal + 2 * P);
+    float *norms1 = (float *)(ws + L.norms1), *norms2 = (float *)(ws + L.norms2);
+    Top2 *top12 = (Top2 *)(ws + L.top12), *top21 = (Top2 *)(ws + L.top21);
+    int32_t *idx12 = (int32_t *)(ws + L.idx12), *idx21 = (int32_t *)(ws + L.idx21);
+    uint2 *flagged = (uint2 *)(ws + L.flagged);
+    const bool tensor = algo == MP_ALGO_TENSOR;
+    __nv_bfloat16 *hi1 = tensor ? (__nv_bfloat16 *)(ws + L.hi1) : nullptr, *mid1 = (__nv_bfloat16 *)(ws + L.mid1);
+    __nv_bfloat16 *hi2 = tensor ? (__nv_bfloat16 *)(ws + L.hi2) : nullptr, *mid2 = (__nv_bfloat16 *)(ws + L.mid2);
+    const int use_bias = metric == MP_METRIC_L2;
+
+    MP_CUDA_OK(cudaMemsetAsync(scal, 0, sizeof(unsigned) * (2 * (size_t)P + 4), s));
+    const long long r1 = (long long)P * N1, r2 = (long long)P * N2;
+    match_prep_kernel<<<(unsigned)((r1 + 7) / 8), 256, 0, s>>>(d1, n1, N1, D, P, norms1, max1, hi1, mid1);
+    MP_LAUNCH_OK();
+    match_prep_kernel<<<(unsigned)((r2 + 7) / 8), 256, 0, s>>>(d2, n2, N2, D, P, norms2, max2, hi2, mid2);
+    MP_LAUNCH_OK();
+
+    if (tensor) {
+        int rc = match_top2_tensor(hi1, mid1, n1, N1, hi2, mid2, n2, N2, P, D, norms2, use_bias, top12, s);
+        if (rc != MP_OK) return rc;
+        rc = match_top2_tensor(hi2, mid2, n2, N2, hi1, mid1, n1, N1, P, D, norms1, use_bias, top21, s);
+        if (rc != MP_OK) return rc;
+    } else {
+        dim3 g1((N1 + ST_ROWS - 1) / ST_ROWS, P), g2((N2 + ST_ROWS - 1) / ST_ROWS, P);
+        match_top2_simt_kernel<<<g1, ST_ROWS, 0, s>>>(d1, n1, N1, d2, n2, N2, D, norms2, use_bias, top12);
+        MP_LAUNCH_OK();
+        match_top2_simt_kernel<<<g2, ST_ROWS, 0, s>>>(d2, n2, N2, d1, n1, N1, D, norms1, use_bias, top21);
+        MP_LAUNCH_OK();
+    }
+    const float eps_rel = tensor ? MATCH_EPS_TENSOR : MATCH_EPS_SIMT;
+    match_flag_kernel<<<(unsigned)((r1 + 255) / 256), 256, 0, s>>>(top12, N1, P, max1, max2, metric, eps_rel, 0, idx12, flagged, n_flagged);
+    MP_LAUNCH_OK();
+    match_flag_kernel<<<(unsigned)((r2 + 255) / 256), 256, 0, s>>>(top21, N2, P, max2, max1, metric, eps_rel, 1, idx21, flagged, n_flagged);
+    MP_LAUNCH_OK();
+    match_recheck_kernel<<<num_sms() * 4, 256, sizeof(double) * D, s>>>(d1, n1, N1, d2, n2, N2, D, metric, flagged, n_flagged, idx12, idx21);
+    MP_LAUNCH_OK();
+    return MP_OK;
+}
+
+static int check_match_args(const char *fn, const float *d1, int N1, const float *d2, int N2, int P, int D, int metric,
+                            int algo, void *workspace, size_t workspace_bytes, const MatchLayout &L) {
+    MP_CHECK_ARG(P >= 0 && N1 >= 0 && N2 >= 0 && D > 0, "%s: bad shape P=%d N1=%d N2=%d D=%d", fn, P, N1, N2, D);
+    MP_CHECK_ARG(metric == MP_METRIC_NN || metric == MP_METRIC_L2, "%s: bad metric %d", fn, metric);
+    MP_CHECK_ARG(algo == MP_ALGO_TENSOR || algo == MP_ALGO_SIMT, "%s: bad algo %d", fn, algo);
+    MP_CHECK_ARG(D <= 4096, "%s: D=%d too large", fn, D);
+    if (algo == MP_ALGO_TENSOR && (D % 64 != 0 || D > 256)) {
+        set_error("%s: the tensor path needs D %% 64 == 0 and D <= 256 (got %d); use MP_ALGO_SIMT", fn, D);
+        return MP_ERR_UNSUPPORTED;
+    }
+    if ((long long)P * N1 == 0 || (long long)P * N2 == 0) return MP_OK;
+    MP_CHECK_ARG(d1 && d2, "%s: null descriptor pointer", fn);
+    if (workspace == nullptr || workspace_bytes < L.total) {
+        set_error("%s: workspace %zu B < required %zu B", fn, workspace_bytes, L.total);
+        return MP_ERR_WORKSPACE;
+    }
+    return MP_OK;
+}
+
+__global__ void fill_i32_kernel(int32_t *p, long long n, int32_t v) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+}  // namespace mp
+
+extern "C" size_t mp_match_workspace_bytes(int P, int N1, int N2, int D) {
+    if (P <= 0 || D <= 0) return 256;
+    return mp::MatchLayout(P, N1 > 0 ? N1 : 0, N2 > 0 ? N2 : 0, D).total;
+}
+
+extern "C" int mp_nearest_f32(const float *d1, const int32_t *n1, int N1, const float *d2,
+                              const int32_t *n2, int N2, int P, int D, int metric, int algo,
+                              int32_t *idx12, float *best12, float *second12, int32_t *idx21,
+                              float *best21, float *second21, void *workspace,
+                              size_t workspace_bytes, mp_stream_t stream) {
+    using namespace mp;
+    const MatchLayout L(P > 0 ? P : 0, N1 > 0 ? N1 : 0, N2 > 0 ? N2 : 0, D > 0 ? D : 1);
+    int rc = check_match_args("mp_nearest_f32", d1, N1, d2, N2, P, D, metric, algo, workspace, workspace_bytes, L);
+    if (rc != MP_OK) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    const long long r1 = (long long)P * N1, r2 = (long long)P * N2;
+    if (r1 == 0 || r2 == 0) {  // one side empty: no neighbours
+        if (r1 && idx12) { fill_i32_kernel<<<(unsigned)((r1 + 255) / 256), 256, 0, s>>>(idx12, r1, -1); MP_LAUNCH_OK(); }
+        if (r2 && idx21) { fill_i32_kernel<<<(unsigned)((r2 + 255) / 256), 256, 0, s>>>(idx21, r2, -1); MP_LAUNCH_OK(); }
+        return MP_OK;
+    }
+    char *ws = (char *)workspace;
+    rc = run_nearest(d1, n1, N1, d2, n2, N2, P, D, metric, algo, L, ws, s);
+    if (rc != MP_OK) return rc;
+    if (idx12) MP_CUDA_OK(cudaMemcpyAsync(idx12, ws + L.idx12, sizeof(int32_t) * r1, cudaMemcpyDeviceToDevice, s));
+    if (idx21) MP_CUDA_OK(cudaMemcpyAsync(idx21, ws + L.idx21, sizeof(int32_t) * r2, cudaMemcpyDeviceToDevice, s));
+    const int use_bias = metric == MP_METRIC_L2;
+    if (best12 || second12) {
+        match_export_kernel<<<(unsigned)((r1 + 255) / 256), 256, 0, s>>>((Top2 *)(ws + L.top12), (float *)(ws + L.norms2), N1, N2, P, use_bias, best12, second12);
+        MP_LAUNCH_OK();
+    }
+    if (best21 || second21) {
+        match_export_kernel<<<(unsigned)((r2 + 255) / 256), 256, 0, s>>>((Top2 *)(ws + L.top21), (float *)(ws + L.norms1), N2, N1, P, use_bias, best21, second21);
+        MP_LAUNCH_OK();
+    }
+    return MP_OK;
+}
+
+extern "C" int mp_match_f32(const float *d1, const int32_t *n1, int N1, const float *d2,
+                            const int32_t *n2, int N2, int P, int D, int metric, int algo, int kind,
+                            int cross_check, double threshold, double ratio, int32_t *query,
+                            int32_t *train, float *dist, int32_t *counts, void *workspace,
+                            size_t workspace_bytes, mp_stream_t stream) {
+    using namespace mp;
+    const MatchLayout L(P > 0 ? P : 0, N1 > 0 ? N1 : 0, N2 > 0 ? N2 : 0, D > 0 ? D : 1);
+    int rc = check_match_args("mp_match_f32", d1, N1, d2, N2, P, D, metric, algo, workspace, workspace_bytes, L);
+    if (rc != MP_OK) return rc;
+    MP_CHECK_ARG(kind == MP_MATCH_MUTUAL || kind == MP_MATCH_RATIO, "mp_match_f32: bad kind %d", kind);
+    if (P == 0) return MP_OK;
+    MP_CHECK_ARG(counts != nullptr, "mp_match_f32: counts is required");
+    cudaStream_t s = (cudaStream_t)stream;
+    if ((long long)P * N1 == 0 || (long long)P * N2 == 0) {
+        MP_CUDA_OK(cudaMemsetAsync(counts, 0, sizeof(int32_t) * P, s));
+        return MP_OK;
+    }
+    MP_CHECK_ARG(query && train && dist, "mp_match_f32: null output pointer");
+    char *ws = (char *)workspace;
+    rc = run_nearest(d1, n1, N1, d2, n2, N2, P, D, metric, algo, L, ws, s);
+    if (rc != MP_OK) return rc;
+    const long long r1 = (long long)P * N1;
+    int32_t *train_tmp = (int32_t *)(ws + L.train_tmp);
+    float *dist_tmp = (float *)(ws + L.dist_tmp);
+    match_decide_kernel<<<(unsigned)((r1 + 7) / 8), 256, 0, s>>>(d1, n1, N1, d2, N2, P, D, metric, kind, cross_check,
+                                                               (float)threshold, (float)ratio, (int32_t *)(ws + L.idx12),
+                                                               (int32_t *)(ws + L.idx21), (Top2 *)(ws + L.top12), train_tmp, dist_tmp);
+    MP_LAUNCH_OK();
+    match_compact_kernel<<<P, 1024, 0, s>>>(train_tmp, dist_tmp, N1, query, train, dist, counts);
+    MP_LAUNCH_OK();
+    return MP_OK;
+}
+
+extern "C" int mp_match_threshold_f32(const float *d1, int N1, const float *d2, int N2, int D,
+                                      double threshold, int32_t *query, int32_t *train, float *dist,
+                                      int64_t cap, int64_t *total_host, void *workspace,
+                                      size_t workspace_bytes, mp_stream_t stream) {
+    using namespace mp;
+    MP_CHECK_ARG(N1 >= 0 && N2 >= 0 && D > 0 && cap >= 0, "mp_match_threshold_f32: bad shape");
+    MP_CHECK_ARG(total_host != nullptr, "mp_match_threshold_f32: total_host is required");
+    *total_host = 0;
+    if (N1 == 0 || N2 == 0) return MP_OK;
+    MP_CHECK_ARG(d1 && d2, "mp_match_threshold_f32: null pointer");
+    const size_t need = align_up(sizeof(long long) * (2 * (size_t)N1 + 1), 256);
+    if (workspace == nullptr || workspace_bytes < need) {
+        set_error("mp_match_threshold_f32: workspace %zu B < required %zu B", workspace_bytes, need);
+        return MP_ERR_WORKSPACE;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    long long *row_counts = (long long *)workspace, *row_offsets = row_counts + N1, *total = row_offsets + N1;
+    const unsigned grid = (unsigned)((N1 + 7) / 8);
+    threshold_rows_kernel<<<grid, 256, 0, s>>>(d1, N1, d2, N2, D, (float)threshold, nullptr, row_counts, nullptr, nullptr, nullptr, 0);
+    MP_LAUNCH_OK();
+    exclusive_scan_ll_kernel<<<1, 1024, 0, s>>>(row_counts, row_offsets, N1, total);
+    MP_LAUNCH_OK();
+    if (cap > 0) {
+        MP_CHECK_ARG(query && train && dist, "mp_match_threshold_f32: null output pointer");
+        threshold_rows_kernel<<<grid, 256, 0, s>>>(d1, N1, d2, N2, D, (float)threshold, row_offsets, nullptr, query, train, dist, cap);
+        MP_LAUNCH_OK();
+    }
+    long long t = 0;
+    MP_CUDA_OK(cudaMemcpyAsync(&t, total, sizeof(long long), cudaMemcpyDeviceToHost, s));
+    MP_CUDA_OK(cudaStreamSynchronize(s));
+    *total_host = t;
+    return MP_OK;
+}

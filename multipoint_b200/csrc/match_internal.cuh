@@ -1,0 +1,42 @@
+// Shared between match.cu (orchestration, SIMT path) and match_tc.cu (tcgen05 path).
+#pragma once
+#include <cuda_bf16.h>
+
+#include "mp_common.cuh"
+
+namespace mp {
+
+// best / second-best similarity key of one descriptor over the other set (larger = closer)
+struct __align__(16) Top2 {
+    float best, second;
+    int best_idx, second_idx;
+};
+
+// ascending-index visits + strict '>' => equal keys resolve to the lowest index
+__device__ __forceinline__ void top2_update(Top2 &t, float key, int idx) {
+    if (key > t.best) {
+        t.second = t.best; t.second_idx = t.best_idx;
+        t.best = key; t.best_idx = idx;
+    } else if (key > t.second) {
+        t.second = key; t.second_idx = idx;
+    }
+}
+
+// Bound on |approximate key - exact key| relative to max|a| * max|b| (derivation in DESIGN.md):
+//  tensor: split bf16 (hi*hi + hi*mid + mid*hi) drops <= 3*2^-18 of sum|a_k b_k| (1.2e-5), fp32
+//          accumulation in the tensor core over <= 48 MMAs adds <= ~1e-5  -> 4e-5 with margin
+//  simt  : fp32 FMA chain over D <= 4096 terms                              -> 4e-5 as well
+constexpr float MATCH_EPS_TENSOR = 4e-5f;
+constexpr float MATCH_EPS_SIMT = 4e-5f;
+
+struct MatchLayout {
+    size_t scalars, norms1, norms2, top12, top21, idx12, idx21, flagged, train_tmp, dist_tmp, hi1, mid1, hi2, mid2, total;
+    MatchLayout(int P, int N1, int N2, int D);
+};
+
+// match_tc.cu: rows of A (hi/mid bf16 planes, (P,NA,D)) against rows of B; writes top[(P,NA)].
+int match_top2_tensor(const __nv_bfloat16 *a_hi, const __nv_bfloat16 *a_mid, const int32_t *na, int NA,
+                      const __nv_bfloat16 *b_hi, const __nv_bfloat16 *b_mid, const int32_t *nb, int NB, int P, int D,
+                      const float *norms_b, int use_bias, Top2 *top, cudaStream_t stream);
+
+}  // namespace mp

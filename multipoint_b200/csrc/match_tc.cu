@@ -1,0 +1,347 @@
+// Rows 6-7 of the hot path on the 5th-generation tensor cores: brute-force nearest-neighbour
+// search (cv2.BFMatcher / NNMatcher, multipoint/utils/matching.py:7,31,50-58) as a GEMM whose
+// similarity matrix never leaves the SM.
+//
+//   S = A . B^T  with fp32 descriptors split into bf16 planes a = a_hi + a_mid (+ 2^-18 |a|):
+//   S ~= A_hi.B_hi^T + A_hi.B_mid^T + A_mid.B_hi^T      (three tcgen05.mma passes, fp32 accumulate)
+//   |S~ - S| <= 4e-5 |a||b|  (match_internal.cuh); rows whose top-2 margin is inside that bound are
+//   re-ranked exactly in fp64 by match_recheck_kernel, so the argmax that leaves this file plus
+//   the recheck equals the fp64 argmax with ties to the lowest index.
+//
+// One CTA owns 128 rows of A for one image pair:
+//   - A_hi / A_mid for the whole K = D (<= 256) stay resident in shared memory (TMA, 128B swizzle)
+//   - B_hi / B_mid stream through a 3-4 stage TMA ring in (128 rows x 64 k) blocks
+//   - one elected thread issues tcgen05.mma (M=128, N=128, K=16, kind::f16) into one of four
+//     128-column TMEM accumulators; tcgen05.commit releases the smem stage / publishes the tile
+//   - four epilogue warps read the accumulator with tcgen05.ld (one row per thread) and keep a
+//     running (best, second, indices) per row while the next tile's MMAs run
+// The only global traffic is the bf16 operands (B re-read once per 128-row block, from L2) and
+// 16 B of result per row.
+#include <cuda.h>
+
+#include "match_internal.cuh"
+
+namespace mp {
+
+constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 64;  // BK bf16 = one 128 B swizzle row
+constexpr int TC_ACC_STAGES = 4;                     // 4 x 128 fp32 columns = all 512 TMEM columns
+constexpr int TC_THREADS = 192;                      // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
+constexpr uint32_t TC_TILE_BYTES = TC_BM * TC_BK * 2;  // 16 KB: one (128 x 64) bf16 block
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// UMMA shared-memory descriptor, K-major operand, 128-byte swizzle (cute::UMMA::SmemDescriptor):
+//   [0,14) start address >> 4   [16,30) leading byte offset >> 4 (=1, unused for swizzled K-major)
+//   [32,46) stride byte offset >> 4 (8 rows x 128 B = 1024)      [46,48) version = 1 (sm_100)
+//   [61,64) layout type = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// UMMA instruction descriptor, kind::f16 (cute::UMMA::InstrDescriptor):
+//   [4,6) D format 1 = f32   [7,10) A format 1 = bf16   [10,13) B format 1 = bf16
+//   [15] A major 0 = K   [16] B major 0 = K   [17,23) N >> 3   [24,29) M >> 4
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+template <int KB>
+struct TcSmem {
+    static constexpr int B_STAGES = KB >= 4 ? 3 : 4;
+    static constexpr uint32_t A_BYTES = 2u * KB * TC_TILE_BYTES;
+    static constexpr uint32_t B_STAGE_BYTES = 2u * TC_TILE_BYTES;
+    static constexpr uint32_t B_OFF = A_BYTES;
+    static constexpr uint32_t BAR_OFF = B_OFF + B_STAGES * B_STAGE_BYTES;
+    static constexpr int NUM_BARS = 1 + 2 * B_STAGES + 2 * TC_ACC_STAGES;
+    static constexpr uint32_t TOTAL = BAR_OFF + NUM_BARS * 8 + 16 + 1024;  // + tmem ptr + alignment slack
+};
+
+template <int KB>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+match_top2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_mid,
+                     const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_mid,
+                     const int32_t *__restrict__ na, int NA, const int32_t *__restrict__ nb, int NB,
+                     const float *__restrict__ norms_b, int use_bias, Top2 *__restrict__ top) {
+    using L = TcSmem<KB>;
+    constexpr int S = L::B_STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int p = blockIdx.y, m0 = blockIdx.x * TC_BM;
+    const int n_a = na ? min(na[p], NA) : NA, n_b = nb ? min(nb[p], NB) : NB;
+
+    if (m0 >= n_a || n_b <= 0) {  // nothing to search: empty results (uniform per CTA)
+        for (int r = threadIdx.x; r < TC_BM; r += TC_THREADS)
+            if (m0 + r < NA) {
+                Top2 e;
+                e.best = -INFINITY; e.second = -INFINITY; e.best_idx = -1; e.second_idx = -1;
+                top[(size_t)p * NA + m0 + r] = e;
+            }
+        return;
+    }
+
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // 128B swizzle needs 1024 B alignment
+    const uint32_t smem_a = base, smem_b = base + L::B_OFF, bars = base + L::BAR_OFF;
+    const uint32_t bar_a_full = bars;
+    auto bar_b_full = [&](int s) { return bars + 8u * (1 + s); };
+    auto bar_b_empty = [&](int s) { return bars + 8u * (1 + S + s); };
+    auto bar_acc_full = [&](int t) { return bars + 8u * (1 + 2 * S + t); };
+    auto bar_acc_empty = [&](int t) { return bars + 8u * (1 + 2 * S + TC_ACC_STAGES + t); };
+    const uint32_t tmem_ptr_addr = bars + 8u * L::NUM_BARS;
+    volatile uint32_t *tmem_ptr_gen = reinterpret_cast<volatile uint32_t *>(smem_raw + (tmem_ptr_addr - smem_u32(smem_raw)));
+
+    const int n_tiles = (n_b + TC_BN - 1) / TC_BN;
+
+    if (warp == 0 && lane == 0) {
+        mbar_init(bar_a_full, 1);
+        for (int s = 0; s < S; ++s) { mbar_init(bar_b_full(s), 1); mbar_init(bar_b_empty(s), 1); }
+        for (int t = 0; t < TC_ACC_STAGES; ++t) { mbar_init(bar_acc_full(t), 1); mbar_init(bar_acc_empty(t), 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {  // one warp allocates all 512 TMEM columns (1 CTA per SM: smem-limited)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_gen;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            mbar_expect_tx(bar_a_full, L::A_BYTES);
+            for (int kb = 0; kb < KB; ++kb) {
+                tma_load_3d(smem_a + (0 * KB + kb) * TC_TILE_BYTES, &map_a_hi, bar_a_full, kb * TC_BK, m0, p);
+                tma_load_3d(smem_a + (1 * KB + kb) * TC_TILE_BYTES, &map_a_mid, bar_a_full, kb * TC_BK, m0, p);
+            }
+            int it = 0;
+            for (int nt = 0; nt < n_tiles; ++nt) {
+                for (int kb = 0; kb < KB; ++kb, ++it) {
+                    const int s = it % S;
+                    mbar_wait(bar_b_empty(s), ((it / S) & 1) ^ 1);
+                    mbar_expect_tx(bar_b_full(s), L::B_STAGE_BYTES);
+                    const uint32_t dst = smem_b + s * L::B_STAGE_BYTES;
+                    tma_load_3d(dst, &map_b_hi, bar_b_full(s), kb * TC_BK, nt * TC_BN, p);
+                    tma_load_3d(dst + TC_TILE_BYTES, &map_b_mid, bar_b_full(s), kb * TC_BK, nt * TC_BN, p);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(TC_BM, TC_BN);
+            mbar_wait(bar_a_full, 0);
+            tc_fence_after();
+            int it = 0;
+            for (int nt = 0; nt < n_tiles; ++nt) {
+                const int t = nt % TC_ACC_STAGES;
+                mbar_wait(bar_acc_empty(t), ((nt / TC_ACC_STAGES) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(t * TC_BN);
+                for (int kb = 0; kb < KB; ++kb, ++it) {
+                    const int s = it % S;
+                    mbar_wait(bar_b_full(s), (it / S) & 1);
+                    tc_fence_after();
+                    const uint32_t a_hi = smem_a + (0 * KB + kb) * TC_TILE_BYTES, a_mid = smem_a + (1 * KB + kb) * TC_TILE_BYTES;
+                    const uint32_t b_hi = smem_b + s * L::B_STAGE_BYTES, b_mid = b_hi + TC_TILE_BYTES;
+#pragma unroll
+                    for (int k = 0; k < TC_BK / 16; ++k) {
+                        const uint32_t ko = k * 32;  // 16 bf16 = 32 B inside the 128 B swizzle row
+                        const uint64_t da_hi = umma_desc_sw128(a_hi + ko), da_mid = umma_desc_sw128(a_mid + ko);
+                        const uint64_t db_hi = umma_desc_sw128(b_hi + ko), db_mid = umma_desc_sw128(b_mid + ko);
+                        tc_mma_f16(d_tmem, da_mid, db_hi, idesc, (kb | k) != 0);  // small terms first
+                        tc_mma_f16(d_tmem, da_hi, db_mid, idesc, 1);
+                        tc_mma_f16(d_tmem, da_hi, db_hi, idesc, 1);
+                    }
+                    tc_commit(bar_b_empty(s));  // smem stage free once these MMAs have read it
+                }
+                tc_commit(bar_acc_full(t));  // accumulator complete
+            }
+        }
+    } else {
+        // ===================== epilogue: running arg-top-2 per row =====================
+        const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+        const int row = quarter * 32 + lane;
+        Top2 best;
+        best.best = -INFINITY; best.second = -INFINITY; best.best_idx = -1; best.second_idx = -1;
+        const float *bias = norms_b + (size_t)p * NB;
+        for (int nt = 0; nt < n_tiles; ++nt) {
+            const int t = nt % TC_ACC_STAGES;
+            mbar_wait(bar_acc_full(t), (nt / TC_ACC_STAGES) & 1);
+            tc_fence_after();
+            const int n0 = nt * TC_BN;
+            const bool full_tile = n0 + TC_BN <= n_b;
+#pragma unroll 1
+            for (int c = 0; c < TC_BN / 32; ++c) {
+                float v[32];
+                tc_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(t * TC_BN + c * 32), v);
+                const int col0 = n0 + c * 32;
+                if (use_bias) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (full_tile || col0 + j < n_b) v[j] -= 0.5f * __ldg(bias + col0 + j);
+                }
+                if (full_tile) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) top2_update(best, v[j], col0 + j);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (col0 + j < n_b) top2_update(best, v[j], col0 + j);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_acc_empty(t));
+        }
+        if (m0 + row < NA) {
+            if (m0 + row >= n_a) { best.best = -INFINITY; best.second = -INFINITY; best.best_idx = -1; best.second_idx = -1; }
+            top[(size_t)p * NA + m0 + row] = best;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    }
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+    static PFN_encodeTiled fn = nullptr;
+    if (fn == nullptr) {
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (PFN_encodeTiled)ptr;
+    }
+    return fn;
+}
+
+// (P, N, D) bf16 row-major -> 3-D map, box = 64 k x 128 rows x 1 pair, 128-byte swizzle
+static int make_operand_map(CUtensorMap *map, const __nv_bfloat16 *ptr, int P, int N, int D) {
+    PFN_encodeTiled enc = get_encode_fn();
+    if (enc == nullptr) {
+        set_error("match_top2_tensor: cuTensorMapEncodeTiled not available from the driver");
+        return MP_ERR_CUDA;
+    }
+    cuuint64_t dims[3] = {(cuuint64_t)D, (cuuint64_t)N, (cuuint64_t)P};
+    cuuint64_t strides[2] = {(cuuint64_t)D * 2, (cuuint64_t)N * D * 2};
+    cuuint32_t box[3] = {(cuuint32_t)TC_BK, (cuuint32_t)TC_BM, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void *)ptr, dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("match_top2_tensor: cuTensorMapEncodeTiled failed with CUresult %d (N=%d D=%d P=%d)", (int)r, N, D, P);
+        return MP_ERR_CUDA;
+    }
+    return MP_OK;
+}
+
+template <int KB>
+static int launch_tc(const CUtensorMap &ah, const CUtensorMap &am, const CUtensorMap &bh, const CUtensorMap &bm,
+                     const int32_t *na, int NA, const int32_t *nb, int NB, int P, const float *norms_b, int use_bias,
+                     Top2 *top, cudaStream_t s) {
+    auto k = match_top2_tc_kernel<KB>;
+    MP_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcSmem<KB>::TOTAL));
+    dim3 grid((NA + TC_BM - 1) / TC_BM, P);
+    k<<<grid, TC_THREADS, TcSmem<KB>::TOTAL, s>>>(ah, am, bh, bm, na, NA, nb, NB, norms_b, use_bias, top);
+    MP_LAUNCH_OK();
+    return MP_OK;
+}
+
+int match_top2_tensor(const __nv_bfloat16 *a_hi, const __nv_bfloat16 *a_mid, const int32_t *na, int NA,
+                      const __nv_bfloat16 *b_hi, const __nv_bfloat16 *b_mid, const int32_t *nb, int NB, int P, int D,
+                      const float *norms_b, int use_bias, Top2 *top, cudaStream_t stream) {
+    if (D % 64 != 0 || D > 256 || D <= 0) {
+        set_error("match_top2_tensor: D=%d must be a multiple of 64 and <= 256", D);
+        return MP_ERR_UNSUPPORTED;
+    }
+    CUtensorMap ah, am, bh, bm;
+    int rc;
+    if ((rc = make_operand_map(&ah, a_hi, P, NA, D)) != MP_OK) return rc;
+    if ((rc = make_operand_map(&am, a_mid, P, NA, D)) != MP_OK) return rc;
+    if ((rc = make_operand_map(&bh, b_hi, P, NB, D)) != MP_OK) return rc;
+    if ((rc = make_operand_map(&bm, b_mid, P, NB, D)) != MP_OK) return rc;
+    switch (D / 64) {
+        case 1: return launch_tc<1>(ah, am, bh, bm, na, NA, nb, NB, P, norms_b, use_bias, top, stream);
+        case 2: return launch_tc<2>(ah, am, bh, bm, na, NA, nb, NB, P, norms_b, use_bias, top, stream);
+        case 3: return launch_tc<3>(ah, am, bh, bm, na, NA, nb, NB, P, norms_b, use_bias, top, stream);
+        default: return launch_tc<4>(ah, am, bh, bm, na, NA, nb, NB, P, norms_b, use_bias, top, stream);
+    }
+}
+
+}  // namespace mp

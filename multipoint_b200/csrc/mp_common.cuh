@@ -1,0 +1,89 @@
+// Shared helpers for the multipoint_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "multipoint_b200.h"
+
+namespace mp {
+
+// ---- error reporting across the C ABI: thread-local message, integer status ----
+void set_error(const char *fmt, ...);
+void count_launch(unsigned n = 1);
+
+#define MP_CHECK_ARG(cond, ...)                 \
+    do {                                        \
+        if (!(cond)) {                          \
+            mp::set_error(__VA_ARGS__);         \
+            return MP_ERR_INVALID;              \
+        }                                       \
+    } while (0)
+
+#define MP_CUDA_OK(expr)                                                                   \
+    do {                                                                                   \
+        cudaError_t e__ = (expr);                                                          \
+        if (e__ != cudaSuccess) {                                                          \
+            mp::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e__)); \
+            return MP_ERR_CUDA;                                                            \
+        }                                                                                  \
+    } while (0)
+
+#define MP_LAUNCH_OK()                                                                     \
+    do {                                                                                   \
+        mp::count_launch();                                                                \
+        cudaError_t e__ = cudaGetLastError();                                              \
+        if (e__ != cudaSuccess) {                                                          \
+            mp::set_error("%s:%d: kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(e__)); \
+            return MP_ERR_CUDA;                                                            \
+        }                                                                                  \
+    } while (0)
+
+inline int num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// bump allocator over the caller's workspace
+struct Workspace {
+    char *base;
+    size_t size, off;
+    Workspace(void *p, size_t n) : base((char *)p), size(n), off(0) {}
+    template <typename T>
+    T *take(size_t count) {
+        off = align_up(off, 256);
+        T *r = (T *)(base + off);
+        off += count * sizeof(T);
+        return r;
+    }
+    bool ok() const { return base != nullptr && off <= size; }
+};
+
+// ---- device helpers ----
+__device__ __forceinline__ float4 ld_stream_f4(const float4 *p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float ld_stream_f(const float *p) {
+    float r;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_stream_f4(float4 *p, float4 v) {
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y),
+                 "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+
+}  // namespace mp

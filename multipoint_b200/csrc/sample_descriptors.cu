@@ -1,0 +1,106 @@
+// Row 5 of the hot path: utils.interpolate_descriptors (multipoint/utils/utils.py:159-167).
+// Bilinear sample of the coarse descriptor map at each keypoint fused with the L2 normalisation,
+// instead of the reference's cast / in-place scale / flip / grid_sample / transpose / normalize
+// chain (~8 kernels).
+//
+// The sampling coordinate follows the reference's fp32 operation order exactly:
+//   y_n = y / (H*0.5) - 1            (utils.py:162-163; note H/2, not (H-1)/2)
+//   iy  = ((y_n + 1) / 2) * (Hc - 1) (ATen grid_sampler unnormalize, align_corners=True)
+// zero padding: a corner outside the map contributes 0.
+//
+// HBM-bound gather: one warp per keypoint, lanes across channels.  With the channels-last map
+// (B,Hc,Wc,D) produced by mp_normalize_descriptors_f32 every corner is one contiguous D*4 B row;
+// with NCHW each lane gathers strided words (kept for drop-in use on the reference's layout).
+#include "mp_common.cuh"
+
+namespace mp {
+
+constexpr int SD_WARPS = 8;
+constexpr int SD_MAX_CPL = 16;  // channels per lane held in registers: D <= 512
+
+template <int LAYOUT>
+__global__ void __launch_bounds__(SD_WARPS * 32)
+sample_descriptors_kernel(const int64_t *__restrict__ kp, const int32_t *__restrict__ counts,
+                          const float *__restrict__ desc, float *__restrict__ out, int B, int K, int D,
+                          int Hc, int Wc, float half_h, float half_w) {
+    const int lane = threadIdx.x & 31;
+    const long long item = (long long)blockIdx.x * SD_WARPS + (threadIdx.x >> 5);
+    if (item >= (long long)B * K) return;
+    const int b = (int)(item / K), k = (int)(item - (long long)b * K);
+    float *o = out + (size_t)item * D;
+    const int n = counts ? min(counts[b], K) : K;
+    if (k >= n) {
+        for (int c = lane; c < D; c += 32) o[c] = 0.f;
+        return;
+    }
+    const float y = (float)kp[2 * item], x = (float)kp[2 * item + 1];
+    const float yn = __fsub_rn(__fdiv_rn(y, half_h), 1.0f);
+    const float xn = __fsub_rn(__fdiv_rn(x, half_w), 1.0f);
+    const float iy = __fmul_rn(__fdiv_rn(__fadd_rn(yn, 1.0f), 2.0f), (float)(Hc - 1));
+    const float ix = __fmul_rn(__fdiv_rn(__fadd_rn(xn, 1.0f), 2.0f), (float)(Wc - 1));
+    const float fx = floorf(ix), fy = floorf(iy);
+    const int x0 = (int)fx, y0 = (int)fy, x1 = x0 + 1, y1 = y0 + 1;
+    const float nw = __fmul_rn((float)x1 - ix, (float)y1 - iy);
+    const float ne = __fmul_rn(ix - (float)x0, (float)y1 - iy);
+    const float sw = __fmul_rn((float)x1 - ix, iy - (float)y0);
+    const float se = __fmul_rn(ix - (float)x0, iy - (float)y0);
+    const bool vx0 = x0 >= 0 && x0 < Wc, vx1 = x1 >= 0 && x1 < Wc;
+    const bool vy0 = y0 >= 0 && y0 < Hc, vy1 = y1 >= 0 && y1 < Hc;
+
+    float v[SD_MAX_CPL];
+    float ss = 0.f;
+#pragma unroll
+    for (int j = 0; j < SD_MAX_CPL; ++j) {
+        const int c = lane + 32 * j;
+        float acc = 0.f;
+        if (c < D) {
+            if (LAYOUT == MP_LAYOUT_NHWC) {
+                const float *m = desc + (size_t)b * Hc * Wc * D + c;
+                if (vy0 && vx0) acc = __fadd_rn(acc, __fmul_rn(__ldg(m + ((size_t)y0 * Wc + x0) * D), nw));
+                if (vy0 && vx1) acc = __fadd_rn(acc, __fmul_rn(__ldg(m + ((size_t)y0 * Wc + x1) * D), ne));
+                if (vy1 && vx0) acc = __fadd_rn(acc, __fmul_rn(__ldg(m + ((size_t)y1 * Wc + x0) * D), sw));
+                if (vy1 && vx1) acc = __fadd_rn(acc, __fmul_rn(__ldg(m + ((size_t)y1 * Wc + x1) * D), se));
+            } else {
+                const float *m = desc + ((size_t)b * D + c) * Hc * Wc;
+                if (vy0 && vx0) acc = __fadd_rn(acc, __fmul_rn(__ldg(m + y0 * Wc + x0), nw));
+                if (vy0 && vx1) acc = __fadd_rn(acc, __fmul_rn(__ldg(m + y0 * Wc + x1), ne));
+                if (vy1 && vx0) acc = __fadd_rn(acc, __fmul_rn(__ldg(m + y1 * Wc + x0), sw));
+                if (vy1 && vx1) acc = __fadd_rn(acc, __fmul_rn(__ldg(m + y1 * Wc + x1), se));
+            }
+        }
+        v[j] = acc;
+        ss += acc * acc;
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, s);
+    const float denom = fmaxf(sqrtf(ss), 1e-12f);
+#pragma unroll
+    for (int j = 0; j < SD_MAX_CPL; ++j) {
+        const int c = lane + 32 * j;
+        if (c < D) o[c] = v[j] / denom;
+    }
+}
+
+}  // namespace mp
+
+extern "C" int mp_sample_descriptors_f32(const int64_t *keypoints, const int32_t *kp_counts, int B,
+                                         int K, const float *desc, int D, int Hc, int Wc, int layout,
+                                         int H, int W, float *out, mp_stream_t stream) {
+    MP_CHECK_ARG(B >= 0 && K >= 0 && D > 0 && Hc > 0 && Wc > 0 && H > 0 && W > 0,
+                 "mp_sample_descriptors_f32: bad shape");
+    MP_CHECK_ARG(D <= 32 * mp::SD_MAX_CPL, "mp_sample_descriptors_f32: D=%d > %d unsupported", D, 32 * mp::SD_MAX_CPL);
+    MP_CHECK_ARG(layout == MP_LAYOUT_NCHW || layout == MP_LAYOUT_NHWC, "mp_sample_descriptors_f32: bad layout %d", layout);
+    if ((long long)B * K == 0) return MP_OK;
+    MP_CHECK_ARG(keypoints && desc && out, "mp_sample_descriptors_f32: null pointer");
+    const long long items = (long long)B * K;
+    const unsigned grid = (unsigned)((items + mp::SD_WARPS - 1) / mp::SD_WARPS);
+    const float hh = (float)H * 0.5f, hw = (float)W * 0.5f;
+    if (layout == MP_LAYOUT_NHWC)
+        mp::sample_descriptors_kernel<MP_LAYOUT_NHWC><<<grid, mp::SD_WARPS * 32, 0, (cudaStream_t)stream>>>(
+            keypoints, kp_counts, desc, out, B, K, D, Hc, Wc, hh, hw);
+    else
+        mp::sample_descriptors_kernel<MP_LAYOUT_NCHW><<<grid, mp::SD_WARPS * 32, 0, (cudaStream_t)stream>>>(
+            keypoints, kp_counts, desc, out, B, K, D, Hc, Wc, hh, hw);
+    MP_LAUNCH_OK();
+    return MP_OK;
+}

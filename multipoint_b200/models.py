@@ -1,0 +1,162 @@
+"""Host-side mirror of ``multipoint.models.MultiPoint`` (reference: multipoint/models/MultiPoint.py).
+
+Same constructor config, same module / state-dict names (``encoder[_optical|_thermal].N.*``,
+``detector_head_convolutions.N.*``, ``descriptor_head_convolutions.N.*``), same parameter creation
+order (so a given ``torch.manual_seed`` gives the reference's initial weights) and the same
+``forward(data) -> {'prob', 'logits', 'desc'}`` contract (MultiPoint.py:99-135).
+
+The convolutional backbone and the two head convolutions stay in PyTorch / cuDNN (north star).
+What follows them is the hot path and runs in this repo's CUDA kernels through the C ABI:
+  detector head tail   softmax(65) + dustbin drop + PixelShuffle(8)   MultiPoint.py:150-158
+  descriptor head tail F.normalize(dim=1)                             MultiPoint.py:160-166
+There is no eager fallback for those tails: inference needs a CUDA device.
+"""
+import copy
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .utils import dict_update
+
+_CHANNELS = {0: ([1, 64, 64, 128, 128], None), 1: ([1, 32, 64, 96, 128], 'desc'), 2: ([1, 8, 16, 32, 64], 'desc')}
+
+
+class MultiPoint(nn.Module):
+    default_config = {
+        'multispectral': True,
+        'descriptor_head': True,
+        'intepolation_mode': 'bilinear',
+        'descriptor_size': 256,
+        'normalize_descriptors': True,
+        'final_batchnorm': True,
+        'reflection_pad': True,
+        'bn_first': False,
+        'double_convolution': True,
+        'channel_version': 0,
+        'verbose': False,
+        'mixed_precision': False,
+        'force_return_logits': False,
+    }
+
+    def __init__(self, config=None):
+        super().__init__()
+        # MultiPoint.py:28-31: a given config is merged into a copy of the defaults
+        self.config = dict_update(copy.deepcopy(self.default_config), config) if config else self.default_config
+        cfg = self.config
+        self.pad_method = nn.ReflectionPad2d if cfg['reflection_pad'] else nn.ZeroPad2d
+
+        version = cfg['channel_version']
+        if version not in _CHANNELS:
+            print('Unknown channel_version: ', version)
+            version = 0
+        self.n_channels, head = _CHANNELS[version]
+        self.head_channels = cfg['descriptor_size'] if head == 'desc' else 256
+
+        # creation order matters for seeded initialisation: thermal before optical (MultiPoint.py:54-58)
+        if cfg['multispectral']:
+            self.encoder_thermal = self.generate_encoder()
+            self.encoder_optical = self.generate_encoder()
+        else:
+            self.encoder = self.generate_encoder()
+
+        self.detector_head_convolutions = self._head(65)
+        # kept for state-dict / attribute compatibility; the tails run in CUDA kernels
+        self.softmax = nn.Softmax2d()
+        self.shuffle = nn.PixelShuffle(8)
+        if cfg['descriptor_head']:
+            self.descriptor_head_convolutions = self._head(cfg['descriptor_size'])
+
+        if cfg['verbose']:
+            print('MultiPoint number of trainable parameter: ' + str(sum(p.numel() for p in self.parameters())))
+
+    # ------------------------------------------------------------------ construction helpers
+    def getNonlinearity(self, N):
+        if self.config['bn_first']:
+            return nn.BatchNorm2d(N), nn.ReLU(True)
+        return nn.ReLU(True), nn.BatchNorm2d(N)
+
+    def getConvolutionBlock(self, N_in, N_out):
+        block = [self.pad_method(1), nn.Conv2d(N_in, N_out, 3), *self.getNonlinearity(N_out)]
+        if self.config['double_convolution']:
+            block += [self.pad_method(1), nn.Conv2d(N_out, N_out, 3), *self.getNonlinearity(N_out)]
+        return tuple(block)
+
+    def generate_encoder(self):
+        c = self.n_channels
+        layers = []
+        for stage in range(4):
+            layers += list(self.getConvolutionBlock(c[stage], c[stage + 1]))
+            if stage < 3:
+                layers.append(nn.MaxPool2d(2, 2))
+        return nn.Sequential(*layers)
+
+    def _head(self, out_channels):
+        layers = [self.pad_method(1), nn.Conv2d(self.n_channels[4], self.head_channels, 3),
+                  *self.getNonlinearity(self.head_channels), nn.Conv2d(self.head_channels, out_channels, 1)]
+        if self.config['final_batchnorm']:
+            layers.append(nn.BatchNorm2d(out_channels))
+        return nn.Sequential(*layers)
+
+    # ------------------------------------------------------------------ reference API
+    def set_force_return_logits(self, value):
+        if not isinstance(value, bool):
+            raise ValueError('set_force_return_logits: The input value needs to be a bool')
+        self.config['force_return_logits'] = value
+
+    def forward(self, data):
+        if self.config['mixed_precision']:
+            with torch.autocast('cuda'):
+                return self.forward_impl(data)
+        return self.forward_impl(data)
+
+    def encode(self, data):
+        """Encoder routing of MultiPoint.py:107-124: each row goes through the optical or the thermal
+        encoder according to data['is_optical'][:,0]."""
+        image = data['image']
+        if not self.config['multispectral']:
+            return self.encoder(image)
+        sel = data['is_optical'][:, 0].bool()
+        n_opt = int(sel.sum())
+        if n_opt == image.shape[0]:
+            return self.encoder_optical(image)
+        if n_opt == 0:
+            return self.encoder_thermal(image)
+        xo = self.encoder_optical(image[sel])
+        xt = self.encoder_thermal(image[~sel])
+        x = torch.empty((image.shape[0],) + tuple(xo.shape[1:]), dtype=xo.dtype, device=xo.device)
+        x[sel] = xo
+        x[~sel] = xt
+        return x
+
+    def forward_impl(self, data):
+        x = self.encode(data)
+        prob, logits = self.detector_head(x)
+        out = {'prob': prob, 'logits': logits}
+        if self.config['descriptor_head']:
+            out['desc'] = self.descriptor_head(x)
+        return out
+
+    def detector_head(self, x):
+        logits = self.detector_head_convolutions(x).to(torch.float)
+        if self.training or self.config['force_return_logits']:
+            return None, logits
+        return ops.detector_head(logits), None
+
+    def descriptor_head(self, x, channels_last=False):
+        x = self.descriptor_head_convolutions(x).to(torch.float)
+        if not self.config['normalize_descriptors']:
+            return x
+        if torch.is_grad_enabled() and x.requires_grad:
+            # training is outside the hot path: keep autograd alive
+            return torch.nn.functional.normalize(x, p=2, dim=1)
+        nchw, nhwc = ops.normalize_descriptors(x, nchw=not channels_last, nhwc=channels_last)
+        return nhwc if channels_last else nchw
+
+    # ------------------------------------------------------------------ fused entry used by the pipeline
+    def backbone_outputs(self, data):
+        """(logits (B,65,Hc,Wc), raw descriptor map (B,D,Hc,Wc)) -- everything cuDNN computes."""
+        x = self.encode(data)
+        logits = self.detector_head_convolutions(x).to(torch.float)
+        raw = self.descriptor_head_convolutions(x).to(torch.float) if self.config['descriptor_head'] else None
+        return logits, raw

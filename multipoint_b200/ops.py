@@ -1,0 +1,276 @@
+"""Device-tensor front end of the C ABI: one function per entry point of multipoint_b200.h.
+
+torch is plumbing only (device memory, current stream).  Every function takes CUDA tensors and
+raises if handed anything else: there is no CPU or eager fallback on the product path.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+
+METRIC = {'nn': 0, 'l2': 1}
+ALGO = {'tensor': 0, 'simt': 1}
+AGG = {None: 0, 'none': 0, 'prod': 1, 'sum': 2}
+HA_INIT, HA_FINISH = 1, 2
+
+
+def _cuda(t, dtype, name):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError("multipoint_b200.ops: %s must be a CUDA tensor (no CPU fallback)" % name)
+    if t.dtype != dtype:
+        raise TypeError("multipoint_b200.ops: %s must be %s, got %s" % (name, dtype, t.dtype))
+    return t.contiguous()
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream(t):
+    return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _ws(nbytes, device):
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+def detector_head(logits, valid_mask=None):
+    """(B,65,Hc,Wc) fp32 logits -> (B,1,8Hc,8Wc) heatmap; optional (B,1,H,W) bool/uint8 mask."""
+    logits = _cuda(logits, torch.float32, "logits")
+    if logits.dim() != 4 or logits.shape[1] != 65:
+        raise ValueError("logits must be (B,65,Hc,Wc), got %s" % (tuple(logits.shape),))
+    B, _, Hc, Wc = logits.shape
+    prob = torch.empty((B, 1, Hc * 8, Wc * 8), dtype=torch.float32, device=logits.device)
+    mask = None
+    if valid_mask is not None:
+        if not valid_mask.is_cuda:
+            raise RuntimeError("valid_mask must be a CUDA tensor")
+        mask = valid_mask.to(torch.uint8).contiguous() if valid_mask.dtype != torch.uint8 else valid_mask.contiguous()
+        if mask.numel() != prob.numel():
+            raise ValueError("valid_mask must have %d elements" % prob.numel())
+    with torch.cuda.device(logits.device):
+        _lib.check(_lib.load().mp_detector_head_f32(_ptr(logits), B, Hc, Wc, _ptr(mask), _ptr(prob), _stream(logits)),
+                   "mp_detector_head_f32")
+    return prob
+
+
+def depth_to_space(x, block_size):
+    x = _cuda(x, torch.float32, "x")
+    N, C, H, W = x.shape
+    bs = int(block_size)
+    if C % (bs * bs) != 0:
+        raise ValueError("channels %d not divisible by block_size^2" % C)
+    out = torch.empty((N, C // (bs * bs), H * bs, W * bs), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().mp_depth_to_space_f32(_ptr(x), N, C // (bs * bs), H, W, bs, _ptr(out), _stream(x)),
+                   "mp_depth_to_space_f32")
+    return out
+
+
+def normalize_descriptors(x, nchw=True, nhwc=False):
+    """F.normalize(x, p=2, dim=1) of (B,D,Hc,Wc); returns (nchw, nhwc) with None for the one not requested."""
+    x = _cuda(x, torch.float32, "x")
+    B, D = x.shape[:2]
+    HW = int(np.prod(x.shape[2:]))
+    o1 = torch.empty_like(x) if nchw else None
+    o2 = torch.empty((B,) + tuple(x.shape[2:]) + (D,), dtype=torch.float32, device=x.device) if nhwc else None
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().mp_normalize_descriptors_f32(_ptr(x), B, D, HW, _ptr(o1), _ptr(o2), _stream(x)),
+                   "mp_normalize_descriptors_f32")
+    return o1, o2
+
+
+def box_nms(prob, size, min_prob, iou=0.1, keep_top_k=0, want_keypoints=False, kp_cap=None):
+    """prob (B,H,W) fp32 -> dense NMS map (B,H,W) [+ keypoints (B,cap,2) int64, scores (B,cap), counts (B)]."""
+    prob = _cuda(prob, torch.float32, "prob")
+    B, H, W = prob.shape
+    dev = prob.device
+    out = torch.empty_like(prob)
+    lib = _lib.load()
+    kp = sc = cnt = None
+    cap = 0
+    if want_keypoints:
+        cap = int(kp_cap) if kp_cap is not None else (int(keep_top_k) if keep_top_k > 0 else H * W)
+        kp = torch.zeros((B, cap, 2), dtype=torch.int64, device=dev)
+        sc = torch.zeros((B, cap), dtype=torch.float32, device=dev)
+        cnt = torch.zeros((B,), dtype=torch.int32, device=dev)
+    nbytes = lib.mp_box_nms_workspace_bytes(B, H, W)
+    ws = _ws(nbytes, dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.mp_box_nms_f32(_ptr(prob), B, H, W, float(size), float(min_prob), float(iou), int(keep_top_k),
+                                      _ptr(out), _ptr(kp), _ptr(sc), _ptr(cnt), cap, _ptr(ws), nbytes, _stream(prob)),
+                   "mp_box_nms_f32")
+    return (out, kp, sc, cnt) if want_keypoints else out
+
+
+def extract_keypoints(prob, threshold, mask=None, kp_cap=None):
+    """torch.nonzero((prob > thr).float() [* mask]) per image: keypoints (B,cap,2) int64, scores, counts."""
+    prob = _cuda(prob, torch.float32, "prob")
+    B, H, W = prob.shape
+    dev = prob.device
+    cap = int(kp_cap) if kp_cap is not None else H * W
+    m = None
+    if mask is not None:
+        m = (mask != 0).to(torch.uint8).contiguous()
+    kp = torch.zeros((B, cap, 2), dtype=torch.int64, device=dev)
+    sc = torch.zeros((B, cap), dtype=torch.float32, device=dev)
+    cnt = torch.zeros((B,), dtype=torch.int32, device=dev)
+    lib = _lib.load()
+    nbytes = lib.mp_extract_keypoints_workspace_bytes(B, H, W)
+    ws = _ws(nbytes, dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.mp_extract_keypoints_f32(_ptr(prob), _ptr(m), B, H, W, float(threshold), _ptr(kp), _ptr(sc),
+                                                _ptr(cnt), cap, _ptr(ws), nbytes, _stream(prob)),
+                   "mp_extract_keypoints_f32")
+    return kp, sc, cnt
+
+
+def sample_descriptors(keypoints, desc, H, W, counts=None, channels_last=False):
+    """keypoints (B,K,2) int64 (y,x); desc (B,D,Hc,Wc) or, channels_last, (B,Hc,Wc,D) -> (B,K,D) unit rows."""
+    keypoints = _cuda(keypoints, torch.int64, "keypoints")
+    desc = _cuda(desc, torch.float32, "desc")
+    B, K = keypoints.shape[:2]
+    if channels_last:
+        _, Hc, Wc, D = desc.shape
+    else:
+        _, D, Hc, Wc = desc.shape
+    if counts is not None:
+        counts = _cuda(counts, torch.int32, "counts")
+    out = torch.empty((B, K, D), dtype=torch.float32, device=desc.device)
+    with torch.cuda.device(desc.device):
+        _lib.check(_lib.load().mp_sample_descriptors_f32(_ptr(keypoints), _ptr(counts), B, K, _ptr(desc), D, Hc, Wc,
+                                                         1 if channels_last else 0, int(H), int(W), _ptr(out),
+                                                         _stream(desc)), "mp_sample_descriptors_f32")
+    return out
+
+
+def _match_args(d1, d2, n1, n2):
+    d1 = _cuda(d1, torch.float32, "desc_1")
+    d2 = _cuda(d2, torch.float32, "desc_2")
+    if d1.dim() == 2:
+        d1, d2 = d1[None], d2[None]
+    P, N1, D = d1.shape
+    if d2.shape[0] != P or d2.shape[2] != D:
+        raise ValueError("descriptor sets disagree: %s vs %s" % (tuple(d1.shape), tuple(d2.shape)))
+    if n1 is not None:
+        n1 = _cuda(n1, torch.int32, "n1")
+    if n2 is not None:
+        n2 = _cuda(n2, torch.int32, "n2")
+    return d1.contiguous(), d2.contiguous(), n1, n2, P, N1, d2.shape[1], D
+
+
+def default_algo(D):
+    return 'tensor' if (D % 64 == 0 and D <= 256) else 'simt'
+
+
+def nearest(d1, d2, metric='nn', algo=None, n1=None, n2=None, want_scores=True):
+    """Exact nearest neighbours both ways.  Returns dict idx12 (P,N1), idx21 (P,N2) [+ best/second sims]."""
+    d1, d2, n1, n2, P, N1, N2, D = _match_args(d1, d2, n1, n2)
+    dev = d1.device
+    algo = algo or default_algo(D)
+    i12 = torch.empty((P, N1), dtype=torch.int32, device=dev)
+    i21 = torch.empty((P, N2), dtype=torch.int32, device=dev)
+    outs = [torch.empty((P, n), dtype=torch.float32, device=dev) if want_scores else None for n in (N1, N1, N2, N2)]
+    lib = _lib.load()
+    nbytes = lib.mp_match_workspace_bytes(P, N1, N2, D)
+    ws = _ws(nbytes, dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.mp_nearest_f32(_ptr(d1), _ptr(n1), N1, _ptr(d2), _ptr(n2), N2, P, D, METRIC[metric], ALGO[algo],
+                                      _ptr(i12), _ptr(outs[0]), _ptr(outs[1]), _ptr(i21), _ptr(outs[2]), _ptr(outs[3]),
+                                      _ptr(ws), nbytes, _stream(d1)), "mp_nearest_f32")
+    return dict(idx12=i12, idx21=i21, best12=outs[0], second12=outs[1], best21=outs[2], second21=outs[3])
+
+
+def match(d1, d2, metric='l2', algo=None, kind='mutual', cross_check=True, threshold=-1.0, ratio=0.9, n1=None, n2=None):
+    """Match lists for P pairs: query (P,N1), train (P,N1) int32, dist (P,N1) fp32, counts (P) int32."""
+    d1, d2, n1, n2, P, N1, N2, D = _match_args(d1, d2, n1, n2)
+    dev = d1.device
+    algo = algo or default_algo(D)
+    q = torch.empty((P, N1), dtype=torch.int32, device=dev)
+    t = torch.empty((P, N1), dtype=torch.int32, device=dev)
+    dist = torch.empty((P, N1), dtype=torch.float32, device=dev)
+    cnt = torch.zeros((P,), dtype=torch.int32, device=dev)
+    lib = _lib.load()
+    nbytes = lib.mp_match_workspace_bytes(P, N1, N2, D)
+    ws = _ws(nbytes, dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.mp_match_f32(_ptr(d1), _ptr(n1), N1, _ptr(d2), _ptr(n2), N2, P, D, METRIC[metric], ALGO[algo],
+                                    {'mutual': 0, 'ratio': 1}[kind], int(bool(cross_check)), float(threshold), float(ratio),
+                                    _ptr(q), _ptr(t), _ptr(dist), _ptr(cnt), _ptr(ws), nbytes, _stream(d1)),
+                   "mp_match_f32")
+    return q, t, dist, cnt
+
+
+def match_threshold(d1, d2, threshold):
+    """ThresholdMatcher: all pairs with sqrt(2-2clip(a.b)) < threshold, row-major.  Synchronises once."""
+    d1 = _cuda(d1, torch.float32, "desc_1")
+    d2 = _cuda(d2, torch.float32, "desc_2")
+    N1, D = d1.shape
+    N2 = d2.shape[0]
+    dev = d1.device
+    lib = _lib.load()
+    nbytes = 16 * (N1 + 1) + 512
+    ws = _ws(nbytes, dev)
+    total = ctypes.c_int64(0)
+    with torch.cuda.device(dev):
+        # pass 1: count only (cap = 0)
+        _lib.check(lib.mp_match_threshold_f32(_ptr(d1), N1, _ptr(d2), N2, D, float(threshold), None, None, None, 0,
+                                              ctypes.byref(total), _ptr(ws), nbytes, _stream(d1)), "mp_match_threshold_f32")
+        n = int(total.value)
+        q = torch.empty((n,), dtype=torch.int32, device=dev)
+        t = torch.empty((n,), dtype=torch.int32, device=dev)
+        dist = torch.empty((n,), dtype=torch.float32, device=dev)
+        if n:
+            _lib.check(lib.mp_match_threshold_f32(_ptr(d1), N1, _ptr(d2), N2, D, float(threshold), _ptr(q), _ptr(t),
+                                                  _ptr(dist), n, ctypes.byref(total), _ptr(ws), nbytes, _stream(d1)),
+                       "mp_match_threshold_f32")
+    return q, t, dist
+
+
+def linspace_tables(H, W, device):
+    """torch.linspace(-1,1,.) tables of kornia's create_meshgrid (normalised destination grid)."""
+    return (torch.linspace(-1, 1, W, dtype=torch.float32).to(device), torch.linspace(-1, 1, H, dtype=torch.float32).to(device))
+
+
+def warp(src, A, mode='bilinear', padding='zeros', tables=None):
+    """src (N,H,W) planes shared by all matrices; A (n,3,3) normalised dst->src; out (n,N,H,W)."""
+    src = _cuda(src, torch.float32, "src")
+    A = _cuda(A, torch.float32, "A")
+    N, H, W = src.shape
+    n = A.shape[0]
+    xs, ys = tables if tables is not None else linspace_tables(H, W, src.device)
+    out = torch.empty((n, N, H, W), dtype=torch.float32, device=src.device)
+    with torch.cuda.device(src.device):
+        _lib.check(_lib.load().mp_warp_f32(_ptr(src), N, n, H, W, _ptr(A), _ptr(xs), _ptr(ys),
+                                           {'bilinear': 0, 'nearest': 1}[mode], {'zeros': 0, 'reflection': 1}[padding],
+                                           _ptr(out), _stream(src)), "mp_warp_f32")
+    return out
+
+
+def ha_aggregate(prob0, probw_a, probw_b, masks, Ainv, aggregation, min_count, init=True, finish=True,
+                 prob_acc=None, count_acc=None, tables=None):
+    """Unwarp + accumulate + finish of homographic adaptation; see mp_ha_aggregate_f32."""
+    probw_a = _cuda(probw_a, torch.float32, "probw_a")
+    n, B, H, W = probw_a.shape
+    dev = probw_a.device
+    if probw_b is not None:
+        probw_b = _cuda(probw_b, torch.float32, "probw_b")
+    masks = _cuda(masks, torch.uint8, "masks")
+    Ainv = _cuda(Ainv, torch.float32, "Ainv")
+    if prob0 is not None:
+        prob0 = _cuda(prob0, torch.float32, "prob0")
+    xs, ys = tables if tables is not None else linspace_tables(H, W, dev)
+    out = torch.empty((B, H, W), dtype=torch.float32, device=dev) if finish else None
+    if not finish or not init:
+        if prob_acc is None:
+            prob_acc = torch.zeros((B, H, W), dtype=torch.float32, device=dev)
+            count_acc = torch.zeros((B, H, W), dtype=torch.float32, device=dev)
+    flags = (HA_INIT if init else 0) | (HA_FINISH if finish else 0)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().mp_ha_aggregate_f32(_ptr(prob0), _ptr(probw_a), _ptr(probw_b), _ptr(masks), _ptr(Ainv), n, B,
+                                                   H, W, _ptr(xs), _ptr(ys), AGG[aggregation], int(min_count), flags,
+                                                   _ptr(prob_acc), _ptr(count_acc), _ptr(out), _stream(probw_a)),
+                   "mp_ha_aggregate_f32")
+    return out if finish else (prob_acc, count_acc)

@@ -1,0 +1,86 @@
+"""Sync-free extract-and-match chain: images -> backbone (cuDNN) ->
+detector-head kernel -> NMS + top-k + ordered keypoints -> channels-last descriptor normalise ->
+descriptor sampling -> mutual nearest-neighbour matching, all on one stream with fixed-capacity
+keypoint buffers and device-side counts, so nothing synchronises with the host until the caller
+reads the result.  It is the batched form of what predict_align_image_pair.py:121-190 does per
+sample; each stage is the same kernel the drop-in functions in multipoint_b200.utils call.
+"""
+import torch
+
+from . import ops
+
+
+class KeypointPipeline:
+    def __init__(self, net, nms=4, detection_threshold=0.015, topk=2048, iou=0.1, metric='l2', cross_check=True,
+                 match_threshold=-1.0, algo=None):
+        if topk <= 0:
+            raise ValueError("KeypointPipeline needs topk > 0 (fixed-capacity keypoint buffers)")
+        self.net, self.nms, self.thr, self.topk, self.iou = net, nms, detection_threshold, int(topk), iou
+        self.metric, self.cross_check, self.match_threshold, self.algo = metric, cross_check, match_threshold, algo
+
+    @torch.no_grad()
+    def extract_from_backbone(self, logits, raw_desc, H, W, valid_mask=None):
+        """Hot path proper: backbone outputs -> keypoints + descriptors (no host sync)."""
+        prob = ops.detector_head(logits, valid_mask)
+        B = prob.shape[0]
+        dense, kp, scores, counts = ops.box_nms(prob.reshape(B, H, W), self.nms, self.thr, iou=self.iou,
+                                                keep_top_k=self.topk, want_keypoints=True, kp_cap=self.topk)
+        _, desc_nhwc = ops.normalize_descriptors(raw_desc, nchw=False, nhwc=True)
+        desc = ops.sample_descriptors(kp, desc_nhwc, H, W, counts=counts, channels_last=True)
+        return {'prob': prob, 'prob_nms': dense.reshape(B, 1, H, W), 'keypoints': kp, 'scores': scores,
+                'counts': counts, 'desc': desc}
+
+    @torch.no_grad()
+    def extract(self, data):
+        H, W = data['image'].shape[-2:]
+        logits, raw = self.net.backbone_outputs(data)
+        return self.extract_from_backbone(logits, raw, H, W, data.get('valid_mask'))
+
+    @torch.no_grad()
+    def match(self, ext_a, ext_b):
+        q, t, d, c = ops.match(ext_a['desc'], ext_b['desc'], metric=self.metric, algo=self.algo, kind='mutual',
+                               cross_check=self.cross_check, threshold=self.match_threshold,
+                               n1=ext_a['counts'], n2=ext_b['counts'])
+        return {'query': q, 'train': t, 'distance': d, 'counts': c}
+
+    @torch.no_grad()
+    def __call__(self, data):
+        """data = {'optical': {...}, 'thermal': {...}} with (B,1,H,W) images: one batched backbone
+        pass over both spectra (the reference notes this at predict_align_image_pair.py:122)."""
+        o, t = data['optical'], data['thermal']
+        B = o['image'].shape[0]
+        both = {'image': torch.cat([o['image'], t['image']])}
+        if 'is_optical' in o and 'is_optical' in t:
+            both['is_optical'] = torch.cat([o['is_optical'], t['is_optical']])
+        if 'valid_mask' in o and 'valid_mask' in t:
+            both['valid_mask'] = torch.cat([o['valid_mask'], t['valid_mask']])
+        ext = self.extract(both)
+        ea = {k: v[:B] for k, v in ext.items()}
+        eb = {k: v[B:] for k, v in ext.items()}
+        return {'optical': ea, 'thermal': eb, 'matches': self.match(ea, eb)}
+
+
+def calibrate_random_init(net, images, sigma=2.0, dustbin_bias=5.0, is_optical=None):
+    """Make a randomly initialised MultiPoint produce non-degenerate outputs for benchmarks
+    (random init gives a flat heatmap ~1/65 > threshold everywhere).  Sets the
+    running statistics of the two final BatchNorms to the actual statistics of the pre-BN
+    activations on ``images`` and the detector BN affine to (sigma, +dustbin_bias on channel 64),
+    so logits ~ sigma*N(0,1) like the synthetic logits of multipoint_b200.synthetic.logits.
+    Weights stay random-init; only BN buffers / affine change."""
+    det, desc = net.detector_head_convolutions, net.descriptor_head_convolutions
+    assert isinstance(det[-1], torch.nn.BatchNorm2d), "needs final_batchnorm"
+    with torch.no_grad():
+        data = {'image': images}
+        if is_optical is not None:
+            data['is_optical'] = is_optical
+        x = net.encode(data)
+        for head, scale, bias64 in ((det, sigma, dustbin_bias), (desc, 1.0, None)):
+            pre = head[:-1](x).float()
+            bn = head[-1]
+            bn.running_mean.copy_(pre.mean(dim=(0, 2, 3)))
+            bn.running_var.copy_(pre.var(dim=(0, 2, 3), unbiased=False))
+            bn.weight.fill_(scale)
+            bn.bias.zero_()
+            if bias64 is not None:
+                bn.bias[64] = bias64
+    return net

@@ -22,6 +22,9 @@ def pytest_collection_modifyitems(config, items):
     except Exception:
         have = False
     if have:
+        # fp32 means fp32: parity tolerances assume cuDNN / cuBLAS do not drop to TF32
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
         return
     skip = pytest.mark.skip(reason="no CUDA device")
     for it in items:

@@ -1,0 +1,512 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs
+and against the golden fixtures frozen from the reference.  Bit-exact for keypoints, NMS maps and
+match indices; floating point within the tolerance written at each assert (north star: 1e-5
+relative for heatmaps and descriptors)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import dense_from_sparse, load_golden
+from multipoint_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from multipoint_b200 import ops as _ops
+    return _ops
+
+
+@pytest.fixture(scope="module")
+def utils():
+    from multipoint_b200 import utils as _utils
+    return _utils
+
+
+def cu(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    return t if dtype is None else t.to(dtype)
+
+
+# ------------------------------------------------------------------ row 1: detector head
+def test_detector_head_golden_and_oracle(ops, oracle):
+    g = load_golden("heads")
+    got = ops.detector_head(cu(g["logits"])).cpu().numpy()
+    np.testing.assert_allclose(got, g["prob"], rtol=RTOL, atol=1e-9)            # vs the reference
+    np.testing.assert_allclose(got, oracle.detector_head(g["logits"]), rtol=RTOL, atol=1e-9)
+    for seed, B, Hc, Wc in [(101, 3, 64, 80), (102, 1, 5, 7), (103, 2, 33, 17)]:  # ragged: warps straddle rows/images
+        lg = syn.logits(seed, B, Hc, Wc)
+        got = ops.detector_head(cu(lg)).cpu().numpy()
+        np.testing.assert_allclose(got, oracle.detector_head(lg), rtol=RTOL, atol=1e-9)
+    # size-independent property at the bench size: each 8x8 cell sums to 1 - dustbin probability <= 1
+    lg = cu(syn.logits(104, 8, 64, 80))
+    prob = ops.detector_head(lg)
+    cell = prob.reshape(8, 64, 8, 80, 8).sum(dim=(2, 4))
+    dust = torch.softmax(lg, 1)[:, 64]
+    torch.testing.assert_close(cell, 1.0 - dust, rtol=1e-4, atol=1e-6)
+
+
+def test_detector_head_valid_mask(ops, oracle):
+    lg = syn.logits(105, 2, 16, 20)
+    mask = (np.random.default_rng(5).random((2, 1, 128, 160)) > 0.3)
+    got = ops.detector_head(cu(lg), cu(mask)).cpu().numpy()
+    np.testing.assert_allclose(got, oracle.detector_head(lg) * mask, rtol=RTOL, atol=1e-9)
+
+
+def test_depth_to_space(utils):
+    g = load_golden("heads")
+    x = cu(g["logits"][:, :64].copy())
+    np.testing.assert_array_equal(utils.depth_to_space(x, 8).cpu().numpy(), g["depth_to_space"])
+    y = torch.randn(2, 12, 5, 7, device="cuda")
+    ref = y.view(2, 2, 2, 3, 5, 7).permute(0, 3, 4, 1, 5, 2).reshape(2, 3, 10, 14)
+    torch.testing.assert_close(utils.depth_to_space(y, 2), ref, rtol=0, atol=0)
+
+
+# ------------------------------------------------------------------ row 2: descriptor normalise
+def test_normalize_descriptors(ops, oracle):
+    g = load_golden("heads")
+    for key_in, key_out in [("desc_in", "desc"), ("desc256_in", "desc256")]:
+        x = g[key_in]
+        nchw, nhwc = ops.normalize_descriptors(cu(x), nchw=True, nhwc=True)
+        np.testing.assert_allclose(nchw.cpu().numpy(), g[key_out], rtol=RTOL, atol=1e-9)
+        np.testing.assert_allclose(nhwc.permute(0, 3, 1, 2).cpu().numpy(), g[key_out], rtol=RTOL, atol=1e-9)
+    for D, HW in [(64, (64, 80)), (256, (64, 80)), (128, (7, 9)), (48, (5, 5)), (300, (4, 6))]:
+        x = syn.descriptor_map(7, 2, D, *HW)
+        nchw, nhwc = ops.normalize_descriptors(cu(x), nchw=True, nhwc=True)
+        want = oracle.normalize_descriptors(x)
+        np.testing.assert_allclose(nchw.cpu().numpy(), want, rtol=RTOL, atol=1e-9)
+        np.testing.assert_allclose(nhwc.permute(0, 3, 1, 2).cpu().numpy(), want, rtol=RTOL, atol=1e-9)
+
+
+# ------------------------------------------------------------------ row 4: box_nms
+@pytest.mark.parametrize("tag,size,topk", [("chain", 4, 0), ("tie4", 4, 0), ("strict", 4, 0), ("top2", 4, 2)])
+def test_box_nms_hand_cases(utils, tag, size, topk):
+    g = load_golden("box_nms")
+    p = g[tag + "_in"]
+    want = dense_from_sparse(g[tag + "_idx"], g[tag + "_val"], p.shape)
+    got = utils.box_nms(cu(p), size, 0.015, keep_top_k=topk)
+    np.testing.assert_array_equal(got.cpu().numpy(), want)
+    got = utils.box_nms(torch.from_numpy(p), size, 0.015, keep_top_k=topk)  # host tensor in -> host tensor out
+    assert got.device.type == "cpu"
+    np.testing.assert_array_equal(got.numpy(), want)
+
+
+def assert_equal_up_to_topk_ties(got, want):
+    for b in range(got.shape[0]):
+        gb, wb = got[b], want[b]
+        np.testing.assert_array_equal(np.sort(gb[gb > 0]), np.sort(wb[wb > 0]))
+        if (wb > 0).any():
+            cut = wb[wb > 0].min()
+            np.testing.assert_array_equal(gb > cut, wb > cut)
+
+
+def test_box_nms_small_random_vs_reference_and_oracle(utils, oracle):
+    g = load_golden("box_nms")
+    for seed, size, topk, quant, B in g["small_cases"]:
+        seed, topk, B = int(seed), int(topk), int(B)
+        hm = syn.heatmap(seed, B, 64, 80, quant=(quant or None))
+        tag = "small%d" % seed
+        got4 = utils.box_nms(cu(hm), size, 0.015, keep_top_k=topk).cpu().numpy()
+        got2 = utils.box_nms(cu(hm[0, 0]), size, 0.015, keep_top_k=topk).cpu().numpy()
+        want4 = dense_from_sparse(g[tag + "_4d_idx"], g[tag + "_4d_val"], hm.shape)
+        want2 = dense_from_sparse(g[tag + "_2d_idx"], g[tag + "_2d_val"], hm.shape[-2:])
+        np.testing.assert_array_equal(got2, want2)
+        if quant and topk:
+            assert_equal_up_to_topk_ties(got4, want4)  # undefined in the reference
+        else:
+            np.testing.assert_array_equal(got4, want4)
+        # against the oracle the stable tie rule is defined: bit-exact always
+        np.testing.assert_array_equal(got4, oracle.box_nms(hm, size, 0.015, keep_top_k=topk))
+
+
+def test_box_nms_full_size_vs_reference(utils, ops, oracle):
+    g = load_golden("box_nms")
+    for seed, topk, quant, B in g["full_cases"]:
+        seed, topk, B = int(seed), int(topk), int(B)
+        hm = syn.heatmap(seed, B, 512, 640, quant=(quant or None))
+        assert syn.checksum(hm) == str(g["full%d_checksum" % seed])
+        want = dense_from_sparse(g["full%d_4d_idx" % seed], g["full%d_4d_val" % seed], hm.shape)
+        got = utils.box_nms(cu(hm), 4, 0.015, keep_top_k=topk).cpu().numpy()
+        if quant and topk:
+            assert_equal_up_to_topk_ties(got, want)
+            np.testing.assert_array_equal(got, oracle.box_nms(hm, 4, 0.015, keep_top_k=topk))
+        else:
+            np.testing.assert_array_equal(got, want)
+    # the reference's own softmax heatmap + top-k 2048 + the keypoint idiom, in one fused call
+    prob = g["softmax34_prob"]
+    want = dense_from_sparse(g["softmax34_idx"], g["softmax34_val"], prob.shape)
+    dense, kp, sc, cnt = utils.box_nms_keypoints(cu(prob), 4, 0.015, keep_top_k=2048)
+    np.testing.assert_array_equal(dense.cpu().numpy(), want)
+    assert int(cnt[0]) == len(g["softmax34_kp"])
+    np.testing.assert_array_equal(kp[0, :int(cnt[0])].cpu().numpy(), g["softmax34_kp"])
+    kpn = g["softmax34_kp"]
+    np.testing.assert_array_equal(sc[0, :int(cnt[0])].cpu().numpy(), want[0, 0][kpn[:, 0], kpn[:, 1]])
+    np.testing.assert_array_equal(utils.extract_keypoints(dense[0], 0.015).cpu().numpy(), g["softmax34_kp"])
+
+
+@pytest.mark.parametrize("size,iou", [(3, 0.1), (8, 0.1), (4, 0.3), (5, 0.1), (2.5, 0.1), (12, 0.1)])
+def test_box_nms_other_sizes_vs_oracle(utils, oracle, size, iou):
+    hm = syn.heatmap(200 + int(size * 2), 2, 96, 136)  # not a multiple of the tile, W % 4 == 0
+    got = utils.box_nms(cu(hm), size, 0.015, iou=iou).cpu().numpy()
+    np.testing.assert_array_equal(got, oracle.box_nms(hm, size, 0.015, iou=iou))
+
+
+def test_box_nms_edge_shapes_vs_oracle(utils, oracle):
+    for seed, H, W in [(301, 1, 1), (302, 7, 5), (303, 33, 130), (304, 65, 257), (305, 40, 56)]:  # W % 4 != 0: scalar path
+        hm = syn.heatmap(seed, 2, H, W)
+        for topk in (0, 5):
+            got = utils.box_nms(cu(hm), 4, 0.015, keep_top_k=topk).cpu().numpy()
+            np.testing.assert_array_equal(got, oracle.box_nms(hm, 4, 0.015, keep_top_k=topk))
+    empty = np.zeros((2, 1, 64, 80), np.float32)
+    assert float(utils.box_nms(cu(empty), 4, 0.015).abs().sum()) == 0.0
+    with pytest.raises(ValueError):
+        utils.box_nms(torch.zeros(3, 64, 80, device="cuda"), 4, 0.015)
+    with pytest.raises(NotImplementedError):
+        utils.box_nms(torch.zeros(64, 80, device="cuda"), 4, -0.5)
+
+
+def test_box_nms_pathological_maps_vs_oracle(utils, oracle):
+    """Flat / constant maps: every pixel is a candidate and (constant map) every score ties, so
+    the dependency chain runs across the whole image: exercises the worklist fix-up kernel."""
+    flat = np.full((1, 1, 64, 80), 0.02, np.float32)
+    np.testing.assert_array_equal(utils.box_nms(cu(flat), 4, 0.015).cpu().numpy(), oracle.box_nms(flat, 4, 0.015))
+    ramp = (0.02 + 1e-4 * np.arange(96 * 136, dtype=np.float32).reshape(1, 1, 96, 136)).astype(np.float32)
+    np.testing.assert_array_equal(utils.box_nms(cu(ramp), 4, 0.015).cpu().numpy(), oracle.box_nms(ramp, 4, 0.015))
+    lg = syn.logits(306, 1, 64, 80, sigma=0.01, bias=0.0)  # random-init-like: ~1/65 everywhere
+    prob = oracle.detector_head(lg)
+    np.testing.assert_array_equal(utils.box_nms(cu(prob), 4, 0.015).cpu().numpy(), oracle.box_nms(prob, 4, 0.015))
+
+
+def test_box_nms_bench_size_properties(ops):
+    """BASELINE config 2 size (128 images, top-k 2048): size-independent properties."""
+    B = 128
+    lg = cu(syn.logits(307, B))
+    prob = ops.detector_head(lg).reshape(B, 512, 640)
+    dense, kp, sc, cnt = ops.box_nms(prob, 4, 0.015, keep_top_k=2048, want_keypoints=True, kp_cap=2048)
+    assert int(cnt.min()) == 2048 and int(cnt.max()) == 2048
+    assert int((dense > 0).sum()) == 2048 * B
+    assert bool(((dense == 0) | (dense == prob)).all())                       # survivors keep their score
+    flat = kp[..., 0] * 640 + kp[..., 1]
+    assert bool((flat[:, 1:] > flat[:, :-1]).all())                            # row-major, strictly increasing
+    assert bool((dense.reshape(B, -1).gather(1, flat) == sc).all())
+    # idempotence: survivors are mutually non-suppressing, so NMS of the NMS map is the identity
+    again = ops.box_nms(dense, 4, 0.015)
+    assert bool((again == dense).all())
+    # no two survivors inside each other's footprint: dilating by the footprint never hits another survivor
+    m = (dense > 0).float()[:, None]
+    k = torch.ones(1, 1, 7, 7, device="cuda")
+    k[0, 0, [0, 0, 0, 0, 6, 6, 6, 6, 1, 1, 5, 5], [0, 1, 5, 6, 0, 1, 5, 6, 0, 6, 0, 6]] = 0
+    neigh = torch.nn.functional.conv2d(m, k, padding=3)
+    assert float((neigh * m).max()) == 1.0                                     # only itself
+
+
+# ------------------------------------------------------------------ row 5: interpolate_descriptors
+def test_interpolate_descriptors(utils, ops, oracle):
+    g = load_golden("interpolate")
+    for D in (64, 256):
+        dm = syn.descriptor_map(int(g["d%d_seed" % D][0]), 1, D, 64, 80)[0]
+        kp = g["d%d_kp" % D]
+        got = utils.interpolate_descriptors(cu(kp), cu(dm), 512, 640).cpu().numpy()
+        np.testing.assert_allclose(got, g["d%d_out" % D], rtol=RTOL, atol=2e-7)                      # vs reference
+        np.testing.assert_allclose(got, oracle.interpolate_descriptors(kp, dm, 512, 640), rtol=RTOL, atol=2e-7)
+        # channels-last layout gives the same rows
+        nhwc = cu(dm).permute(1, 2, 0).contiguous()[None]
+        got2 = ops.sample_descriptors(cu(kp)[None], nhwc, 512, 640, channels_last=True)[0].cpu().numpy()
+        np.testing.assert_allclose(got2, got, rtol=1e-6, atol=1e-7)
+    got = utils.interpolate_descriptors(cu(g["small_kp"]), cu(g["small_in"]), 40, 56).cpu().numpy()
+    np.testing.assert_allclose(got, g["small_out"], rtol=RTOL, atol=2e-7)
+    kp_before = cu(g["small_kp"])
+    kp_copy = kp_before.clone()
+    utils.interpolate_descriptors(kp_before, cu(g["small_in"]), 40, 56)
+    assert torch.equal(kp_before, kp_copy)                                     # never mutates its input
+    assert tuple(utils.interpolate_descriptors(torch.zeros((0, 2), dtype=torch.int64, device="cuda"),
+                                               cu(g["small_in"]), 40, 56).shape) == tuple(g["empty_shape"])
+    # per-image counts: rows beyond the count are zero
+    kp = cu(syn.keypoints(9, 50, 512, 640))[None].repeat(2, 1, 1)
+    dm = cu(syn.descriptor_map(9, 2, 64))
+    out = ops.sample_descriptors(kp, dm, 512, 640, counts=torch.tensor([50, 20], dtype=torch.int32, device="cuda"))
+    assert float(out[1, 20:].abs().sum()) == 0.0 and float(out[1, :20].abs().sum()) > 0
+    torch.testing.assert_close(out.norm(dim=2)[0], torch.ones(50, device="cuda"), rtol=1e-5, atol=1e-5)
+
+
+# ------------------------------------------------------------------ rows 6-8: matching
+def _golden_inputs(g, case):
+    seed, N1, N2, D, noise, dup = case
+    tag = "m%d" % int(seed)
+    if tag + "_a" in g.files:
+        return tag, g[tag + "_a"], g[tag + "_b"]
+    return (tag,) + syn.descriptor_sets(int(seed), int(N1), int(N2), int(D), float(noise), int(dup))
+
+
+@pytest.mark.parametrize("algo", ["simt", "tensor"])
+def test_matching_vs_reference_goldens(ops, algo):
+    """bfmatcher crossCheck / plain, nnmatcher (two thresholds) and the knn ratio test on the
+    fixtures produced by the reference's get_matches: match indices bit-exact, distances 1e-5
+    (2e-4 absolute for sqrt(2-2s), which amplifies the fp32 rounding of s near 1)."""
+    g = load_golden("matching")
+    for case in g["cases"]:
+        tag, a, b = _golden_inputs(g, case)
+        A, Bm = cu(a), cu(b)
+
+        def run(**kw):
+            q, t, d, c = ops.match(A, Bm, algo=algo, **kw)
+            n = int(c[0])
+            return q[0, :n].cpu().numpy(), t[0, :n].cpu().numpy(), d[0, :n].cpu().numpy()
+
+        q, t, d = run(metric='l2', kind='mutual', cross_check=True)
+        np.testing.assert_array_equal(q, g[tag + "_bf_q"]); np.testing.assert_array_equal(t, g[tag + "_bf_t"])
+        np.testing.assert_allclose(d, g[tag + "_bf_d"], rtol=RTOL, atol=1e-6)
+        q, t, d = run(metric='l2', kind='mutual', cross_check=False)
+        np.testing.assert_array_equal(q, g[tag + "_bfnc_q"]); np.testing.assert_array_equal(t, g[tag + "_bfnc_t"])
+        for thr, key in [(0.7, "_nn"), (1.1, "_nn11")]:
+            q, t, d = run(metric='nn', kind='mutual', cross_check=True, threshold=thr)
+            np.testing.assert_array_equal(q, g[tag + key + "_q"]); np.testing.assert_array_equal(t, g[tag + key + "_t"])
+            np.testing.assert_allclose(d, g[tag + key + "_d"], rtol=RTOL, atol=2e-4)
+        if tag + "_knn_q" in g.files:
+            q, t, d = run(metric='l2', kind='ratio', ratio=0.9)
+            np.testing.assert_array_equal(q, g[tag + "_knn_q"]); np.testing.assert_array_equal(t, g[tag + "_knn_t"])
+
+
+@pytest.mark.parametrize("algo", ["simt", "tensor"])
+@pytest.mark.parametrize("metric", ["nn", "l2"])
+def test_nearest_equals_fp64_truth(ops, oracle, algo, metric):
+    """The index contract: argmin equals the fp64 argmin of the oracle on every row, both
+    directions, including planted exact duplicates (lowest index) and near-ties."""
+    mode = {'nn': 'nn', 'l2': 'bf'}[metric]
+    for seed, N1, N2, D, noise, dup in [(401, 500, 700, 64, 0.05, 25), (402, 1000, 900, 256, 0.6, 0),
+                                        (403, 130, 257, 128, 0.2, 10), (404, 3, 1, 64, 0.1, 0)]:
+        a, b = syn.descriptor_sets(seed, N1, N2, D, noise, dup)
+        if seed == 402:  # near-ties: rows that differ from a neighbour by ~1e-7
+            b[1::2] = b[0:-1:2] + np.float32(3e-8) * np.sign(b[0:-1:2])
+        res = ops.nearest(cu(a), cu(b), metric=metric, algo=algo)
+        want = oracle.nearest(a, b, mode, f64=True)
+        np.testing.assert_array_equal(res["idx12"][0].cpu().numpy(), want["idx12"])
+        np.testing.assert_array_equal(res["idx21"][0].cpu().numpy(), want["idx21"])
+        # approximate similarities stay inside the documented error bound (4e-5 |a||b|)
+        sim = a.astype(np.float64) @ b.astype(np.float64).T
+        best = np.take_along_axis(sim, res["idx12"][0].cpu().numpy().astype(np.int64)[:, None], 1)[:, 0]
+        assert np.abs(res["best12"][0].cpu().numpy() - best).max() < 4e-5
+
+
+def test_matching_batched_counts_and_empty(ops, oracle):
+    """P pairs in one call with per-pair valid counts (the pipeline's layout), vs per-pair oracle."""
+    P, N, D = 3, 384, 64
+    sets = [syn.descriptor_sets(500 + p, N, N, D, 0.3) for p in range(P)]
+    A = cu(np.stack([s[0] for s in sets]))
+    Bm = cu(np.stack([s[1] for s in sets]))
+    n1 = torch.tensor([384, 100, 0], dtype=torch.int32, device="cuda")
+    n2 = torch.tensor([384, 257, 50], dtype=torch.int32, device="cuda")
+    for algo in ("simt", "tensor"):
+        q, t, d, c = ops.match(A, Bm, metric='l2', algo=algo, kind='mutual', cross_check=True, n1=n1, n2=n2)
+        for p in range(P):
+            a, b = sets[p][0][:int(n1[p])], sets[p][1][:int(n2[p])]
+            wq, wt, wd = oracle.match_mutual(a, b, 'bf', f64=True, cross_check=True) if len(a) else (np.zeros(0),) * 3
+            n = int(c[p])
+            assert n == len(wq)
+            np.testing.assert_array_equal(q[p, :n].cpu().numpy(), wq)
+            np.testing.assert_array_equal(t[p, :n].cpu().numpy(), wt)
+            np.testing.assert_allclose(d[p, :n].cpu().numpy(), wd, rtol=RTOL, atol=1e-6)
+
+
+def test_matching_bench_sizes_properties(ops):
+    """Config 3 sizes (up to 16k x 16k x 256): planted permutation recovered; mutual property."""
+    for N in (2048, 16384):
+        a, b = syn.descriptor_sets(600 + N, N, N, 256, 0.05)
+        A, Bm = cu(a), cu(b)
+        res = ops.nearest(A, Bm, metric='nn', algo='tensor', want_scores=False)
+        i12, i21 = res["idx12"][0].long(), res["idx21"][0].long()
+        assert bool((i21[i12] == torch.arange(N, device="cuda")).all())      # planted matches are mutual
+        sim = (A[:512] @ Bm.T)                                               # fp32 check on a slice
+        assert bool((sim.argmax(1) == i12[:512]).all())
+        q, t, d, c = ops.match(A, Bm, metric='l2', algo='tensor', kind='mutual', cross_check=True)
+        assert int(c[0]) == N and bool((q[0] == torch.arange(N, device="cuda")).all())
+
+
+def test_get_matches_dropin(utils):
+    import cv2
+    g = load_golden("matching")
+    a, b = g["m51_a"], g["m51_b"]
+    m = utils.get_matches(a, b, 'bfmatcher', False, crossCheck=True)
+    assert isinstance(m[0], cv2.DMatch)
+    assert [x.queryIdx for x in m] == list(g["m51_bf_q"]) and [x.trainIdx for x in m] == list(g["m51_bf_t"])
+    np.testing.assert_allclose([x.distance for x in m], g["m51_bf_d"], rtol=RTOL, atol=1e-6)
+    m = utils.get_matches(a, b, 'nnmatcher', False)
+    assert [x.trainIdx for x in m] == list(g["m51_nn_t"])
+    m = utils.get_matches(a, b, 'bfmatcher', True)
+    assert [x.queryIdx for x in m] == list(g["m51_knn_q"])
+    m = utils.get_matches(a, b, 'thresholdmatcher', False, threshold=0.9)
+    assert [x.queryIdx for x in m] == list(g["m51_thr_q"]) and [x.trainIdx for x in m] == list(g["m51_thr_t"])
+    np.testing.assert_allclose([x.distance for x in m], g["m51_thr_d"], rtol=RTOL, atol=2e-4)
+    a4, b4 = g["m54_a"], g["m54_b"]   # planted exact duplicates
+    m = utils.get_matches(a4, b4, 'thresholdmatcher', False, threshold=0.9)
+    assert [x.trainIdx for x in m] == list(g["m54_thr_t"])
+    with pytest.raises(ValueError, match=str(g["err_unknown"])):
+        utils.get_matches(a, b, 'nope')
+    with pytest.raises(ValueError, match="non-negative"):
+        utils.NNMatcher(threshold=-1.0)
+    with pytest.raises(AttributeError):
+        utils.get_matches(a, b, 'nnmatcher', True)
+    assert utils.get_matches(np.zeros((0, 64), np.float32), b, 'nnmatcher') == []
+    assert utils.get_matches(np.zeros((0, 64), np.float32), b, 'bfmatcher', crossCheck=True) == []
+
+
+# ------------------------------------------------------------------ rows 9-10: warp / adaptation
+def test_warp_vs_oracle_and_restatement(ops, utils, oracle):
+    g = load_golden("adaptation")
+    H, W = g["img_o"].shape[-2:]
+    img = cu(g["img_o"][:, 0])
+    for i in range(len(g["H"])):
+        for A_np, mode, pad in [(g["A_warp"][i], 'bilinear', 'reflection'), (g["A_unwarp"][i], 'bilinear', 'zeros'),
+                                (g["A_unwarp"][i], 'nearest', 'zeros'), (g["A_warp"][i], 'nearest', 'reflection')]:
+            got = ops.warp(img, cu(A_np)[None], mode, pad)[0].cpu().numpy()
+            want = oracle.warp(g["img_o"][:, 0], A_np, mode, pad)
+            # same matrices, same un-fused fp32 op order: the kernel reproduces the oracle to 1 ulp
+            np.testing.assert_allclose(got, want, rtol=1e-6, atol=1e-7)
+    # against the torch restatement of the kornia path (different op order: 1e-5 px sampling noise)
+    M = torch.from_numpy(g["H"][0].astype(np.float32))[None].repeat(2, 1, 1)
+    got = utils.warp_perspective_tensor(cu(g["img_o"]), M.cuda(), (H, W), 'bilinear', 'reflection').cpu().numpy()
+    np.testing.assert_allclose(got, g["warp_bilinear_reflection"], rtol=1e-5, atol=2e-5)
+    got = utils.warp_perspective_tensor(cu(g["img_o"]), torch.inverse(M).cuda(), (H, W), 'bilinear', 'zeros').cpu().numpy()
+    np.testing.assert_allclose(got, g["warp_bilinear_zeros"], rtol=1e-5, atol=2e-5)
+    # linspace tables are bit-identical to the oracle's restatement
+    xs, ys = ops.linspace_tables(H, W, "cuda")
+    np.testing.assert_array_equal(xs.cpu().numpy(), oracle.linspace_table(W))
+    np.testing.assert_array_equal(ys.cpu().numpy(), oracle.linspace_table(H))
+
+
+def _stub(g):
+    conv = torch.nn.Conv2d(1, 65, 8, stride=8).cuda()
+    conv.weight.data = cu(g["stub_w"])
+    conv.bias.data = cu(g["stub_b"])
+
+    def net(data):
+        from multipoint_b200 import ops as _ops
+        with torch.no_grad():
+            return {'prob': _ops.detector_head(conv(data['image']).float())}
+    return net
+
+
+def assert_close_but_mask_ties(got, want, rtol=1e-4, atol=2e-6, outliers=3e-3):
+    bad = np.abs(got - want) > atol + rtol * np.abs(want)
+    assert bad.mean() <= outliers, bad.mean()
+    assert np.abs(got - want).max() < 0.05 * max(1e-6, np.abs(want).max())
+
+
+def test_homographic_adaptation_vs_restatement_and_oracle(utils, ops, oracle):
+    g = load_golden("adaptation")
+    net = _stub(g)
+    cfg = dict(num=6, min_count=2, erosion_radius=3, filter_size=0)
+    masks = (g["masks"] != 0).astype(np.uint8)
+    img_o, img_t = cu(g["img_o"]), cu(g["img_t"])
+    out = utils.homographic_adaptation({'image': img_o}, net, dict(cfg), homographies=g["H"], masks=masks)
+    assert_close_but_mask_ties(out.cpu().numpy(), g["single"])
+    for agg in ("prod", "sum"):
+        data = {'optical': {'image': img_o, 'is_optical': torch.ones(2, 1, dtype=torch.bool, device="cuda")},
+                'thermal': {'image': img_t, 'is_optical': torch.zeros(2, 1, dtype=torch.bool, device="cuda")}}
+        out = utils.homographic_adaptation_multispectral(data, net, dict(cfg, aggregation=agg), homographies=g["H"], masks=masks)
+        assert_close_but_mask_ties(out.cpu().numpy(), g["multi_" + agg])
+    # the aggregate kernel alone against the C oracle on identical inputs: tight
+    rng = np.random.default_rng(3)
+    n, B, H, W = 5, 2, 64, 80
+    pa = rng.random((n, B, H, W), dtype=np.float32) * 0.3
+    pb = rng.random((n, B, H, W), dtype=np.float32) * 0.3
+    p0 = rng.random((B, H, W), dtype=np.float32) * 0.1
+    for agg, second in [("none", None), ("prod", pb), ("sum", pb)]:
+        want, wcount = oracle.ha_aggregate(p0, pa, second, masks.astype(np.float32), g["A_unwarp"], agg, 2)
+        got = ops.ha_aggregate(cu(p0), cu(pa), None if second is None else cu(second), cu(masks), cu(g["A_unwarp"]), agg, 2)
+        np.testing.assert_allclose(got.cpu().numpy(), want, rtol=1e-6, atol=1e-7)
+        # split into two partial accumulations (the multi-GPU path) and finish: same result to fp32 rounding
+        acc = ops.ha_aggregate(cu(p0), cu(pa[:3]), None if second is None else cu(second[:3]), cu(masks[:3]),
+                               cu(g["A_unwarp"][:3]), agg, 2, init=True, finish=False)
+        got2 = ops.ha_aggregate(None, cu(pa[3:]), None if second is None else cu(second[3:]), cu(masks[3:]),
+                                cu(g["A_unwarp"][3:]), agg, 2, init=False, finish=True, prob_acc=acc[0], count_acc=acc[1])
+        np.testing.assert_allclose(got2.cpu().numpy(), want, rtol=1e-6, atol=1e-7)
+    # error behaviour (homographies.py:42-46,68,123)
+    with pytest.raises(ValueError, match="num must be larger than 0"):
+        utils.homographic_adaptation({'image': img_o}, net, dict(cfg, num=0))
+    with pytest.raises(ValueError, match="filter_size must be uneven"):
+        utils.homographic_adaptation({'image': img_o}, net, dict(cfg, filter_size=4))
+    with pytest.raises(ValueError, match="Unknown aggregation"):
+        utils.homographic_adaptation_multispectral(data, net, dict(cfg, num=2, aggregation='max'))
+
+
+def test_homographic_adaptation_host_sampling_matches_reference_stream(utils):
+    """With np.random.seed(5) the product draws the same homographies and masks as the reference run
+    that produced the fixture, so the end-to-end call (no injected samples) matches it too."""
+    g = load_golden("adaptation")
+    net = _stub(g)
+    cfg = dict(num=6, aggregation='prod', erosion_radius=3, mask_border=True, min_count=2, filter_size=0,
+               homographies=dict(translation=True, rotation=True, scaling=True, perspective=True, scaling_amplitude=0.2,
+                                 perspective_amplitude_x=0.2, perspective_amplitude_y=0.2, patch_ratio=0.85,
+                                 max_angle=1.57, allow_artifacts=True))
+    np.random.seed(int(g["seed"][0]))
+    out = utils.homographic_adaptation({'image': cu(g["img_o"])}, net, cfg)
+    assert_close_but_mask_ties(out.cpu().numpy(), g["single"])
+
+
+# ------------------------------------------------------------------ row 3: model contract
+def test_multipoint_forward_vs_reference(oracle):
+    from multipoint_b200.models import MultiPoint
+    g = load_golden("model")
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    for tag, cfg in [("shipped", {'multispectral': False, 'descriptor_size': 64, 'bn_first': False,
+                                  'descriptor_head': True, 'final_batchnorm': True, 'reflection_pad': True,
+                                  'normalize_descriptors': True}),
+                     ("multi", {'multispectral': True, 'descriptor_size': 256})]:
+        torch.manual_seed(0)
+        net = MultiPoint(cfg)
+        assert list(net.state_dict().keys()) == list(g[tag + "_keys"])
+        assert [str(tuple(v.shape)) for v in net.state_dict().values()] == list(g[tag + "_shapes"])
+        net = net.cuda().eval()
+        img = syn.images(81, 2, 64, 80)
+        data = {'image': cu(img), 'is_optical': torch.tensor([[True], [False]], device="cuda")}
+        with torch.no_grad():
+            out = net(data)
+        assert out['logits'] is None
+        # same seeded weights as the reference; cuDNN fp32 vs the reference's CPU convolutions
+        np.testing.assert_allclose(out['prob'].cpu().numpy(), g[tag + "_prob"], rtol=2e-3, atol=1e-6)
+        np.testing.assert_allclose(out['desc'].cpu().numpy(), g[tag + "_desc"], rtol=2e-3, atol=2e-5)
+        net.set_force_return_logits(True)
+        with torch.no_grad():
+            o2 = net(data)
+        assert o2['prob'] is None and o2['logits'].shape == (2, 65, 8, 10)
+        # given identical backbone outputs the tails match the oracle to 1e-5
+        np.testing.assert_allclose(out['prob'].cpu().numpy(), oracle.detector_head(o2['logits'].cpu().numpy()), rtol=RTOL, atol=1e-9)
+        with pytest.raises(ValueError):
+            net.set_force_return_logits(1)
+
+
+def test_pipeline_matches_stagewise_reference_chain(utils, oracle):
+    """The fused sync-free pipeline equals the stage-by-stage drop-in calls (what
+    predict_align_image_pair.py does) and the oracle chain on the same backbone outputs."""
+    from multipoint_b200.pipeline import KeypointPipeline
+    B, H, W, D = 2, 128, 160, 64
+    lg = syn.logits(701, 2 * B, H // 8, W // 8)
+    raw = syn.descriptor_map(702, 2 * B, D, H // 8, W // 8)
+    pipe = KeypointPipeline(None, nms=4, detection_threshold=0.015, topk=300)
+    ext = pipe.extract_from_backbone(cu(lg), cu(raw), H, W)
+    ea = {k: v[:B] for k, v in ext.items()}
+    eb = {k: v[B:] for k, v in ext.items()}
+    m = pipe.match(ea, eb)
+    prob = oracle.detector_head(lg)
+    desc = oracle.normalize_descriptors(raw)
+    kps, descs = [], []
+    for b in range(2 * B):
+        nms = oracle.box_nms(ext['prob'][b, 0].cpu().numpy(), 4, 0.015, keep_top_k=300)  # same heatmap bits as the GPU
+        kp = oracle.extract_keypoints(nms, 0.015)
+        n = int(ext['counts'][b])
+        np.testing.assert_array_equal(ext['keypoints'][b, :n].cpu().numpy(), kp)
+        np.testing.assert_array_equal(ext['prob_nms'][b, 0].cpu().numpy(), nms)
+        d = oracle.interpolate_descriptors(kp, desc[b], H, W)
+        np.testing.assert_allclose(ext['desc'][b, :n].cpu().numpy(), d, rtol=RTOL, atol=2e-7)
+        kps.append(kp); descs.append(ext['desc'][b, :n].cpu().numpy())
+    np.testing.assert_allclose(ext['prob'].cpu().numpy(), prob, rtol=RTOL, atol=1e-9)
+    for p in range(B):
+        wq, wt, wd = oracle.match_mutual(descs[p], descs[B + p], 'bf', f64=True, cross_check=True)
+        n = int(m['counts'][p])
+        np.testing.assert_array_equal(m['query'][p, :n].cpu().numpy(), wq)
+        np.testing.assert_array_equal(m['train'][p, :n].cpu().numpy(), wt)
+        np.testing.assert_allclose(m['distance'][p, :n].cpu().numpy(), wd, rtol=RTOL, atol=1e-6)

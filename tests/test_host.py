@@ -1,0 +1,162 @@
+"""CPU-only checks: the C-ABI library loads and exports every symbol include/multipoint_b200.h
+declares, the host-side mirror of the reference interface (homography sampling, masks, model
+layout, error behaviour) matches the fixtures frozen from the reference, and the product path
+fails loudly without a CUDA device instead of falling back."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, load_golden
+from multipoint_b200 import _lib
+from multipoint_b200 import synthetic as syn
+
+
+def test_abi_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "multipoint_b200.h")).read()
+    declared = set(re.findall(r"MP_API\s+[\w\s\*]+?\b(mp_\w+)\s*\(", header))
+    assert len(declared) >= 17
+    lib = _lib.load()                                  # loads without a GPU
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.mp_version() == 100
+    # size queries are pure host functions
+    assert lib.mp_box_nms_workspace_bytes(1, 512, 640) >= 512 * 640 * 12
+    assert lib.mp_match_workspace_bytes(1, 2048, 2048, 256) >= 2 * 2 * 2048 * 256 * 2
+    assert lib.mp_extract_keypoints_workspace_bytes(2, 512, 640) >= 2 * 512 * 640 // 8
+
+
+def test_abi_argument_errors_without_gpu():
+    lib = _lib.load()
+    rc = lib.mp_detector_head_f32(None, 1, 8, 8, None, None, None)
+    assert rc == _lib.MP_ERR_INVALID and "null" in _lib.last_error()
+    rc = lib.mp_box_nms_f32(None, 1, 8, 8, 4.0, -1.0, 0.1, 0, None, None, None, None, 0, None, 0, None)
+    assert rc == _lib.MP_ERR_UNSUPPORTED
+    with pytest.raises(NotImplementedError):
+        _lib.check(rc, "mp_box_nms_f32")
+    rc = lib.mp_nearest_f32(None, None, 4, None, None, 4, 1, 100, 0, 0, None, None, None, None, None, None, None, 0, None)
+    assert rc == _lib.MP_ERR_UNSUPPORTED and "D % 64 == 0" in _lib.last_error()
+    rc = lib.mp_warp_f32(None, 1, 1, 8, 8, None, None, None, 7, 0, None, None)
+    assert rc == _lib.MP_ERR_INVALID
+    with pytest.raises(ValueError):
+        _lib.check(rc, "mp_warp_f32")
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_no_cpu_fallback():
+    from multipoint_b200 import ops, utils
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.detector_head(torch.zeros(1, 65, 8, 8))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        utils.box_nms(torch.zeros(16, 16), 4, 0.015)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        utils.get_matches(np.zeros((4, 64), np.float32), np.zeros((4, 64), np.float32), 'bfmatcher', crossCheck=True)
+    # reference error behaviour that does not need a device
+    with pytest.raises(ValueError, match="either 2D"):
+        utils.box_nms(torch.zeros(3, 16, 16), 4, 0.015)
+    with pytest.raises(ValueError, match="unknown matching method"):
+        utils.get_matches(np.zeros((4, 64), np.float32), np.zeros((4, 64), np.float32), 'nope')
+    with pytest.raises(ValueError, match="non-negative"):
+        utils.ThresholdMatcher(threshold=-0.1)
+
+
+def test_product_does_not_import_the_oracle():
+    pkg = os.path.join(ROOT, "multipoint_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "mp_oracle" not in src and "import oracle" not in src and "ref_shim" not in src, f
+
+
+def test_sample_homography_and_valid_mask_match_reference():
+    from multipoint_b200 import utils
+    g = load_golden("homographies")
+    cfg_default = dict(utils.homography_adaptation_default_config['homographies'])
+    cfg_export = dict(translation=True, rotation=True, scaling=True, perspective=True, scaling_amplitude=0.2,
+                      perspective_amplitude_x=0.2, perspective_amplitude_y=0.2, patch_ratio=0.85, max_angle=1.57,
+                      allow_artifacts=True)
+    cfg_noart = dict(cfg_export, allow_artifacts=False, translation_overflow=0.05)
+    for tag, cfg in [("default", cfg_default), ("export", cfg_export), ("noart", cfg_noart), ("small", cfg_export)]:
+        shape = tuple(int(v) for v in g[tag + "_shape"])
+        seed, erosion = (int(v) for v in g[tag + "_seed"])
+        np.random.seed(seed)
+        want_masks = np.unpackbits(g[tag + "_mask"], axis=-1)[..., :shape[1]]
+        for i in range(len(g[tag + "_H"])):
+            Hm = utils.sample_homography(np.array(shape), **cfg)
+            np.testing.assert_array_equal(Hm, g[tag + "_H"][i])           # same RNG stream, same solver: bit-exact
+            mask = utils.compute_valid_mask(shape, Hm, erosion, True)
+            np.testing.assert_array_equal(mask != 0, want_masks[i] != 0)
+    Hm = g["small_H"][0]
+    np.testing.assert_array_equal(utils.compute_valid_mask((64, 80), Hm, 0, False) != 0,
+                                  np.unpackbits(g["small_mask_e0"], axis=-1)[..., :80] != 0)
+    np.testing.assert_array_equal(utils.compute_valid_mask((64, 80), Hm, 2, False) != 0,
+                                  np.unpackbits(g["small_mask_e2nb"], axis=-1)[..., :80] != 0)
+    np.testing.assert_array_equal(utils.warp_keypoints(g["wk_kp"], Hm), g["wk_out"])
+    np.testing.assert_array_equal(utils.filter_points(g["wk_out"], (64, 80)), g["wk_filtered"])
+    # pre-sampling num-1 homographies consumes the stream exactly like the reference's loop
+    cfg = utils._check_ha_config(dict(num=9, erosion_radius=3, homographies=cfg_export))
+    np.random.seed(3)
+    Hs, masks = utils.sample_adaptation_homographies((64, 80), cfg)
+    np.testing.assert_array_equal(Hs, g["small_H"])
+    np.testing.assert_array_equal(masks != 0, np.unpackbits(g["small_mask"], axis=-1)[..., :80] != 0)
+
+
+def test_normalized_warp_matrix_matches_restatement():
+    from multipoint_b200 import utils
+    g = load_golden("adaptation")
+    M = torch.from_numpy(g["H"].astype(np.float32))
+    np.testing.assert_allclose(utils.normalized_warp_matrix(M, (64, 80), (64, 80)).numpy(), g["A_warp"], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(utils.normalized_warp_matrix(torch.inverse(M), (64, 80), (64, 80)).numpy(), g["A_unwarp"], rtol=0, atol=1e-6)
+
+
+def test_config_handling_matches_reference():
+    from multipoint_b200 import utils
+    d = utils.dict_update({'a': {'b': 1, 'c': 2}, 'd': 3}, {'a': {'b': 5}, 'e': 6})
+    assert d == {'a': {'b': 5, 'c': 2}, 'd': 3, 'e': 6}
+    with pytest.raises(ValueError, match="num must be larger than 0"):
+        utils._check_ha_config({'num': 0})
+    with pytest.raises(ValueError, match="filter_size must be uneven"):
+        utils._check_ha_config({'filter_size': 2})
+    utils._check_ha_config({'num': 2})
+    assert utils.homography_adaptation_default_config['num'] == 100          # defaults are not mutated
+    w = utils.fix_model_weigth_keys({'module__encoder.0.weight': 1, 'x__y__head.bias': 2, 'plain': 3})
+    assert list(w.keys()) == ['encoder.0.weight', 'head.bias', 'plain']
+    f = utils.get_gaussian_filter(5)
+    assert f.weight.shape == (1, 1, 5, 5) and abs(float(f.weight.sum()) - 1.0) < 1e-6
+    x = torch.arange(2 * 3 * 4 * 6, dtype=torch.float32).reshape(2, 3, 4, 6)
+    s2d = utils.space_to_depth(x, 2)
+    assert s2d.shape == (2, 12, 2, 3)
+
+
+def test_model_layout_matches_reference_state_dict():
+    from multipoint_b200.models import MultiPoint
+    g = load_golden("model")
+    for tag, cfg in [("shipped", {'multispectral': False, 'descriptor_size': 64}), ("multi", {'multispectral': True, 'descriptor_size': 256})]:
+        torch.manual_seed(0)
+        net = MultiPoint(cfg)
+        assert list(net.state_dict().keys()) == list(g[tag + "_keys"])
+        assert [str(tuple(v.shape)) for v in net.state_dict().values()] == list(g[tag + "_shapes"])
+        assert sum(p.numel() for p in net.parameters()) == int(g[tag + "_nparams"])
+    net = MultiPoint({'multispectral': False, 'descriptor_size': 64})
+    net.train()
+    out = net({'image': torch.from_numpy(syn.images(1, 1, 32, 32))})          # training mode: logits only, pure torch
+    assert out['prob'] is None and out['logits'].shape == (1, 65, 4, 4) and out['desc'].shape == (1, 64, 4, 4)
+    with pytest.raises(ValueError):
+        net.set_force_return_logits("yes")
+
+
+def test_synthetic_inputs_are_reproducible():
+    a = syn.heatmap(31, 1, 64, 80)
+    assert syn.checksum(a) == syn.checksum(syn.heatmap(31, 1, 64, 80))
+    frac = float((syn.heatmap(5, 1, 512, 640) > 0.015).mean())
+    assert 0.1 < frac < 0.25
+    d1, d2 = syn.descriptor_sets(1, 50, 70, 64, 0.05, 3)
+    assert d1.shape == (50, 64) and d2.shape == (70, 64)
+    np.testing.assert_allclose(np.linalg.norm(d2, axis=1), 1.0, atol=1e-6)
+    batch = syn.image_pair_batch(2, 3, 32, 40)
+    assert batch['optical']['image'].shape == (3, 1, 32, 40) and batch['thermal']['is_optical'].sum() == 0
