@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""Benchmark of the keypoint extract-and-match path (BASELINE.json metric: image pairs/s at
+512x640, extract+match).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (library port)
+
+Own arm.  One process per GPU (torchrun for N>1), weak scaling: every rank runs the workload of
+BASELINE config 2 -- 64 synthetic 512x640 optical/thermal pairs, box NMS size 4, threshold 0.015,
+top-k 2048 -- followed by mutual-NN matching of each pair, on its own shard of pairs; there is no
+data-path collective (pairs are independent units).  A step is one pass over the 64
+pairs: MultiPoint forward for both spectra in one batch (cuDNN fp32 backbone, random-init weights
+with calibrated final BatchNorms so heatmaps are not degenerate) -> detector-head kernel -> NMS +
+top-k + ordered keypoints -> descriptor normalise (channels-last) -> descriptor sampling ->
+tcgen05 matcher.
+  value     pairs/s with the images already resident in HBM (CUDA events, max over ranks)
+  e2e       the same step from pinned host images: H2D of the images + the step + D2H of keypoints
+            and matches, through the public pipeline API
+  hot_path  the same without the cuDNN backbone (backbone outputs resident in HBM): the part this
+            repo implements; per-stage times and the roofline of its dominant kernel
+  cpu_baseline  (N=1) the reference's CPU chain for ONE pair on the host cores: torch CPU backbone +
+            oracle/reference_port.py (torch softmax / torchvision nms / grid_sample / cv2.BFMatcher)
+Reference arm: that same CPU chain, one pair per step, all host threads, rank 0 only.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H, W = 512, 640
+METRIC = "image_pairs_per_sec_512x640_extract_match"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--pairs", type=int, default=64, help="image pairs per rank per step")
+    ap.add_argument("--desc", type=int, default=256, help="descriptor size (256 = class default, 64 = shipped params.yaml)")
+    ap.add_argument("--topk", type=int, default=2048)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def model_config(desc):
+    # MultiPoint class defaults (multipoint/models/MultiPoint.py:9-23): two encoders, 256-d descriptors
+    return {'multispectral': True, 'descriptor_size': desc}
+
+
+def workload_config(args, extra=None):
+    cfg = {"workload": "config2+matching: %d synthetic 512x640 optical/thermal pairs per GPU per step, "
+                       "MultiPoint(multispectral, D=%d) fp32 cuDNN backbone, box NMS size 4 thr 0.015 top-k %d, "
+                       "bfmatcher crossCheck" % (args.pairs, args.desc, args.topk),
+           "pairs_per_gpu": args.pairs, "descriptor_size": args.desc, "topk": args.topk, "nms": 4,
+           "detection_threshold": 0.015, "weights": "random init (seed 0), final BatchNorms calibrated",
+           "l2_policy": "inputs larger than L2 (168 MB of images, 1.5 GB of backbone outputs per step)"}
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+# --------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_id):
+        self.gpu_id, self.proc, self.path = gpu_id, None, "/tmp/mp_bench_clocks_%d.csv" % os.getpid()
+
+    def start(self):
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu_id)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1])); mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[5:9]):
+                if val == "Active":
+                    reasons.add(name)
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------- CPU chain
+def cpu_reference_chain(net_cpu, pair_np, topk, threads):
+    """The reference's CPU path for one pair: two forward passes (torch CPU) + the library port of
+    box_nms / nonzero / interpolate_descriptors / get_matches.  Returns seconds and the match count."""
+    import cv2
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import reference_port as rp
+    torch.set_num_threads(threads)
+    cv2.setNumThreads(threads)
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        lo, ro = net_cpu.backbone_outputs({'image': torch.from_numpy(pair_np['optical']['image']),
+                                           'is_optical': torch.from_numpy(pair_np['optical']['is_optical'])})
+        lt, rt = net_cpu.backbone_outputs({'image': torch.from_numpy(pair_np['thermal']['image']),
+                                           'is_optical': torch.from_numpy(pair_np['thermal']['is_optical'])})
+        t1 = time.perf_counter()
+        kps, ds, matches = rp.pair_chain(torch.cat([lo, lt]), torch.cat([ro, rt]), H, W, 4, 0.015, topk)
+    t2 = time.perf_counter()
+    return t2 - t0, t1 - t0, len(matches), [len(k) for k in kps]
+
+
+def build_net(desc, device):
+    import torch
+    from multipoint_b200 import synthetic as syn
+    from multipoint_b200.models import MultiPoint
+    from multipoint_b200.pipeline import calibrate_random_init
+    torch.manual_seed(0)
+    net = MultiPoint(model_config(desc)).eval()
+    calib = syn.image_pair_batch(999, 2, H, W)
+    imgs = torch.from_numpy(__import__("numpy").concatenate([calib['optical']['image'], calib['thermal']['image']]))
+    opt = torch.tensor([[True], [True], [False], [False]])
+    net = net.to(device)
+    calibrate_random_init(net, imgs.to(device), is_optical=opt.to(device))
+    return net
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path on the host cores."""
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return 0
+    import torch
+    from multipoint_b200 import synthetic as syn
+    threads = os.cpu_count() or 1
+    net_cpu = build_net(args.desc, "cpu")
+    times = []
+    for i in range(args.warmup + args.steps):
+        pair = syn.image_pair_batch(5000 + i, 1, H, W)
+        sec, fwd, nm, nk = cpu_reference_chain(net_cpu, pair, args.topk, threads)
+        if i >= args.warmup:
+            times.append(sec)
+    ms = 1000.0 * sum(times) / len(times)
+    v = 1000.0 / ms
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, {"sample": "1 pair per step (bounded sample of the 64-pair workload)"}),
+            "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": threads, "kind": "port",
+                             "sample": "1 pair per step: torch CPU backbone x2 + oracle/reference_port.py "
+                                       "(torch softmax, torchvision batched_nms, grid_sample, cv2.BFMatcher crossCheck)"},
+            "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from multipoint_b200 import _lib, ops, parallel
+    from multipoint_b200 import synthetic as syn
+    from multipoint_b200.pipeline import KeypointPipeline
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    rank, local_rank, world = parallel.init_distributed("nccl")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    torch.backends.cudnn.allow_tf32 = False           # fp32 like the reference: no reduced precision
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.benchmark = True
+    K, Wm, P = args.steps, max(args.warmup, 3), args.pairs
+
+    net = build_net(args.desc, dev)
+    pipe = KeypointPipeline(net, nms=4, detection_threshold=0.015, topk=args.topk, metric='l2', cross_check=True)
+    batch = syn.image_pair_batch(1000 + rank, P, H, W)
+    host = {s: {k: torch.from_numpy(v).pin_memory() for k, v in batch[s].items() if k != 'valid_mask'} for s in ('optical', 'thermal')}
+    resident = {s: {k: v.to(dev) for k, v in host[s].items()} for s in host}
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    def timed(fn, steps, warm):
+        for _ in range(warm):
+            fn()
+        barrier(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(); barrier()
+        return max_over_ranks(e0.elapsed_time(e1) / steps)
+
+    # ---- value: whole step, images resident in HBM
+    out_holder = {}
+
+    def step_resident():
+        out_holder['r'] = pipe(resident)
+
+    gpu_uuid = None
+    try:
+        gpu_uuid = "GPU-" + str(torch.cuda.get_device_properties(local_rank).uuid)
+    except Exception:
+        pass
+    sampler = ClockSampler(gpu_uuid if gpu_uuid else local_rank)
+    for _ in range(Wm):
+        step_resident()
+    torch.cuda.synchronize()
+    sampler.start()
+    launches0 = _lib.launch_count()
+    ms_value = timed(step_resident, K, 0)
+    launches = _lib.launch_count() - launches0
+    clocks = sampler.stop()
+
+    # ---- e2e: pinned host images -> H2D -> step -> D2H of keypoints and matches
+    res = out_holder['r']
+    d2h_src = lambda r: [r['optical']['keypoints'], r['optical']['counts'], r['thermal']['keypoints'], r['thermal']['counts'],  # noqa: E731
+                         r['matches']['query'], r['matches']['train'], r['matches']['distance'], r['matches']['counts']]
+    pinned_out = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in d2h_src(res)]
+    h2d_bytes = sum(v.numel() * v.element_size() for s in host for v in host[s].values())
+    d2h_bytes = sum(t.numel() * t.element_size() for t in pinned_out)
+
+    def step_e2e():
+        data = {s: {k: v.to(dev, non_blocking=True) for k, v in host[s].items()} for s in host}
+        r = pipe(data)
+        for dst, src in zip(pinned_out, d2h_src(r)):
+            dst.copy_(src, non_blocking=True)
+
+    ms_e2e = timed(step_e2e, K, Wm)
+    n_matches = int(pinned_out[-1].sum())
+    n_kp = int(pinned_out[1].sum()) + int(pinned_out[3].sum())
+
+    # ---- hot path only: backbone outputs resident in HBM
+    both = {'image': torch.cat([resident['optical']['image'], resident['thermal']['image']]),
+            'is_optical': torch.cat([resident['optical']['is_optical'], resident['thermal']['is_optical']])}
+    with torch.no_grad():
+        logits, raw = net.backbone_outputs(both)
+    torch.cuda.synchronize()
+
+    def hot():
+        ext = pipe.extract_from_backbone(logits, raw, H, W)
+        ea = {k: v[:P] for k, v in ext.items()}
+        eb = {k: v[P:] for k, v in ext.items()}
+        out_holder['h'] = (ext, pipe.match(ea, eb))
+
+    ms_hot = timed(hot, K, Wm)
+    ext, _ = out_holder['h']
+    B2 = 2 * P
+    prob = ext['prob'].reshape(B2, H, W)
+    kp, cnt, desc_s = ext['keypoints'], ext['counts'], ext['desc']
+    stages = {
+        "detector_head": (lambda: ops.detector_head(logits), B2 * (65 * 5120 * 4 + H * W * 4)),
+        "nms_tile(+fixup launch)": (lambda: ops.box_nms(prob, 4, 0.015), B2 * 2 * H * W * 4),
+        "nms_full(top-k+keypoints)": (lambda: ops.box_nms(prob, 4, 0.015, keep_top_k=args.topk, want_keypoints=True, kp_cap=args.topk),
+                                      B2 * (2 * H * W * 4 + 20 * args.topk)),
+        "normalize_desc_nhwc": (lambda: ops.normalize_descriptors(raw, nchw=False, nhwc=True), B2 * 2 * 4 * args.desc * 5120),
+        "sample_descriptors": (lambda: ops.sample_descriptors(kp, ops.normalize_descriptors(raw, nchw=False, nhwc=True)[1], H, W, counts=cnt, channels_last=True), None),
+        "match(both directions+select)": (lambda: ops.match(desc_s[:P], desc_s[P:], metric='l2', kind='mutual', cross_check=True, n1=cnt[:P], n2=cnt[P:]), None),
+    }
+    kernels = {}
+    for name, (fn, nbytes) in stages.items():
+        ms = timed(fn, max(K, 10), 3)
+        kernels[name] = {"ms": ms}
+        if nbytes:
+            kernels[name]["algorithmic_GBps"] = nbytes / ms / 1e6
+    # sample_descriptors timed above includes the normalise it depends on; subtract
+    kernels["sample_descriptors"]["ms"] = max(0.0, kernels["sample_descriptors"]["ms"] - kernels["normalize_desc_nhwc"]["ms"])
+    kernels["sample_descriptors"]["algorithmic_GBps"] = B2 * (16 * args.topk * args.desc + 4 * args.topk * args.desc + 16 * args.topk) / max(kernels["sample_descriptors"]["ms"], 1e-6) / 1e6
+    flops = 2.0 * P * args.topk * args.topk * args.desc
+    kernels["match(both directions+select)"]["algorithmic_TFLOPs"] = flops / kernels["match(both directions+select)"]["ms"] / 1e9
+    kernels["match(both directions+select)"]["executed_TFLOPs"] = 6 * flops / kernels["match(both directions+select)"]["ms"] / 1e9
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    dom = "nms_tile(+fixup launch)"
+    roofline = {"kernel": "nms_tile_kernel<32,128,8> (timed as mp_box_nms_f32 without top-k: tile kernel + the fix-up launch that exits immediately)",
+                "bound": "hbm", "achieved": kernels[dom]["algorithmic_GBps"], "peak": hbm_peak, "unit": "GB/s",
+                "frac": kernels[dom]["algorithmic_GBps"] / hbm_peak,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
+                "algorithmic_bytes_per_launch": B2 * 2 * H * W * 4, "traffic": None}
+
+    line = {"metric": METRIC, "value": P * world * 1000.0 / ms_value, "unit": "pairs/s", "n_gpus": world, "steps": K, "warmup": Wm,
+            "ms_per_step": ms_value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": workload_config(args), "clocks": clocks,
+            "e2e": {"value": P * world * 1000.0 / ms_e2e, "unit": "pairs/s", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},
+            "gpu_launches": int(launches),
+            "hot_path": {"value": P * world * 1000.0 / ms_hot, "unit": "pairs/s", "ms_per_step": ms_hot,
+                         "note": "backbone outputs resident in HBM; everything after cuDNN", "stages": kernels},
+            "roofline": roofline,
+            "result_check": {"keypoints_per_step": n_kp, "matches_per_step": n_matches}}
+
+    if world == 1 and rank == 0 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        net_cpu = build_net(args.desc, "cpu")
+        pair = syn.image_pair_batch(5000, 1, H, W)
+        cpu_reference_chain(net_cpu, pair, args.topk, threads)          # warm-up (allocator, thread pools)
+        secs = [cpu_reference_chain(net_cpu, syn.image_pair_batch(5001 + i, 1, H, W), args.topk, threads) for i in range(2)]
+        sec = sum(s[0] for s in secs) / len(secs)
+        line["cpu_baseline"] = {"value": 1.0 / sec, "unit": "pairs/s", "cores": threads, "kind": "port",
+                                "sample": "1 pair (of the 64-pair step), mean of 2 runs after 1 warm-up: torch CPU backbone x2 + "
+                                          "oracle/reference_port.py (torch softmax, torchvision batched_nms, grid_sample, cv2.BFMatcher)",
+                                "seconds_per_pair": sec, "backbone_seconds": sum(s[1] for s in secs) / len(secs),
+                                "matches": secs[0][2], "keypoints": secs[0][3]}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

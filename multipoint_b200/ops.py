@@ -229,9 +229,23 @@ def match_threshold(d1, d2, threshold):
     return q, t, dist
 
 
+def _linspace_f32(n):
+    """linspace(-1, 1, n) in fp32 by ATen's scalar formula (one rounding per operation):
+    step = 2/(n-1); -1 + step*i below the midpoint, 1 - step*(n-1-i) from it on.  torch.linspace on
+    the CPU is vectorised and rounds differently per SIMD width, so the table is built here to be
+    the same bits on every host."""
+    if n == 1:
+        return np.array([-1.0], np.float32)
+    step = np.float32(np.float32(2.0) / np.float32(n - 1))
+    i = np.arange(n)
+    lo = np.float32(-1.0) + step * i.astype(np.float32)
+    hi = np.float32(1.0) - step * (n - 1 - i).astype(np.float32)
+    return np.where(i < n // 2, lo, hi).astype(np.float32)
+
+
 def linspace_tables(H, W, device):
-    """torch.linspace(-1,1,.) tables of kornia's create_meshgrid (normalised destination grid)."""
-    return (torch.linspace(-1, 1, W, dtype=torch.float32).to(device), torch.linspace(-1, 1, H, dtype=torch.float32).to(device))
+    """Normalised destination grid of kornia's create_meshgrid: (xs (W), ys (H)) device tensors."""
+    return torch.from_numpy(_linspace_f32(W)).to(device), torch.from_numpy(_linspace_f32(H)).to(device)
 
 
 def warp(src, A, mode='bilinear', padding='zeros', tables=None):

@@ -231,3 +231,32 @@ def test_homographic_adaptation_matches_restatement(oracle):
         np.testing.assert_allclose(oracle.warp_matrix(M, H, W), g["A_warp"][i], rtol=0, atol=1e-6)
         np.testing.assert_allclose(oracle.warp_matrix(np.linalg.inv(M).astype(np.float32), H, W),
                                    g["A_unwarp"][i], rtol=0, atol=1e-6)
+
+
+def test_reference_port_matches_reference_fixtures():
+    """oracle/reference_port.py (the library-level port bench.py times as the CPU baseline) gives
+    exactly what the real reference produced for the fixtures."""
+    import sys
+    import torch
+    from conftest import ROOT
+    sys.path.insert(0, ROOT + "/oracle")
+    import reference_port as rp
+    g = load_golden("heads")
+    np.testing.assert_array_equal(rp.detector_head(torch.from_numpy(g["logits"])).numpy(), g["prob"])
+    np.testing.assert_array_equal(rp.descriptor_head(torch.from_numpy(g["desc_in"])).numpy(), g["desc"])
+    g = load_golden("box_nms")
+    for seed, size, topk, quant, B in g["small_cases"]:
+        seed, topk, B = int(seed), int(topk), int(B)
+        hm = syn.heatmap(seed, B, 64, 80, quant=(quant or None))
+        tag = "small%d" % seed
+        want2 = dense_from_sparse(g[tag + "_2d_idx"], g[tag + "_2d_val"], hm.shape[-2:])
+        np.testing.assert_array_equal(rp.box_nms(torch.from_numpy(hm[0, 0]), size, 0.015, keep_top_k=topk).numpy(), want2)
+        if not (quant and topk):
+            want4 = dense_from_sparse(g[tag + "_4d_idx"], g[tag + "_4d_val"], hm.shape)
+            np.testing.assert_array_equal(rp.box_nms(torch.from_numpy(hm), size, 0.015, keep_top_k=topk).numpy(), want4)
+    g = load_golden("interpolate")
+    got = rp.interpolate_descriptors(torch.from_numpy(g["small_kp"]), torch.from_numpy(g["small_in"]), 40, 56)
+    np.testing.assert_array_equal(got.numpy(), g["small_out"])
+    g = load_golden("matching")
+    m = rp.get_matches_bf_crosscheck(g["m51_a"], g["m51_b"])
+    assert [x.queryIdx for x in m] == list(g["m51_bf_q"]) and [x.trainIdx for x in m] == list(g["m51_bf_t"])
