@@ -47,6 +47,7 @@ def parse_args():
     ap.add_argument("--desc", type=int, default=256, help="descriptor size (256 = class default, 64 = shipped params.yaml)")
     ap.add_argument("--topk", type=int, default=2048)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--only-value", action="store_true", help="time only the resident step (used under ncu)")
     return ap.parse_args()
 
 
@@ -251,6 +252,12 @@ def main():
     ms_value = timed(step_resident, K, 0)
     launches = _lib.launch_count() - launches0
     clocks = sampler.stop()
+
+    if args.only_value:
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": P * world * 1000.0 / ms_value, "unit": "pairs/s", "ms_per_step": ms_value,
+                              "gpu_launches": int(launches), "note": "--only-value run (profiling aid, not a bench line)"}))
+        return 0
 
     # ---- e2e: pinned host images -> H2D -> step -> D2H of keypoints and matches
     res = out_holder['r']

@@ -62,25 +62,29 @@ class KeypointPipeline:
 
 def calibrate_random_init(net, images, sigma=2.0, dustbin_bias=5.0, is_optical=None):
     """Make a randomly initialised MultiPoint produce non-degenerate outputs for benchmarks
-    (random init gives a flat heatmap ~1/65 > threshold everywhere).  Sets the
-    running statistics of the two final BatchNorms to the actual statistics of the pre-BN
-    activations on ``images`` and the detector BN affine to (sigma, +dustbin_bias on channel 64),
-    so logits ~ sigma*N(0,1) like the synthetic logits of multipoint_b200.synthetic.logits.
-    Weights stay random-init; only BN buffers / affine change."""
-    det, desc = net.detector_head_convolutions, net.descriptor_head_convolutions
-    assert isinstance(det[-1], torch.nn.BatchNorm2d), "needs final_batchnorm"
+    (with random weights the activations collapse to ~1e-5 variance, the
+    heatmap is flat ~1/65 > threshold everywhere and all descriptors coincide).  One forward pass in
+    training mode with momentum 1 sets every BatchNorm's running statistics to the statistics of
+    its own input on ``images`` (data-dependent init); the detector's final BatchNorm affine is then
+    set to (sigma, +dustbin_bias on channel 64) so logits ~ sigma*N(0,1) with a dominant dustbin,
+    like multipoint_b200.synthetic.logits.  Convolution weights stay random-init."""
+    bns = [m for m in net.modules() if isinstance(m, torch.nn.BatchNorm2d)]
+    old = [(m.momentum, m.training) for m in bns]
+    was_training = net.training
+    net.train()
+    for m in bns:
+        m.momentum = 1.0
     with torch.no_grad():
         data = {'image': images}
         if is_optical is not None:
             data['is_optical'] = is_optical
-        x = net.encode(data)
-        for head, scale, bias64 in ((det, sigma, dustbin_bias), (desc, 1.0, None)):
-            pre = head[:-1](x).float()
-            bn = head[-1]
-            bn.running_mean.copy_(pre.mean(dim=(0, 2, 3)))
-            bn.running_var.copy_(pre.var(dim=(0, 2, 3), unbiased=False))
-            bn.weight.fill_(scale)
-            bn.bias.zero_()
-            if bias64 is not None:
-                bn.bias[64] = bias64
+        net.backbone_outputs(data)
+        det = net.detector_head_convolutions[-1]
+        assert isinstance(det, torch.nn.BatchNorm2d), "needs final_batchnorm"
+        det.weight.fill_(sigma)
+        det.bias.zero_()
+        det.bias[64] = dustbin_bias
+    for m, (mom, _) in zip(bns, old):
+        m.momentum = mom
+    net.train(was_training)
     return net
