@@ -48,6 +48,8 @@ def parse_args():
     ap.add_argument("--topk", type=int, default=2048)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--only-value", action="store_true", help="time only the resident step (used under ncu)")
+    ap.add_argument("--only-hot", action="store_true",
+                    help="run only the post-backbone hot path on synthetic backbone outputs (used under ncu)")
     return ap.parse_args()
 
 
@@ -202,6 +204,34 @@ def main():
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.benchmark = True
     K, Wm, P = args.steps, max(args.warmup, 3), args.pairs
+
+    if args.only_hot:
+        # profiling aid: the hot path alone at the full batch size, on synthetic backbone outputs
+        # (logits ~ 2*N(0,1) with +5 on the dustbin, random descriptor maps), no cuDNN in the process
+        g = torch.Generator(device=dev).manual_seed(1234 + rank)
+        logits = torch.randn((2 * P, 65, H // 8, W // 8), generator=g, device=dev) * 2.0
+        logits[:, 64] += 5.0
+        raw = torch.randn((2 * P, args.desc, H // 8, W // 8), generator=g, device=dev)
+        pipe = KeypointPipeline(None, nms=4, detection_threshold=0.015, topk=args.topk, metric='l2', cross_check=True)
+
+        def hot_only():
+            ext = pipe.extract_from_backbone(logits, raw, H, W)
+            pipe.match({k: v[:P] for k, v in ext.items()}, {k: v[P:] for k, v in ext.items()})
+
+        for _ in range(Wm):
+            hot_only()
+        torch.cuda.synchronize()
+        l0 = _lib.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(K):
+            hot_only()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / K
+        print(json.dumps({"note": "--only-hot run (profiling aid, not a bench line)", "ms_per_step": ms,
+                          "pairs_per_s": P * 1000.0 / ms, "gpu_launches_per_step": (_lib.launch_count() - l0) // K}))
+        return 0
 
     net = build_net(args.desc, dev)
     pipe = KeypointPipeline(net, nms=4, detection_threshold=0.015, topk=args.topk, metric='l2', cross_check=True)

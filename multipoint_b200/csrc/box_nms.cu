@@ -86,6 +86,36 @@ __device__ __forceinline__ float nms_decide(float val, const NmsFootprint &fp, F
     return blocked ? val : s;
 }
 
+// Same decision for a pixel of the staged tile, with a candidate bitmap as pre-filter: the 2R+1
+// neighbours of one footprint row are one funnel-shifted 32-bit window of the bitmap row, so only
+// actual candidates (~15 % of the footprint) are fetched and compared.
+template <int EW, int BW>
+__device__ __forceinline__ float nms_decide_tile(float val, int ey, int ex, const float *v, const uint32_t *bm,
+                                                 const NmsFootprint &fp) {
+    const float s = -val;
+    const int R = fp.R;
+    const int bitpos = ex - R, w = bitpos >> 5, sh = bitpos & 31;
+    bool blocked = false;
+    for (int dy = -R; dy <= R; ++dy) {
+        const uint32_t *bw = bm + (ey + dy) * BW + w;
+        uint32_t win = __funnelshift_r(bw[0], bw[1], sh) & fp.rows[dy + R];
+        const float *vr = v + (ey + dy) * EW + bitpos;
+        while (win) {
+            const int bit = __ffs(win) - 1;
+            win &= win - 1;
+            const float nv = vr[bit];
+            if (nv == 0.f) continue;  // was a candidate, already suppressed
+            const float sn = fabsf(nv);
+            const int dx = bit - R;
+            const bool higher = sn > s || (sn == s && (dy < 0 || (dy == 0 && dx < 0)));
+            if (!higher) continue;
+            if (nv > 0.f) return 0.f;
+            blocked = true;
+        }
+    }
+    return blocked ? val : s;
+}
+
 template <int TH, int TW, int E, bool VEC>
 __global__ void __launch_bounds__(NMS_THREADS)
 nms_tile_kernel(const float *__restrict__ prob, float *__restrict__ out, int H, int W, float thr,
@@ -94,10 +124,14 @@ nms_tile_kernel(const float *__restrict__ prob, float *__restrict__ out, int H, 
     constexpr int EH = TH + 2 * E, EW = TW + 2 * E;
     static_assert(EW % 4 == 0 && E % 4 == 0 && TW % 4 == 0, "float4 staging needs 4-px alignment");
     static_assert(EH * EW < 65536, "list entries are uint16");
+    constexpr int BW = (EW + 31) / 32 + 1;                          // bitmap words per row (+1: 64-bit windows)
     extern __shared__ __align__(16) float smem[];
     float *v = smem;                                                // [EH][EW] signed state
-    uint16_t *list = reinterpret_cast<uint16_t *>(v + EH * EW);     // undecided positions
+    uint32_t *bm = reinterpret_cast<uint32_t *>(v + EH * EW);       // [EH][BW] candidate bitmap
+    uint16_t *list = reinterpret_cast<uint16_t *>(bm + EH * BW);    // undecided positions (ping)
+    uint16_t *list2 = list + EH * EW;                               // (pong)
     __shared__ int n_list;
+    __shared__ int n_next[3];
     __shared__ int warp_sums[NMS_THREADS / 32];
     __shared__ int bases[2];
 
@@ -107,7 +141,8 @@ nms_tile_kernel(const float *__restrict__ prob, float *__restrict__ out, int H, 
     const int gy0 = ty0 - E, gx0 = tx0 - E;
     const float *img = prob + (size_t)b * H * W;
     const int R = fp.R;
-    if (tid == 0) n_list = 0;
+    if (tid == 0) { n_list = 0; n_next[0] = n_next[1] = n_next[2] = 0; }
+    for (int i = tid; i < EH * BW; i += NMS_THREADS) bm[i] = 0;
     __syncthreads();
 
     // ---- 1. stage the tile + apron; threshold; encode: 0 = nothing, -s = undecided ----
@@ -131,10 +166,12 @@ nms_tile_kernel(const float *__restrict__ prob, float *__restrict__ out, int H, 
         }
         float c[4] = {val.x, val.y, val.z, val.w};
         const bool rows_ok = act && ey >= R && ey < EH - R;
+        uint32_t nib = 0;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const bool cand = c[j] > thr;  // strict, fp32 (utils.py:97); NaN is not a candidate
             c[j] = cand ? -c[j] : 0.f;
+            nib |= (uint32_t)cand << j;
             const int ex = 4 * q + j;
             const bool push = cand && rows_ok && ex >= R && ex < EW - R;
             const unsigned m = __ballot_sync(0xffffffffu, push);
@@ -145,26 +182,53 @@ nms_tile_kernel(const float *__restrict__ prob, float *__restrict__ out, int H, 
                 if (push) list[base + __popc(m & ((1u << lane) - 1))] = (uint16_t)(ey * EW + ex);
             }
         }
-        if (act) *reinterpret_cast<float4 *>(v + ey * EW + 4 * q) = make_float4(c[0], c[1], c[2], c[3]);
+        if (act) {
+            *reinterpret_cast<float4 *>(v + ey * EW + 4 * q) = make_float4(c[0], c[1], c[2], c[3]);
+            if (nib) atomicOr(&bm[ey * BW + (q >> 3)], nib << ((4 * q) & 31));
+        }
     }
     __syncthreads();
 
     // ---- 2. iterate to the local fixed point ----
-    const int n = n_list;
-    while (true) {
-        bool changed = false;
-        for (int i = tid; i < n; i += NMS_THREADS) {
-            const int e = list[i];
-            const float val = v[e];
-            if (val >= 0.f) continue;
-            const float *centre = v + e;
-            const float nv = nms_decide(val, fp, [&](int dy, int dx) { return centre[dy * EW + dx]; });
-            if (nv != val) {
-                v[e] = nv;
-                changed = true;
+    // Every round re-packs the still-undecided pixels into the other list so warps stay dense
+    // (after two rounds only ~15 % are left).  Counters rotate over three slots: slot (r+1)%3 is
+    // cleared at the top of round r, when every thread has long since read it (round r-2).
+    {
+        int n = n_list;
+        uint16_t *cur = list, *nxt = list2;
+        for (int round = 0; n > 0; ++round) {
+            int *cnt = &n_next[round % 3];
+            if (tid == 0) n_next[(round + 1) % 3] = 0;
+            bool changed = false;
+            for (int i0 = 0; i0 < n; i0 += NMS_THREADS) {
+                const int i = i0 + tid;
+                bool still = false;
+                int e = 0;
+                if (i < n) {
+                    e = cur[i];
+                    const float val = v[e];
+                    const int ey = e / EW, ex = e - ey * EW;
+                    const float nv = nms_decide_tile<EW, BW>(val, ey, ex, v, bm, fp);
+                    if (nv != val) {
+                        v[e] = nv;
+                        changed = true;
+                    } else {
+                        still = true;
+                    }
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, still);
+                if (m) {
+                    int base = 0;
+                    if (lane == (__ffs(m) - 1)) base = atomicAdd(cnt, __popc(m));
+                    base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+                    if (still) nxt[base + __popc(m & ((1u << lane) - 1))] = (uint16_t)e;
+                }
             }
+            const bool any = __syncthreads_or(changed);
+            n = *cnt;
+            uint16_t *tmp = cur; cur = nxt; nxt = tmp;
+            if (!any) break;  // what is left depends on pixels outside the apron
         }
-        if (!__syncthreads_or(changed)) break;
     }
 
     // ---- 3. write the interior once; queue survivors and unresolved pixels ----
@@ -425,7 +489,8 @@ static int launch_tile(const float *prob, float *out, int B, int H, int W, float
                        uint2 *surv, int *surv_count, uint32_t *work, int *work_count, int cap, bool vec,
                        cudaStream_t s) {
     constexpr int EH = TH + 2 * E, EW = TW + 2 * E;
-    constexpr size_t smem = (size_t)EH * EW * (sizeof(float) + sizeof(uint16_t));
+    constexpr int BW = (EW + 31) / 32 + 1;
+    constexpr size_t smem = (size_t)EH * EW * (sizeof(float) + 2 * sizeof(uint16_t)) + (size_t)EH * BW * sizeof(uint32_t);
     dim3 grid((W + TW - 1) / TW, (H + TH - 1) / TH, B);
     if (vec) {
         auto k = nms_tile_kernel<TH, TW, E, true>;

@@ -118,9 +118,11 @@ match_top2_simt_kernel(const float *__restrict__ a, const int32_t *__restrict__ 
 }
 
 // ------------------------------------------------------------------ flag near-ties
+// One list of flagged rows per (pair, side) so the recheck can share the other set's rows
+// between the flagged queries of a group.  group = 2*pair + side; capacity N rows each.
 __global__ void match_flag_kernel(const Top2 *__restrict__ top, int N, int P, const unsigned *__restrict__ max_a,
-                                  const unsigned *__restrict__ max_b, int metric, float eps_rel, int side,
-                                  int32_t *__restrict__ idx_out, uint2 *__restrict__ flagged, int *__restrict__ n_flagged) {
+                                  const unsigned *__restrict__ max_b, int metric, float eps_rel, float pack_rel, int side,
+                                  int32_t *__restrict__ idx_out, int32_t *__restrict__ flagged, int *__restrict__ n_flagged) {
     const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= (long long)P * N) return;
     const int p = (int)(g / N);
@@ -128,27 +130,132 @@ __global__ void match_flag_kernel(const Top2 *__restrict__ top, int N, int P, co
     idx_out[g] = t.best_idx;
     if (t.best_idx < 0) return;
     const float ma = __uint_as_float(max_a[p]), mb = __uint_as_float(max_b[p]);
-    const float eps = eps_rel * fmaxf(ma * mb, 1e-30f);
+    const float eps = eps_rel * fmaxf(ma * mb, 1e-30f) +
+                      pack_rel * 2.f * (1.002f * ma * mb + (metric == MP_METRIC_L2 ? 0.5f * mb * mb : 0.f));
     bool flag = (t.second_idx >= 0) && !(t.best - t.second >= 2.f * eps);  // also catches NaN keys
     if (metric == MP_METRIC_NN && t.best >= 1.f - eps && t.second_idx >= 0) flag = true;  // clip(.,-1,1) ties
-    if (flag) flagged[atomicAdd(n_flagged, 1)] = make_uint2((uint32_t)(p * 2 + side), (uint32_t)(g - (long long)p * N));
+    if (flag) flagged[(size_t)p * N + atomicAdd(n_flagged + 2 * p + side, 1)] = (int32_t)(g - (long long)p * N);
 }
 
 // ------------------------------------------------------------------ exact recheck
-// One CTA per flagged row: fp64 key against every row of the other set; first minimum wins.
+// fp64 key of each flagged row against every row of the other set; first minimum wins.
 //   NN: key = -clip(a.b, -1, 1)      L2: key = sum (a-b)^2       (monotone in the distance)
-__global__ void __launch_bounds__(256)
+// grid (2P groups, RK_Z): a CTA takes chunks of RK_ROWS flagged rows of its group.  The chunk's
+// query rows live in registers as doubles (lane l holds elements l, l+32, ...); each warp walks
+// the other set's rows with coalesced 128 B loads and reduces RK_ROWS partial sums per row with a
+// halving exchange (18 shuffles instead of 80), so row r's total lands in the lanes with
+// ((lane >> 2) & 7) == r.
+constexpr int RK_ROWS = 8, RK_Z = 4, RK_WARPS = 8, RK_MAXD = 256;
+
+template <int DPL>  // elements per lane: D <= 32*DPL
+__global__ void __launch_bounds__(RK_WARPS * 32)
 match_recheck_kernel(const float *__restrict__ d1, const int32_t *__restrict__ n1, int N1,
                      const float *__restrict__ d2, const int32_t *__restrict__ n2, int N2, int D, int metric,
-                     const uint2 *__restrict__ flagged, const int *__restrict__ n_flagged,
-                     int32_t *__restrict__ idx12, int32_t *__restrict__ idx21) {
+                     const int32_t *__restrict__ flagged1, const int32_t *__restrict__ flagged2,
+                     const int *__restrict__ n_flagged, int32_t *__restrict__ idx12, int32_t *__restrict__ idx21) {
+    __shared__ double red_key[RK_WARPS][RK_ROWS];
+    __shared__ int red_idx[RK_WARPS][RK_ROWS];
+    const int group = blockIdx.x, p = group >> 1, side = group & 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int count = n_flagged[group];
+    const int NA = side == 0 ? N1 : N2, NB = side == 0 ? N2 : N1;
+    const float *A = side == 0 ? d1 + (size_t)p * N1 * D : d2 + (size_t)p * N2 * D;
+    const float *Bm = side == 0 ? d2 + (size_t)p * N2 * D : d1 + (size_t)p * N1 * D;
+    const int32_t *rows = (side == 0 ? flagged1 : flagged2) + (size_t)p * NA;
+    int32_t *dst = side == 0 ? idx12 + (size_t)p * N1 : idx21 + (size_t)p * N2;
+    const int nb = side == 0 ? (n2 ? min(n2[p], N2) : N2) : (n1 ? min(n1[p], N1) : N1);
+
+    for (int c0 = blockIdx.y * RK_ROWS; c0 < count; c0 += RK_Z * RK_ROWS) {
+        double a[RK_ROWS][DPL];
+#pragma unroll
+        for (int r = 0; r < RK_ROWS; ++r) {
+            const int row = c0 + r < count ? rows[c0 + r] : -1;
+#pragma unroll
+            for (int i = 0; i < DPL; ++i) {
+                const int k = lane + 32 * i;
+                a[r][i] = (row >= 0 && k < D) ? (double)A[(size_t)row * D + k] : 0.0;
+            }
+        }
+        double best = INFINITY;
+        int bidx = 0x7fffffff;
+        for (int j = warp; j < nb; j += RK_WARPS) {
+            double b[DPL];
+#pragma unroll
+            for (int i = 0; i < DPL; ++i) {
+                const int k = lane + 32 * i;
+                b[i] = k < D ? (double)__ldg(Bm + (size_t)j * D + k) : 0.0;
+            }
+            double acc[RK_ROWS];
+#pragma unroll
+            for (int r = 0; r < RK_ROWS; ++r) {
+                double s = 0.0;
+                if (metric == MP_METRIC_NN) {
+#pragma unroll
+                    for (int i = 0; i < DPL; ++i) s = fma(a[r][i], b[i], s);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < DPL; ++i) { const double df = a[r][i] - b[i]; s = fma(df, df, s); }
+                }
+                acc[r] = s;
+            }
+            // halving exchange: after the 3 steps each lane holds the partial of one row
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {  // step 1: partner lane^16, keep rows [0,4) or [4,8)
+                const bool up = lane & 16;
+                const double send = up ? acc[r] : acc[r + 4], keep = up ? acc[r + 4] : acc[r];
+                acc[r] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+            }
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {  // step 2: lane^8
+                const bool up = lane & 8;
+                const double send = up ? acc[r] : acc[r + 2], keep = up ? acc[r + 2] : acc[r];
+                acc[r] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+            }
+            {  // step 3: lane^4
+                const bool up = lane & 4;
+                const double send = up ? acc[0] : acc[1], keep = up ? acc[1] : acc[0];
+                acc[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+            }
+            acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], 2);
+            acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], 1);
+            // acc[0] is now the total of row ((lane>>4)&1)*4 + ((lane>>3)&1)*2 + ((lane>>2)&1)
+            double key = acc[0];
+            if (metric == MP_METRIC_NN) key = -fmin(1.0, fmax(-1.0, key));
+            if (key < best) { best = key; bidx = j; }  // ascending j per warp: first minimum
+        }
+        // lanes 4r..4r+3 (in the bit order above) all hold row r's result; publish one per warp
+        const int r_of_lane = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+        __syncthreads();
+        if ((lane & 3) == 0) { red_key[warp][r_of_lane] = best; red_idx[warp][r_of_lane] = bidx; }
+        __syncthreads();
+        if (threadIdx.x < RK_ROWS && c0 + threadIdx.x < count) {
+            double bk = INFINITY;
+            int bi = 0x7fffffff;
+            for (int w = 0; w < RK_WARPS; ++w) {
+                const double k = red_key[w][threadIdx.x];
+                const int i = red_idx[w][threadIdx.x];
+                if (k < bk || (k == bk && i < bi)) { bk = k; bi = i; }
+            }
+            dst[rows[c0 + threadIdx.x]] = bi == 0x7fffffff ? -1 : bi;
+        }
+    }
+}
+
+// any D (> 256): one CTA per flagged row, threads stride over the other set's rows
+__global__ void __launch_bounds__(256)
+match_recheck_generic_kernel(const float *__restrict__ d1, const int32_t *__restrict__ n1, int N1,
+                             const float *__restrict__ d2, const int32_t *__restrict__ n2, int N2, int D, int metric,
+                             const int32_t *__restrict__ flagged1, const int32_t *__restrict__ flagged2,
+                             const int *__restrict__ n_flagged, int32_t *__restrict__ idx12, int32_t *__restrict__ idx21) {
     extern __shared__ double arow[];  // [D]
     __shared__ double red_key[256];
     __shared__ int red_idx[256];
-    const int total = *n_flagged;
-    for (int item = blockIdx.x; item < total; item += gridDim.x) {
-        const uint2 f = flagged[item];
-        const int p = (int)(f.x >> 1), side = (int)(f.x & 1), row = (int)f.y;
+    const int group = blockIdx.x, p = group >> 1, side = group & 1;
+    const int count = n_flagged[group];
+    const int NA = side == 0 ? N1 : N2;
+    const int32_t *rows = (side == 0 ? flagged1 : flagged2) + (size_t)p * NA;
+    for (int item = blockIdx.y; item < count; item += gridDim.y) {
+        const int row = rows[item];
         const float *a = side == 0 ? d1 + ((size_t)p * N1 + row) * D : d2 + ((size_t)p * N2 + row) * D;
         const float *b = side == 0 ? d2 + (size_t)p * N2 * D : d1 + (size_t)p * N1 * D;
         const int nb = side == 0 ? (n2 ? min(n2[p], N2) : N2) : (n1 ? min(n1[p], N1) : N1);
@@ -159,17 +266,14 @@ match_recheck_kernel(const float *__restrict__ d1, const int32_t *__restrict__ n
         int bidx = 0x7fffffff;
         for (int j = threadIdx.x; j < nb; j += blockDim.x) {
             const float *bj = b + (size_t)j * D;
-            double key;
+            double key = 0.0;
             if (metric == MP_METRIC_NN) {
-                double dot = 0.0;
-                for (int c = 0; c < D; ++c) dot += arow[c] * (double)bj[c];
-                key = -fmin(1.0, fmax(-1.0, dot));
+                for (int c = 0; c < D; ++c) key = fma(arow[c], (double)bj[c], key);
+                key = -fmin(1.0, fmax(-1.0, key));
             } else {
-                double s = 0.0;
-                for (int c = 0; c < D; ++c) { const double df = arow[c] - (double)bj[c]; s += df * df; }
-                key = s;
+                for (int c = 0; c < D; ++c) { const double df = arow[c] - (double)bj[c]; key = fma(df, df, key); }
             }
-            if (key < best) { best = key; bidx = j; }  // ascending j per thread: first minimum
+            if (key < best) { best = key; bidx = j; }
         }
         red_key[threadIdx.x] = best;
         red_idx[threadIdx.x] = bidx;
@@ -380,14 +484,15 @@ MatchLayout::MatchLayout(int P, int N1, int N2, int D) {
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
     const size_t r1 = (size_t)P * N1, r2 = (size_t)P * N2;
-    scalars = take(sizeof(unsigned) * (2 * (size_t)P + 4));
+    scalars = take(sizeof(unsigned) * (4 * (size_t)P + 4));
     norms1 = take(sizeof(float) * r1);
     norms2 = take(sizeof(float) * r2);
     top12 = take(sizeof(Top2) * r1);
     top21 = take(sizeof(Top2) * r2);
     idx12 = take(sizeof(int32_t) * r1);
     idx21 = take(sizeof(int32_t) * r2);
-    flagged = take(sizeof(uint2) * (r1 + r2));
+    flagged1 = take(sizeof(int32_t) * r1);
+    flagged2 = take(sizeof(int32_t) * r2);
     train_tmp = take(sizeof(int32_t) * r1);
     dist_tmp = take(sizeof(float) * r1);
     hi1 = take(sizeof(__nv_bfloat16) * r1 * D);
@@ -406,13 +511,13 @@ static int run_nearest(const float *d1, const int32_t *n1, int N1, const float *
     float *norms1 = (float *)(ws + L.norms1), *norms2 = (float *)(ws + L.norms2);
     Top2 *top12 = (Top2 *)(ws + L.top12), *top21 = (Top2 *)(ws + L.top21);
     int32_t *idx12 = (int32_t *)(ws + L.idx12), *idx21 = (int32_t *)(ws + L.idx21);
-    uint2 *flagged = (uint2 *)(ws + L.flagged);
+    int32_t *flagged1 = (int32_t *)(ws + L.flagged1), *flagged2 = (int32_t *)(ws + L.flagged2);
     const bool tensor = algo == MP_ALGO_TENSOR;
     __nv_bfloat16 *hi1 = tensor ? (__nv_bfloat16 *)(ws + L.hi1) : nullptr, *mid1 = (__nv_bfloat16 *)(ws + L.mid1);
     __nv_bfloat16 *hi2 = tensor ? (__nv_bfloat16 *)(ws + L.hi2) : nullptr, *mid2 = (__nv_bfloat16 *)(ws + L.mid2);
     const int use_bias = metric == MP_METRIC_L2;
 
-    MP_CUDA_OK(cudaMemsetAsync(scal, 0, sizeof(unsigned) * (2 * (size_t)P + 4), s));
+    MP_CUDA_OK(cudaMemsetAsync(scal, 0, sizeof(unsigned) * (4 * (size_t)P + 4), s));
     const long long r1 = (long long)P * N1, r2 = (long long)P * N2;
     match_prep_kernel<<<(unsigned)((r1 + 7) / 8), 256, 0, s>>>(d1, n1, N1, D, P, norms1, max1, hi1, mid1);
     MP_LAUNCH_OK();
@@ -420,9 +525,9 @@ static int run_nearest(const float *d1, const int32_t *n1, int N1, const float *
     MP_LAUNCH_OK();
 
     if (tensor) {
-        int rc = match_top2_tensor(hi1, mid1, n1, N1, hi2, mid2, n2, N2, P, D, norms2, use_bias, top12, s);
+        int rc = match_top2_tensor(hi1, mid1, n1, N1, hi2, mid2, n2, N2, P, D, norms2, use_bias, max1, max2, top12, s);
         if (rc != MP_OK) return rc;
-        rc = match_top2_tensor(hi2, mid2, n2, N2, hi1, mid1, n1, N1, P, D, norms1, use_bias, top21, s);
+        rc = match_top2_tensor(hi2, mid2, n2, N2, hi1, mid1, n1, N1, P, D, norms1, use_bias, max2, max1, top21, s);
         if (rc != MP_OK) return rc;
     } else {
         dim3 g1((N1 + ST_ROWS - 1) / ST_ROWS, P), g2((N2 + ST_ROWS - 1) / ST_ROWS, P);
@@ -431,12 +536,22 @@ static int run_nearest(const float *d1, const int32_t *n1, int N1, const float *
         match_top2_simt_kernel<<<g2, ST_ROWS, 0, s>>>(d2, n2, N2, d1, n1, N1, D, norms1, use_bias, top21);
         MP_LAUNCH_OK();
     }
-    const float eps_rel = tensor ? MATCH_EPS_TENSOR : MATCH_EPS_SIMT;
-    match_flag_kernel<<<(unsigned)((r1 + 255) / 256), 256, 0, s>>>(top12, N1, P, max1, max2, metric, eps_rel, 0, idx12, flagged, n_flagged);
+    const float eps_rel = tensor ? MATCH_EPS_TENSOR : MATCH_EPS_SIMT, pack_rel = tensor ? MATCH_PACK_REL : 0.f;
+    match_flag_kernel<<<(unsigned)((r1 + 255) / 256), 256, 0, s>>>(top12, N1, P, max1, max2, metric, eps_rel, pack_rel, 0, idx12, flagged1, n_flagged);
     MP_LAUNCH_OK();
-    match_flag_kernel<<<(unsigned)((r2 + 255) / 256), 256, 0, s>>>(top21, N2, P, max2, max1, metric, eps_rel, 1, idx21, flagged, n_flagged);
+    match_flag_kernel<<<(unsigned)((r2 + 255) / 256), 256, 0, s>>>(top21, N2, P, max2, max1, metric, eps_rel, pack_rel, 1, idx21, flagged2, n_flagged);
     MP_LAUNCH_OK();
-    match_recheck_kernel<<<num_sms() * 4, 256, sizeof(double) * D, s>>>(d1, n1, N1, d2, n2, N2, D, metric, flagged, n_flagged, idx12, idx21);
+    if (D <= RK_MAXD) {
+        dim3 grid(2 * P, RK_Z);
+#define MP_RECHECK(DPL) match_recheck_kernel<DPL><<<grid, RK_WARPS * 32, 0, s>>>(d1, n1, N1, d2, n2, N2, D, metric, flagged1, flagged2, n_flagged, idx12, idx21)
+        if (D <= 64) MP_RECHECK(2);
+        else if (D <= 128) MP_RECHECK(4);
+        else MP_RECHECK(8);
+#undef MP_RECHECK
+    } else {
+        dim3 grid(2 * P, 32);
+        match_recheck_generic_kernel<<<grid, 256, sizeof(double) * D, s>>>(d1, n1, N1, d2, n2, N2, D, metric, flagged1, flagged2, n_flagged, idx12, idx21);
+    }
     MP_LAUNCH_OK();
     return MP_OK;
 }

@@ -27,16 +27,20 @@ __device__ __forceinline__ void top2_update(Top2 &t, float key, int idx) {
 //          accumulation in the tensor core over <= 48 MMAs adds <= ~1e-5  -> 4e-5 with margin
 //  simt  : fp32 FMA chain over D <= 4096 terms                              -> 4e-5 as well
 constexpr float MATCH_EPS_TENSOR = 4e-5f;
+// the tensor epilogue packs the column index into the 5 low mantissa bits of (key + C), C <= 1.002|a||b| + |b|^2/2:
+// an extra absolute error of 2^-18 * 2C, added to the bound by the flag kernel
+constexpr float MATCH_PACK_REL = 3.8147e-6f;  // 2^-18
 constexpr float MATCH_EPS_SIMT = 4e-5f;
 
 struct MatchLayout {
-    size_t scalars, norms1, norms2, top12, top21, idx12, idx21, flagged, train_tmp, dist_tmp, hi1, mid1, hi2, mid2, total;
+    size_t scalars, norms1, norms2, top12, top21, idx12, idx21, flagged1, flagged2, train_tmp, dist_tmp, hi1, mid1, hi2, mid2, total;
     MatchLayout(int P, int N1, int N2, int D);
 };
 
 // match_tc.cu: rows of A (hi/mid bf16 planes, (P,NA,D)) against rows of B; writes top[(P,NA)].
 int match_top2_tensor(const __nv_bfloat16 *a_hi, const __nv_bfloat16 *a_mid, const int32_t *na, int NA,
                       const __nv_bfloat16 *b_hi, const __nv_bfloat16 *b_mid, const int32_t *nb, int NB, int P, int D,
-                      const float *norms_b, int use_bias, Top2 *top, cudaStream_t stream);
+                      const float *norms_b, int use_bias, const unsigned *max_a, const unsigned *max_b, Top2 *top,
+                      cudaStream_t stream);
 
 }  // namespace mp

@@ -125,7 +125,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 match_top2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_mid,
                      const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_mid,
                      const int32_t *__restrict__ na, int NA, const int32_t *__restrict__ nb, int NB,
-                     const float *__restrict__ norms_b, int use_bias, Top2 *__restrict__ top) {
+                     const float *__restrict__ norms_b, int use_bias, const unsigned *__restrict__ max_a,
+                     const unsigned *__restrict__ max_b, Top2 *__restrict__ top) {
     using L = TcSmem<KB>;
     constexpr int S = L::B_STAGES;
     extern __shared__ uint8_t smem_raw[];
@@ -225,43 +226,72 @@ match_top2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
         }
     } else {
         // ===================== epilogue: running arg-top-2 per row =====================
+        // Keys are made positive (key + C > 0) so their fp32 bit patterns order like unsigned
+        // integers, and the column's position inside its 32-column chunk replaces the 5 lowest
+        // mantissa bits: one integer max then carries value and index together.  Truncation costs
+        // 2^-18 relative (included in MATCH_EPS_TENSOR); equal packed keys prefer the lower column.
         const int quarter = warp & 3;  // TMEM lane quarter this warp may access
         const int row = quarter * 32 + lane;
-        Top2 best;
-        best.best = -INFINITY; best.second = -INFINITY; best.best_idx = -1; best.second_idx = -1;
+        const float ma = __uint_as_float(max_a[p]), mb = __uint_as_float(max_b[p]);
+        const float C = 1.002f * ma * mb + (use_bias ? 0.5f * mb * mb : 0.f) + 1e-30f;
         const float *bias = norms_b + (size_t)p * NB;
+        uint32_t best = 0, second = 0;          // packed keys; 0 = nothing yet
+        int best_chunk = -1, second_chunk = -1;  // global chunk index (32 columns each)
         for (int nt = 0; nt < n_tiles; ++nt) {
             const int t = nt % TC_ACC_STAGES;
             mbar_wait(bar_acc_full(t), (nt / TC_ACC_STAGES) & 1);
             tc_fence_after();
             const int n0 = nt * TC_BN;
-            const bool full_tile = n0 + TC_BN <= n_b;
 #pragma unroll 1
             for (int c = 0; c < TC_BN / 32; ++c) {
+                const int col0 = n0 + c * 32;
+                if (col0 >= n_b) break;
                 float v[32];
                 tc_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(t * TC_BN + c * 32), v);
-                const int col0 = n0 + c * 32;
-                if (use_bias) {
+                // per-column additive term: C (NN) or C - |b|^2/2 (L2); one coalesced load + shuffles
+                float add_lane = C;
+                if (use_bias && col0 + lane < n_b) add_lane = fmaf(-0.5f, __ldg(bias + col0 + lane), C);
+                const bool full = col0 + 32 <= n_b;
+                uint32_t b4[4] = {0, 0, 0, 0}, s4[4] = {0, 0, 0, 0};
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (full_tile || col0 + j < n_b) v[j] -= 0.5f * __ldg(bias + col0 + j);
+                for (int j = 0; j < 32; ++j) {
+                    const float add = use_bias ? __shfl_sync(0xffffffffu, add_lane, j) : C;
+                    uint32_t x = (__float_as_uint(v[j] + add) & ~31u) | (uint32_t)(31 - j);
+                    if (!full && col0 + j >= n_b) x = 0;
+                    s4[j & 3] = max(s4[j & 3], min(x, b4[j & 3]));
+                    b4[j & 3] = max(b4[j & 3], x);
                 }
-                if (full_tile) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) top2_update(best, v[j], col0 + j);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (col0 + j < n_b) top2_update(best, v[j], col0 + j);
-                }
+                // merge the four accumulators, then into the running pair
+                uint32_t cb = max(b4[0], b4[1]), cs = max(min(b4[0], b4[1]), max(s4[0], s4[1]));
+                const uint32_t cb2 = max(b4[2], b4[3]), cs2 = max(min(b4[2], b4[3]), max(s4[2], s4[3]));
+                cs = max(min(cb, cb2), max(cs, cs2));
+                cb = max(cb, cb2);
+                const int chunk = col0 >> 5;
+                const uint32_t old_best = best, old_second = second;
+                const int old_best_chunk = best_chunk;
+                best = max(old_best, cb);
+                second = max(min(old_best, cb), max(old_second, cs));
+                if (best != old_best) best_chunk = chunk;
+                if (second != old_second) second_chunk = (second == old_best && best != old_best) ? old_best_chunk : chunk;
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_acc_empty(t));
         }
         if (m0 + row < NA) {
-            if (m0 + row >= n_a) { best.best = -INFINITY; best.second = -INFINITY; best.best_idx = -1; best.second_idx = -1; }
-            top[(size_t)p * NA + m0 + row] = best;
+            Top2 out;
+            out.best = -INFINITY; out.second = -INFINITY; out.best_idx = -1; out.second_idx = -1;
+            if (m0 + row < n_a) {
+                if (best_chunk >= 0) {
+                    out.best_idx = best_chunk * 32 + 31 - (int)(best & 31u);
+                    out.best = __uint_as_float(best & ~31u) - C;
+                }
+                if (second_chunk >= 0) {
+                    out.second_idx = second_chunk * 32 + 31 - (int)(second & 31u);
+                    out.second = __uint_as_float(second & ~31u) - C;
+                }
+            }
+            top[(size_t)p * NA + m0 + row] = out;
         }
     }
 
@@ -314,18 +344,19 @@ static int make_operand_map(CUtensorMap *map, const __nv_bfloat16 *ptr, int P, i
 template <int KB>
 static int launch_tc(const CUtensorMap &ah, const CUtensorMap &am, const CUtensorMap &bh, const CUtensorMap &bm,
                      const int32_t *na, int NA, const int32_t *nb, int NB, int P, const float *norms_b, int use_bias,
-                     Top2 *top, cudaStream_t s) {
+                     const unsigned *max_a, const unsigned *max_b, Top2 *top, cudaStream_t s) {
     auto k = match_top2_tc_kernel<KB>;
     MP_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcSmem<KB>::TOTAL));
     dim3 grid((NA + TC_BM - 1) / TC_BM, P);
-    k<<<grid, TC_THREADS, TcSmem<KB>::TOTAL, s>>>(ah, am, bh, bm, na, NA, nb, NB, norms_b, use_bias, top);
+    k<<<grid, TC_THREADS, TcSmem<KB>::TOTAL, s>>>(ah, am, bh, bm, na, NA, nb, NB, norms_b, use_bias, max_a, max_b, top);
     MP_LAUNCH_OK();
     return MP_OK;
 }
 
 int match_top2_tensor(const __nv_bfloat16 *a_hi, const __nv_bfloat16 *a_mid, const int32_t *na, int NA,
                       const __nv_bfloat16 *b_hi, const __nv_bfloat16 *b_mid, const int32_t *nb, int NB, int P, int D,
-                      const float *norms_b, int use_bias, Top2 *top, cudaStream_t stream) {
+                      const float *norms_b, int use_bias, const unsigned *max_a, const unsigned *max_b, Top2 *top,
+                      cudaStream_t stream) {
     if (D % 64 != 0 || D > 256 || D <= 0) {
         set_error("match_top2_tensor: D=%d must be a multiple of 64 and <= 256", D);
         return MP_ERR_UNSUPPORTED;
@@ -337,10 +368,10 @@ int match_top2_tensor(const __nv_bfloat16 *a_hi, const __nv_bfloat16 *a_mid, con
     if ((rc = make_operand_map(&bh, b_hi, P, NB, D)) != MP_OK) return rc;
     if ((rc = make_operand_map(&bm, b_mid, P, NB, D)) != MP_OK) return rc;
     switch (D / 64) {
-        case 1: return launch_tc<1>(ah, am, bh, bm, na, NA, nb, NB, P, norms_b, use_bias, top, stream);
-        case 2: return launch_tc<2>(ah, am, bh, bm, na, NA, nb, NB, P, norms_b, use_bias, top, stream);
-        case 3: return launch_tc<3>(ah, am, bh, bm, na, NA, nb, NB, P, norms_b, use_bias, top, stream);
-        default: return launch_tc<4>(ah, am, bh, bm, na, NA, nb, NB, P, norms_b, use_bias, top, stream);
+        case 1: return launch_tc<1>(ah, am, bh, bm, na, NA, nb, NB, P, norms_b, use_bias, max_a, max_b, top, stream);
+        case 2: return launch_tc<2>(ah, am, bh, bm, na, NA, nb, NB, P, norms_b, use_bias, max_a, max_b, top, stream);
+        case 3: return launch_tc<3>(ah, am, bh, bm, na, NA, nb, NB, P, norms_b, use_bias, max_a, max_b, top, stream);
+        default: return launch_tc<4>(ah, am, bh, bm, na, NA, nb, NB, P, norms_b, use_bias, max_a, max_b, top, stream);
     }
 }
 

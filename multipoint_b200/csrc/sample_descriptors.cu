@@ -81,6 +81,80 @@ sample_descriptors_kernel(const int64_t *__restrict__ kp, const int32_t *__restr
     }
 }
 
+// Channels-last fast path: D = 32 * V * NV, every lane moves V-wide vectors (128-bit for V=4), so a
+// corner row of D*4 bytes is NV fully coalesced requests instead of D/32 scalar ones.
+template <int V, int NV>
+__global__ void __launch_bounds__(SD_WARPS * 32)
+sample_descriptors_nhwc_vec_kernel(const int64_t *__restrict__ kp, const int32_t *__restrict__ counts,
+                                   const float *__restrict__ desc, float *__restrict__ out, int B, int K, int Hc, int Wc,
+                                   float half_h, float half_w) {
+    constexpr int D = 32 * V * NV;
+    const int lane = threadIdx.x & 31;
+    const long long item = (long long)blockIdx.x * SD_WARPS + (threadIdx.x >> 5);
+    if (item >= (long long)B * K) return;
+    const int b = (int)(item / K), k = (int)(item - (long long)b * K);
+    float *o = out + (size_t)item * D;
+    const int n = counts ? min(counts[b], K) : K;
+    float v[NV][V];
+    if (k >= n) {
+#pragma unroll
+        for (int j = 0; j < NV; ++j)
+#pragma unroll
+            for (int e = 0; e < V; ++e) v[j][e] = 0.f;
+    } else {
+        const float y = (float)kp[2 * item], x = (float)kp[2 * item + 1];
+        const float yn = __fsub_rn(__fdiv_rn(y, half_h), 1.0f);
+        const float xn = __fsub_rn(__fdiv_rn(x, half_w), 1.0f);
+        const float iy = __fmul_rn(__fdiv_rn(__fadd_rn(yn, 1.0f), 2.0f), (float)(Hc - 1));
+        const float ix = __fmul_rn(__fdiv_rn(__fadd_rn(xn, 1.0f), 2.0f), (float)(Wc - 1));
+        const float fx = floorf(ix), fy = floorf(iy);
+        const int x0 = (int)fx, y0 = (int)fy, x1 = x0 + 1, y1 = y0 + 1;
+        const float w4[4] = {__fmul_rn((float)x1 - ix, (float)y1 - iy), __fmul_rn(ix - (float)x0, (float)y1 - iy),
+                             __fmul_rn((float)x1 - ix, iy - (float)y0), __fmul_rn(ix - (float)x0, iy - (float)y0)};
+        const int cy[4] = {y0, y0, y1, y1}, cx[4] = {x0, x1, x0, x1};
+        const float *m = desc + (size_t)b * Hc * Wc * D;
+#pragma unroll
+        for (int j = 0; j < NV; ++j)
+#pragma unroll
+            for (int e = 0; e < V; ++e) v[j][e] = 0.f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {  // nw, ne, sw, se in the reference's accumulation order
+            if (cy[c] < 0 || cy[c] >= Hc || cx[c] < 0 || cx[c] >= Wc) continue;
+            const float *rowp = m + ((size_t)cy[c] * Wc + cx[c]) * D;
+#pragma unroll
+            for (int j = 0; j < NV; ++j) {
+                float t[V];
+                if (V == 4) {
+                    const float4 q = __ldg(reinterpret_cast<const float4 *>(rowp) + lane + 32 * j);
+                    t[0] = q.x; t[1] = q.y; t[2 % V] = q.z; t[3 % V] = q.w;
+                } else {
+                    const float2 q = __ldg(reinterpret_cast<const float2 *>(rowp) + lane + 32 * j);
+                    t[0] = q.x; t[1] = q.y;
+                }
+#pragma unroll
+                for (int e = 0; e < V; ++e) v[j][e] = __fadd_rn(v[j][e], __fmul_rn(t[e], w4[c]));
+            }
+        }
+        float ss = 0.f;
+#pragma unroll
+        for (int j = 0; j < NV; ++j)
+#pragma unroll
+            for (int e = 0; e < V; ++e) ss += v[j][e] * v[j][e];
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, s);
+        const float denom = fmaxf(sqrtf(ss), 1e-12f);
+#pragma unroll
+        for (int j = 0; j < NV; ++j)
+#pragma unroll
+            for (int e = 0; e < V; ++e) v[j][e] = v[j][e] / denom;
+    }
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        if (V == 4) reinterpret_cast<float4 *>(o)[lane + 32 * j] = make_float4(v[j][0], v[j][1], v[j][2 % V], v[j][3 % V]);
+        else reinterpret_cast<float2 *>(o)[lane + 32 * j] = make_float2(v[j][0], v[j][1]);
+    }
+}
+
 }  // namespace mp
 
 extern "C" int mp_sample_descriptors_f32(const int64_t *keypoints, const int32_t *kp_counts, int B,
@@ -95,7 +169,13 @@ extern "C" int mp_sample_descriptors_f32(const int64_t *keypoints, const int32_t
     const long long items = (long long)B * K;
     const unsigned grid = (unsigned)((items + mp::SD_WARPS - 1) / mp::SD_WARPS);
     const float hh = (float)H * 0.5f, hw = (float)W * 0.5f;
-    if (layout == MP_LAYOUT_NHWC)
+    const bool aligned = (((uintptr_t)desc | (uintptr_t)out) & 15) == 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (layout == MP_LAYOUT_NHWC && aligned && (D == 64 || D == 128 || D == 256)) {
+        if (D == 64) mp::sample_descriptors_nhwc_vec_kernel<2, 1><<<grid, mp::SD_WARPS * 32, 0, s>>>(keypoints, kp_counts, desc, out, B, K, Hc, Wc, hh, hw);
+        else if (D == 128) mp::sample_descriptors_nhwc_vec_kernel<4, 1><<<grid, mp::SD_WARPS * 32, 0, s>>>(keypoints, kp_counts, desc, out, B, K, Hc, Wc, hh, hw);
+        else mp::sample_descriptors_nhwc_vec_kernel<4, 2><<<grid, mp::SD_WARPS * 32, 0, s>>>(keypoints, kp_counts, desc, out, B, K, Hc, Wc, hh, hw);
+    } else if (layout == MP_LAYOUT_NHWC)
         mp::sample_descriptors_kernel<MP_LAYOUT_NHWC><<<grid, mp::SD_WARPS * 32, 0, (cudaStream_t)stream>>>(
             keypoints, kp_counts, desc, out, B, K, D, Hc, Wc, hh, hw);
     else

@@ -510,3 +510,58 @@ def test_pipeline_matches_stagewise_reference_chain(utils, oracle):
         np.testing.assert_array_equal(m['query'][p, :n].cpu().numpy(), wq)
         np.testing.assert_array_equal(m['train'][p, :n].cpu().numpy(), wt)
         np.testing.assert_allclose(m['distance'][p, :n].cpu().numpy(), wd, rtol=RTOL, atol=1e-6)
+
+
+# ------------------------------------------------------------------ multi-GPU path, simulated in one process
+def test_sharded_adaptation_equals_fused(utils, ops):
+    """Two ranks' partial accumulators summed (what the NCCL all-reduce does) then finished equal
+    the single-process fused result to fp32 rounding."""
+    g = load_golden("adaptation")
+    net = _stub(g)
+    masks = (g["masks"] != 0).astype(np.uint8)
+    img_o, img_t = cu(g["img_o"]), cu(g["img_t"])
+    cfg = utils._check_ha_config(dict(num=6, min_count=2, aggregation='prod'))
+    opt = torch.ones(2, 1, dtype=torch.bool, device="cuda")
+    second = (img_t, ~opt)
+    fused = utils._adaptation(img_o, opt, net, cfg, second, g["H"], masks)
+    parts = [utils._adaptation_core(img_o, opt, net, cfg, second, g["H"], masks, r, 2, False) for r in range(2)]
+    prob_sum, count_sum = parts[0][0] + parts[1][0], parts[0][1] + parts[1][1]
+    out = utils.adaptation_finish(prob_sum, count_sum, 'prod', 2)[:, None]
+    torch.testing.assert_close(out, fused, rtol=1e-5, atol=1e-7)
+    # world larger than the number of samples: some ranks only contribute zeros
+    parts = [utils._adaptation_core(img_o, opt, net, cfg, second, g["H"], masks, r, 8, False) for r in range(8)]
+    out8 = utils.adaptation_finish(sum(p[0] for p in parts), sum(p[1] for p in parts), 'prod', 2)[:, None]
+    torch.testing.assert_close(out8, fused, rtol=1e-5, atol=1e-7)
+
+
+# ------------------------------------------------------------------ entry points
+def test_entry_points_run_and_agree(tmp_path, utils):
+    import yaml
+    from multipoint_b200.scripts import export_keypoints, predict_align_image_pair, predict_keypoints
+    model_dir = tmp_path / "model"
+    model_dir.mkdir()
+    (model_dir / "params.yaml").write_text(yaml.dump({'model': {'type': 'MultiPoint', 'multispectral': False, 'descriptor_size': 64,
+                                                                 'descriptor_head': True, 'final_batchnorm': True}}))
+    cfg = {'prediction': {'allow_gpu': True, 'batchsize': 2, 'detection_threshold': 0.015, 'nms': 4, 'cpu_nms': True, 'topk': 100,
+                          'reprojection_threshold': 3,
+                          'matching': {'method': 'bfmatcher', 'method_kwargs': {'crossCheck': True}, 'knn_matches': False},
+                          'homographic_adaptation': {'num': 4, 'aggregation': 'sum', 'erosion_radius': 3, 'min_count': 1}}}
+    (tmp_path / "cfg.yaml").write_text(yaml.dump(cfg))
+    imgs = syn.image_pair_batch(11, 2, 64, 80)
+    np.savez(tmp_path / "in.npz", optical=imgs['optical']['image'], thermal=imgs['thermal']['image'], names=np.array(['a', 'b']))
+    common = ['-y', str(tmp_path / "cfg.yaml"), '-m', str(model_dir), '-v', 'none', '--input', str(tmp_path / "in.npz")]
+    r1 = predict_align_image_pair.main(common + ['-i', '1', '-o', str(tmp_path / "pair.npz")])
+    assert r1['keypoints_optical'].shape[1] == 2 and len(r1['query']) == len(r1['train']) == len(r1['distance'])
+    assert (tmp_path / "pair.npz").exists()
+    r2 = predict_keypoints.main(common + ['-b', '-o', str(tmp_path / "kp.npz")])
+    dense = torch.from_numpy(r2['prob_optical'][1, 0])
+    np.testing.assert_array_equal(torch.nonzero((dense > 0.015).float()).numpy(), r2['keypoints_optical_1'])
+    assert len(r2['keypoints_thermal_0']) == 100                               # top-k 100 of a dense candidate map
+    # same seed-0 random-init weights and the same batch size of 1 in both scripts: same keypoints
+    r2s = predict_keypoints.main(common + ['-i', '1'])
+    np.testing.assert_array_equal(r2s['keypoints_optical_0'], r1['keypoints_optical'])
+    out = tmp_path / "labels.npz"
+    r3 = export_keypoints.main(common + ['-o', str(out)])
+    z = np.load(out)
+    assert sorted(z.files) == ['a/keypoints', 'b/keypoints'] and z['a/keypoints'].dtype == np.int64
+    assert export_keypoints.main(common + ['-o', str(out), '-skip']) == {}     # resume: nothing left to do
