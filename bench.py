@@ -202,7 +202,7 @@ def main():
     dev = torch.device("cuda", local_rank)
     torch.backends.cudnn.allow_tf32 = False           # fp32 like the reference: no reduced precision
     torch.backends.cuda.matmul.allow_tf32 = False
-    torch.backends.cudnn.benchmark = True
+    torch.backends.cudnn.benchmark = os.environ.get("MP_BENCH_NO_AUTOTUNE", "0") != "1"   # autotuning floods ncu
     K, Wm, P = args.steps, max(args.warmup, 3), args.pairs
 
     if args.only_hot:

@@ -527,11 +527,13 @@ def test_sharded_adaptation_equals_fused(utils, ops):
     parts = [utils._adaptation_core(img_o, opt, net, cfg, second, g["H"], masks, r, 2, False) for r in range(2)]
     prob_sum, count_sum = parts[0][0] + parts[1][0], parts[0][1] + parts[1][1]
     out = utils.adaptation_finish(prob_sum, count_sum, 'prod', 2)[:, None]
-    torch.testing.assert_close(out, fused, rtol=1e-5, atol=1e-7)
+    # not bit-exact: the summation order changes and cuDNN picks batch-size dependent algorithms for
+    # the per-rank forward passes; sqrt of the product aggregation amplifies both near zero
+    torch.testing.assert_close(out, fused, rtol=2e-4, atol=1e-5)
     # world larger than the number of samples: some ranks only contribute zeros
     parts = [utils._adaptation_core(img_o, opt, net, cfg, second, g["H"], masks, r, 8, False) for r in range(8)]
     out8 = utils.adaptation_finish(sum(p[0] for p in parts), sum(p[1] for p in parts), 'prod', 2)[:, None]
-    torch.testing.assert_close(out8, fused, rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(out8, fused, rtol=2e-4, atol=1e-5)
 
 
 # ------------------------------------------------------------------ entry points
