@@ -53,6 +53,53 @@ match_prep_kernel(const float *__restrict__ d, const int32_t *__restrict__ count
     }
 }
 
+// Vector form for D % 8 == 0: every lane converts 8 consecutive elements (two 128-bit loads, one
+// 128-bit store per bf16 plane); 4 / 2 / 1 rows per warp for D <= 64 / 128 / larger.
+template <int RPW>
+__global__ void __launch_bounds__(256)
+match_prep_vec_kernel(const float *__restrict__ d, const int32_t *__restrict__ counts, int N, int D, int P,
+                      float *__restrict__ norms, unsigned *__restrict__ max_norm_bits,
+                      __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ mid) {
+    constexpr int LPR = 32 / RPW;  // lanes per row
+    const int lane = threadIdx.x & 31, sub = lane % LPR;
+    const long long row = ((long long)blockIdx.x * 8 + (threadIdx.x >> 5)) * RPW + lane / LPR;
+    const bool in_range = row < (long long)P * N;
+    const int p = in_range ? (int)(row / N) : 0, i = in_range ? (int)(row - (long long)p * N) : 0;
+    const bool valid = in_range && (counts == nullptr || i < counts[p]);
+    float ss = 0.f;
+    if (in_range) {
+        for (int c0 = 8 * sub; c0 < D; c0 += 8 * LPR) {
+            float v[8];
+            if (valid) {
+                const float4 q0 = __ldg(reinterpret_cast<const float4 *>(d + (size_t)row * D + c0));
+                const float4 q1 = __ldg(reinterpret_cast<const float4 *>(d + (size_t)row * D + c0 + 4));
+                v[0] = q0.x; v[1] = q0.y; v[2] = q0.z; v[3] = q0.w; v[4] = q1.x; v[5] = q1.y; v[6] = q1.z; v[7] = q1.w;
+            } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] = 0.f;
+            }
+            if (hi != nullptr) {
+                __align__(16) __nv_bfloat16 h[8], m[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    h[e] = __float2bfloat16_rn(v[e]);
+                    m[e] = __float2bfloat16_rn(v[e] - __bfloat162float(h[e]));
+                }
+                *reinterpret_cast<uint4 *>(hi + (size_t)row * D + c0) = *reinterpret_cast<const uint4 *>(h);
+                *reinterpret_cast<uint4 *>(mid + (size_t)row * D + c0) = *reinterpret_cast<const uint4 *>(m);
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) ss += v[e] * v[e];
+        }
+    }
+#pragma unroll
+    for (int s = LPR / 2; s > 0; s >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, s);
+    if (in_range && sub == 0) {
+        norms[row] = ss;
+        if (valid) atomicMax(max_norm_bits + p, __float_as_uint(sqrtf(ss)));
+    }
+}
+
 // ------------------------------------------------------------------ SIMT top-2
 // 128 rows per CTA (one per thread), 32 columns of the other set per step, K chunks of 16
 // through shared memory.  Columns are visited in ascending order with strict '>' updates, so
@@ -178,50 +225,67 @@ match_recheck_kernel(const float *__restrict__ d1, const int32_t *__restrict__ n
         }
         double best = INFINITY;
         int bidx = 0x7fffffff;
-        for (int j = warp; j < nb; j += RK_WARPS) {
-            double b[DPL];
+        // two columns per iteration, the next two prefetched while these are reduced: the first
+        // version (one column, load -> convert -> FMA -> shuffle chain) stalled 11.6 cycles per
+        // issue on the loads (ncu long_scoreboard)
+        float nx[2][DPL];
+        auto fetch = [&](int j, float (&dst)[DPL]) {
 #pragma unroll
             for (int i = 0; i < DPL; ++i) {
                 const int k = lane + 32 * i;
-                b[i] = k < D ? (double)__ldg(Bm + (size_t)j * D + k) : 0.0;
+                dst[i] = (j < nb && k < D) ? __ldg(Bm + (size_t)j * D + k) : 0.f;
             }
-            double acc[RK_ROWS];
+        };
+        fetch(warp * 2, nx[0]);
+        fetch(warp * 2 + 1, nx[1]);
+        for (int j = warp * 2; j < nb; j += RK_WARPS * 2) {
+            float cur[2][DPL];
 #pragma unroll
-            for (int r = 0; r < RK_ROWS; ++r) {
-                double s = 0.0;
-                if (metric == MP_METRIC_NN) {
+            for (int c = 0; c < 2; ++c)
 #pragma unroll
-                    for (int i = 0; i < DPL; ++i) s = fma(a[r][i], b[i], s);
-                } else {
+                for (int i = 0; i < DPL; ++i) cur[c][i] = nx[c][i];
+            fetch(j + RK_WARPS * 2, nx[0]);
+            fetch(j + RK_WARPS * 2 + 1, nx[1]);
 #pragma unroll
-                    for (int i = 0; i < DPL; ++i) { const double df = a[r][i] - b[i]; s = fma(df, df, s); }
+            for (int c = 0; c < 2; ++c) {
+                double acc[RK_ROWS];
+#pragma unroll
+                for (int r = 0; r < RK_ROWS; ++r) {
+                    double sum = 0.0;
+                    if (metric == MP_METRIC_NN) {
+#pragma unroll
+                        for (int i = 0; i < DPL; ++i) sum = fma(a[r][i], (double)cur[c][i], sum);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < DPL; ++i) { const double df = a[r][i] - (double)cur[c][i]; sum = fma(df, df, sum); }
+                    }
+                    acc[r] = sum;
                 }
-                acc[r] = s;
-            }
-            // halving exchange: after the 3 steps each lane holds the partial of one row
+                // halving exchange: after the 3 steps each lane holds the partial of one row
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {  // step 1: partner lane^16, keep rows [0,4) or [4,8)
-                const bool up = lane & 16;
-                const double send = up ? acc[r] : acc[r + 4], keep = up ? acc[r + 4] : acc[r];
-                acc[r] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-            }
+                for (int r = 0; r < 4; ++r) {  // step 1: partner lane^16, keep rows [0,4) or [4,8)
+                    const bool up = lane & 16;
+                    const double send = up ? acc[r] : acc[r + 4], keep = up ? acc[r + 4] : acc[r];
+                    acc[r] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+                }
 #pragma unroll
-            for (int r = 0; r < 2; ++r) {  // step 2: lane^8
-                const bool up = lane & 8;
-                const double send = up ? acc[r] : acc[r + 2], keep = up ? acc[r + 2] : acc[r];
-                acc[r] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+                for (int r = 0; r < 2; ++r) {  // step 2: lane^8
+                    const bool up = lane & 8;
+                    const double send = up ? acc[r] : acc[r + 2], keep = up ? acc[r + 2] : acc[r];
+                    acc[r] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+                }
+                {  // step 3: lane^4
+                    const bool up = lane & 4;
+                    const double send = up ? acc[0] : acc[1], keep = up ? acc[1] : acc[0];
+                    acc[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+                }
+                acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], 2);
+                acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], 1);
+                // acc[0] is now the total of row ((lane>>4)&1)*4 + ((lane>>3)&1)*2 + ((lane>>2)&1)
+                double key = acc[0];
+                if (metric == MP_METRIC_NN) key = -fmin(1.0, fmax(-1.0, key));
+                if (j + c < nb && key < best) { best = key; bidx = j + c; }  // ascending j per warp: first minimum
             }
-            {  // step 3: lane^4
-                const bool up = lane & 4;
-                const double send = up ? acc[0] : acc[1], keep = up ? acc[1] : acc[0];
-                acc[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-            }
-            acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], 2);
-            acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], 1);
-            // acc[0] is now the total of row ((lane>>4)&1)*4 + ((lane>>3)&1)*2 + ((lane>>2)&1)
-            double key = acc[0];
-            if (metric == MP_METRIC_NN) key = -fmin(1.0, fmax(-1.0, key));
-            if (key < best) { best = key; bidx = j; }  // ascending j per warp: first minimum
         }
         // lanes 4r..4r+3 (in the bit order above) all hold row r's result; publish one per warp
         const int r_of_lane = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
@@ -519,9 +583,17 @@ static int run_nearest(const float *d1, const int32_t *n1, int N1, const float *
 
     MP_CUDA_OK(cudaMemsetAsync(scal, 0, sizeof(unsigned) * (4 * (size_t)P + 4), s));
     const long long r1 = (long long)P * N1, r2 = (long long)P * N2;
-    match_prep_kernel<<<(unsigned)((r1 + 7) / 8), 256, 0, s>>>(d1, n1, N1, D, P, norms1, max1, hi1, mid1);
+    auto prep = [&](const float *d, const int32_t *n, int N, long long rows, float *norms, unsigned *mx, __nv_bfloat16 *h,
+                    __nv_bfloat16 *m) {
+        const bool vec = D % 8 == 0 && (((uintptr_t)d | (uintptr_t)h | (uintptr_t)m) & 15) == 0;
+        if (!vec) match_prep_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(d, n, N, D, P, norms, mx, h, m);
+        else if (D <= 64) match_prep_vec_kernel<4><<<(unsigned)((rows + 31) / 32), 256, 0, s>>>(d, n, N, D, P, norms, mx, h, m);
+        else if (D <= 128) match_prep_vec_kernel<2><<<(unsigned)((rows + 15) / 16), 256, 0, s>>>(d, n, N, D, P, norms, mx, h, m);
+        else match_prep_vec_kernel<1><<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(d, n, N, D, P, norms, mx, h, m);
+    };
+    prep(d1, n1, N1, r1, norms1, max1, hi1, mid1);
     MP_LAUNCH_OK();
-    match_prep_kernel<<<(unsigned)((r2 + 7) / 8), 256, 0, s>>>(d2, n2, N2, D, P, norms2, max2, hi2, mid2);
+    prep(d2, n2, N2, r2, norms2, max2, hi2, mid2);
     MP_LAUNCH_OK();
 
     if (tensor) {

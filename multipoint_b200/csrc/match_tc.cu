@@ -25,7 +25,8 @@ namespace mp {
 
 constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 64;  // BK bf16 = one 128 B swizzle row
 constexpr int TC_ACC_STAGES = 4;                     // 4 x 128 fp32 columns = all 512 TMEM columns
-constexpr int TC_THREADS = 192;                      // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
+constexpr int TC_EPI_WARPS = 8;                      // two per TMEM lane quarter, alternating 32-column chunks
+constexpr int TC_THREADS = 32 * (2 + TC_EPI_WARPS);  // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
 constexpr uint32_t TC_TILE_BYTES = TC_BM * TC_BK * 2;  // 16 KB: one (128 x 64) bf16 block
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -159,7 +160,7 @@ match_top2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
     if (warp == 0 && lane == 0) {
         mbar_init(bar_a_full, 1);
         for (int s = 0; s < S; ++s) { mbar_init(bar_b_full(s), 1); mbar_init(bar_b_empty(s), 1); }
-        for (int t = 0; t < TC_ACC_STAGES; ++t) { mbar_init(bar_acc_full(t), 1); mbar_init(bar_acc_empty(t), 4); }
+        for (int t = 0; t < TC_ACC_STAGES; ++t) { mbar_init(bar_acc_full(t), 1); mbar_init(bar_acc_empty(t), TC_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -230,7 +231,11 @@ match_top2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
         // integers, and the column's position inside its 32-column chunk replaces the 5 lowest
         // mantissa bits: one integer max then carries value and index together.  Truncation costs
         // 2^-18 relative (included in MATCH_EPS_TENSOR); equal packed keys prefer the lower column.
+        // Two warps share each TMEM lane quarter and take alternate chunks, so every scheduler has
+        // two epilogue warps to hide the tcgen05.ld latency (with one, ncu showed 3.4 stall cycles
+        // per issued instruction and the epilogue, not the MMAs, set the tile time).
         const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+        const int half = (warp - 2) >> 2;
         const int row = quarter * 32 + lane;
         const float ma = __uint_as_float(max_a[p]), mb = __uint_as_float(max_b[p]);
         const float C = 1.002f * ma * mb + (use_bias ? 0.5f * mb * mb : 0.f) + 1e-30f;
@@ -243,7 +248,7 @@ match_top2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
             tc_fence_after();
             const int n0 = nt * TC_BN;
 #pragma unroll 1
-            for (int c = 0; c < TC_BN / 32; ++c) {
+            for (int c = half; c < TC_BN / 32; c += 2) {
                 const int col0 = n0 + c * 32;
                 if (col0 >= n_b) break;
                 float v[32];
@@ -278,7 +283,23 @@ match_top2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_acc_empty(t));
         }
-        if (m0 + row < NA) {
+        // merge the two column subsets of each row (A's smem is free: every MMA has completed)
+        uint32_t *mrg = reinterpret_cast<uint32_t *>(smem_raw + (smem_a - smem_u32(smem_raw)));
+        if (half == 1) {
+            mrg[row * 4 + 0] = best; mrg[row * 4 + 1] = second;
+            mrg[row * 4 + 2] = (uint32_t)best_chunk; mrg[row * 4 + 3] = (uint32_t)second_chunk;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_WARPS * 32) : "memory");
+        if (half == 0) {
+            const uint32_t ob = mrg[row * 4 + 0], os = mrg[row * 4 + 1];
+            const int obc = (int)mrg[row * 4 + 2], osc = (int)mrg[row * 4 + 3];
+            // (best, second) of the union; on equal packed keys either index is fine (flagged anyway)
+            uint32_t nb_, ns_; int nbc, nsc;
+            if (ob > best) { nb_ = ob; nbc = obc; if (best >= os) { ns_ = best; nsc = best_chunk; } else { ns_ = os; nsc = osc; } }
+            else { nb_ = best; nbc = best_chunk; if (ob >= second) { ns_ = ob; nsc = obc; } else { ns_ = second; nsc = second_chunk; } }
+            best = nb_; best_chunk = nbc; second = ns_; second_chunk = nsc;
+        }
+        if (half == 0 && m0 + row < NA) {
             Top2 out;
             out.best = -INFINITY; out.second = -INFINITY; out.best_idx = -1; out.second_idx = -1;
             if (m0 + row < n_a) {

@@ -560,6 +560,7 @@ def test_entry_points_run_and_agree(tmp_path, utils):
     np.testing.assert_array_equal(torch.nonzero((dense > 0.015).float()).numpy(), r2['keypoints_optical_1'])
     assert len(r2['keypoints_thermal_0']) == 100                               # top-k 100 of a dense candidate map
     # same seed-0 random-init weights and the same batch size of 1 in both scripts: same keypoints
+    torch.manual_seed(0)   # predict_align_image_pair seeds torch itself (-s 0); predict_keypoints does not (like the reference)
     r2s = predict_keypoints.main(common + ['-i', '1'])
     np.testing.assert_array_equal(r2s['keypoints_optical_0'], r1['keypoints_optical'])
     out = tmp_path / "labels.npz"
