@@ -560,6 +560,8 @@ nms_tile_fast_kernel(const float *__restrict__ prob, float *__restrict__ out, in
 }
 
 // One CTA per image: resolve the pixels whose dependency chain left their tile's apron.
+// One warp per queued pixel: the lanes fetch the (2R+1)^2 window from the dense map (L2) in
+// parallel and vote, so a round costs one L2 round trip instead of one per neighbour.
 __global__ void __launch_bounds__(1024)
 nms_fixup_kernel(float *__restrict__ out, int H, int W, const NmsFootprint fp, uint2 *__restrict__ survivors,
                  int *__restrict__ surv_count, const uint32_t *__restrict__ worklist,
@@ -570,21 +572,38 @@ nms_fixup_kernel(float *__restrict__ out, int H, int W, const NmsFootprint fp, u
     float *img = out + (size_t)b * H * W;
     const uint32_t *work = worklist + (size_t)b * cap;
     uint2 *surv = survivors + (size_t)b * cap;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int R = fp.R, S = 2 * R + 1;
     while (true) {
         bool changed = false, pending = false;
-        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        for (int i = warp; i < n; i += nwarps) {
             const int idx = (int)work[i];
             const float val = __ldcg(img + idx);
-            if (val >= 0.f) continue;
+            if (val >= 0.f) continue;  // warp-uniform
+            const float s = -val;
             const int y = idx / W, x = idx - y * W;
-            const float nv = nms_decide(val, fp, [&](int dy, int dx) {
+            bool kept_higher = false, und_higher = false;
+            for (int k = lane; k < S * S; k += 32) {
+                const int dy = k / S - R, dx = k - (dy + R) * S - R;
+                if (!((fp.rows[dy + R] >> (dx + R)) & 1u)) continue;
                 const int yy = y + dy, xx = x + dx;
-                return (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldcg(img + yy * W + xx) : 0.f;
-            });
-            if (nv != val) {
-                __stcg(img + idx, nv);
+                if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+                const float nv = __ldcg(img + yy * W + xx);
+                if (nv == 0.f) continue;
+                const float sn = fabsf(nv);
+                if (sn > s || (sn == s && (dy < 0 || (dy == 0 && dx < 0)))) {
+                    if (nv > 0.f) kept_higher = true; else und_higher = true;
+                }
+            }
+            kept_higher = __any_sync(0xffffffffu, kept_higher);
+            und_higher = __any_sync(0xffffffffu, und_higher);
+            if (kept_higher || !und_higher) {
+                const float nv = kept_higher ? 0.f : s;
+                if (lane == 0) {
+                    __stcg(img + idx, nv);
+                    if (nv > 0.f) surv[atomicAdd(surv_count + b, 1)] = make_uint2((uint32_t)idx, __float_as_uint(nv));
+                }
                 changed = true;
-                if (nv > 0.f) surv[atomicAdd(surv_count + b, 1)] = make_uint2((uint32_t)idx, __float_as_uint(nv));
             } else {
                 pending = true;
             }
@@ -592,7 +611,7 @@ nms_fixup_kernel(float *__restrict__ out, int H, int W, const NmsFootprint fp, u
         __threadfence_block();
         const bool any_pending = __syncthreads_or(pending);
         const bool any_changed = __syncthreads_or(changed);
-        if (!any_pending || !any_changed) break;  // !changed with pending cannot happen (progress is guaranteed)
+        if (!any_pending || !any_changed) break;  // progress is guaranteed while anything is pending
     }
 }
 

@@ -94,10 +94,26 @@ match_prep_vec_kernel(const float *__restrict__ d, const int32_t *__restrict__ c
     }
 #pragma unroll
     for (int s = LPR / 2; s > 0; s >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, s);
-    if (in_range && sub == 0) {
-        norms[row] = ss;
-        if (valid) atomicMax(max_norm_bits + p, __float_as_uint(sqrtf(ss)));
+    if (in_range && sub == 0) norms[row] = ss;
+    // largest norm per pair: one atomic per (block, pair) instead of one per row -- 2048 rows of a
+    // pair hitting one address serialised in L2 and cost more than the conversion itself
+    __shared__ unsigned blk_max[2];
+    __shared__ int blk_pair0;
+    if (threadIdx.x == 0) {
+        blk_max[0] = blk_max[1] = 0;
+        const long long first = (long long)blockIdx.x * 8 * RPW;
+        blk_pair0 = (int)(first / N);
     }
+    __syncthreads();
+    if (valid && sub == 0) {
+        const int slot = p - blk_pair0;  // a block of <= 32 rows spans at most two pairs when N >= 32
+        const unsigned bits = __float_as_uint(sqrtf(ss));
+        if (slot == 0 || slot == 1) atomicMax(&blk_max[slot], bits);
+        else atomicMax(max_norm_bits + p, bits);
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 && blk_max[threadIdx.x] != 0 && blk_pair0 + (int)threadIdx.x < P)
+        atomicMax(max_norm_bits + blk_pair0 + threadIdx.x, blk_max[threadIdx.x]);
 }
 
 // ------------------------------------------------------------------ SIMT top-2
