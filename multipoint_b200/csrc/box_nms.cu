@@ -320,7 +320,6 @@ nms_tile_fast_kernel(const float *__restrict__ prob, float *__restrict__ out, in
     uint16_t *ids_a = pos + CAP, *ids_b = ids_a + CAP;                 // undecided ids, ping / pong
     __shared__ int n_list;
     __shared__ int n_next[3];
-    __shared__ int warp_sums[NMS_THREADS / 32];
     __shared__ int bases[2];
     __shared__ uint32_t fp7[7];
 
@@ -399,45 +398,52 @@ nms_tile_fast_kernel(const float *__restrict__ prob, float *__restrict__ out, in
     __syncthreads();
     const int n0 = n_list;
 
+    const int warp = tid >> 5;
     if (n0 <= CAP) {
         // ---- 3a. round 0: higher-priority candidate neighbours of every candidate, once ----
-        for (int i0 = 0; i0 < n0; i0 += NMS_THREADS) {
-            const int id = i0 + tid;
+        // mask bit 8*r + c  <=>  neighbour at (dy, dx) = (r - 3, c - 3); two 32-bit words (rows 0-3, 4-6)
+        for (int base = warp * 32; base < n0; base += NMS_THREADS) {  // warp-strided: idle warps skip
+            const int id = base + lane;
             bool still = false;
             if (id < n0) {
                 const int e = pos[id];
                 const int ey = e / EW, ex = e - ey * EW;
-                const float s = -v[e];  // may already be read as +s by nobody: only this thread writes v[e]
+                const float s = -v[e];
                 const int bitpos = ex - RM, w = bitpos >> 5, sh = bitpos & 31;
-                uint64_t m = 0;
+                uint32_t lo = 0, hi = 0;
 #pragma unroll
                 for (int r = 0; r < 7; ++r) {
                     const uint32_t *bw = bm + (ey + r - RM) * BW + w;
                     const uint32_t win = __funnelshift_r(bw[0], bw[1], sh) & fp7[r];
-                    m |= (uint64_t)win << (7 * r);
+                    if (r < 4) lo |= win << (8 * r); else hi |= win << (8 * (r - 4));
                 }
                 const float *vb = v + e - RM * EW - RM;
-                uint64_t hm = 0;
-                while (m) {
-                    const int k = __ffsll((long long)m) - 1;
-                    m &= m - 1;
-                    const int dy = (k * 37) >> 8, dx = k - 7 * dy;  // k / 7 for k < 49
-                    const float sn = fabsf(vb[dy * EW + dx]);        // every candidate still carries its score
-                    if (sn > s || (sn == s && k < 24)) hm |= 1ull << k;  // k < 24 <=> earlier in row-major order
+                uint32_t hlo = 0, hhi = 0;
+                while (lo) {
+                    const int k = __ffs(lo) - 1;
+                    lo &= lo - 1;
+                    const float sn = fabsf(vb[(k >> 3) * EW + (k & 7)]);  // every candidate still carries its score
+                    if (sn > s || (sn == s && k < 27)) hlo |= 1u << k;     // k < 27 <=> earlier in row-major order
                 }
-                if (hm == 0) {
+                while (hi) {
+                    const int k = __ffs(hi) - 1;
+                    hi &= hi - 1;
+                    const float sn = fabsf(vb[(4 + (k >> 3)) * EW + (k & 7)]);
+                    if (sn > s) hhi |= 1u << k;
+                }
+                if ((hlo | hhi) == 0) {
                     v[e] = s;  // local maximum: kept
                 } else {
-                    mask[id] = hm;
+                    mask[id] = ((uint64_t)hhi << 32) | hlo;
                     still = true;
                 }
             }
             const unsigned bal = __ballot_sync(0xffffffffu, still);
             if (bal) {
-                int base = 0;
-                if (lane == (__ffs(bal) - 1)) base = atomicAdd(&n_next[0], __popc(bal));
-                base = __shfl_sync(0xffffffffu, base, __ffs(bal) - 1);
-                if (still) ids_a[base + __popc(bal & ((1u << lane) - 1))] = (uint16_t)id;
+                int slot = 0;
+                if (lane == (__ffs(bal) - 1)) slot = atomicAdd(&n_next[0], __popc(bal));
+                slot = __shfl_sync(0xffffffffu, slot, __ffs(bal) - 1);
+                if (still) ids_a[slot + __popc(bal & ((1u << lane) - 1))] = (uint16_t)id;
             }
         }
         __syncthreads();
@@ -448,34 +454,45 @@ nms_tile_fast_kernel(const float *__restrict__ prob, float *__restrict__ out, in
             int *cnt = &n_next[round % 3];
             if (tid == 0) n_next[(round + 1) % 3] = 0;
             bool changed = false;
-            for (int i0 = 0; i0 < n; i0 += NMS_THREADS) {
-                const int i = i0 + tid;
+            for (int base = warp * 32; base < n; base += NMS_THREADS) {
+                const int i = base + lane;
                 bool still = false;
                 int id = 0;
                 if (i < n) {
                     id = cur[i];
                     const int e = pos[id];
                     const float *vb = v + e - RM * EW - RM;
-                    uint64_t hm = mask[id], m = hm;
+                    const uint64_t old = mask[id];
+                    uint32_t hlo = (uint32_t)old, hhi = (uint32_t)(old >> 32);
                     bool sup = false;
-                    while (m) {
-                        const int k = __ffsll((long long)m) - 1;
+                    for (uint32_t m = hlo; m && !sup;) {
+                        const int k = __ffs(m) - 1;
                         m &= m - 1;
-                        const int dy = (k * 37) >> 8, dx = k - 7 * dy;
-                        const float nv = vb[dy * EW + dx];
-                        if (nv > 0.f) { sup = true; break; }       // kept higher-priority neighbour
-                        if (nv == 0.f) hm &= ~(1ull << k);          // it was suppressed: no longer blocks
+                        const float nv = vb[(k >> 3) * EW + (k & 7)];
+                        if (nv > 0.f) sup = true;                  // kept higher-priority neighbour
+                        else if (nv == 0.f) hlo &= ~(1u << k);     // it was suppressed: no longer blocks
+                    }
+                    for (uint32_t m = hhi; m && !sup;) {
+                        const int k = __ffs(m) - 1;
+                        m &= m - 1;
+                        const float nv = vb[(4 + (k >> 3)) * EW + (k & 7)];
+                        if (nv > 0.f) sup = true;
+                        else if (nv == 0.f) hhi &= ~(1u << k);
                     }
                     if (sup) { v[e] = 0.f; changed = true; }
-                    else if (hm == 0) { v[e] = -v[e]; changed = true; }
-                    else { if (hm != mask[id]) { mask[id] = hm; } still = true; }
+                    else if ((hlo | hhi) == 0) { v[e] = -v[e]; changed = true; }
+                    else {
+                        const uint64_t nm = ((uint64_t)hhi << 32) | hlo;
+                        if (nm != old) mask[id] = nm;
+                        still = true;
+                    }
                 }
                 const unsigned bal = __ballot_sync(0xffffffffu, still);
                 if (bal) {
-                    int base = 0;
-                    if (lane == (__ffs(bal) - 1)) base = atomicAdd(cnt, __popc(bal));
-                    base = __shfl_sync(0xffffffffu, base, __ffs(bal) - 1);
-                    if (still) nxt[base + __popc(bal & ((1u << lane) - 1))] = (uint16_t)id;
+                    int slot = 0;
+                    if (lane == (__ffs(bal) - 1)) slot = atomicAdd(cnt, __popc(bal));
+                    slot = __shfl_sync(0xffffffffu, slot, __ffs(bal) - 1);
+                    if (still) nxt[slot + __popc(bal & ((1u << lane) - 1))] = (uint16_t)id;
                 }
             }
             const bool any = __syncthreads_or(changed);
@@ -500,63 +517,80 @@ nms_tile_fast_kernel(const float *__restrict__ prob, float *__restrict__ out, in
     }
     __syncthreads();
 
-    // ---- 4. write the interior once; queue survivors and unresolved pixels ----
+    // ---- 4. write the interior once; survivors / unresolved pixels are staged in shared memory (the
+    //         mask and id arrays are free now) and leave as two contiguous runs per tile ----
     constexpr int IQ = TW / 4;
     constexpr int PER_THREAD = (TH * IQ + NMS_THREADS - 1) / NMS_THREADS;
-    int kept = 0, unres = 0;
-#pragma unroll
-    for (int k = 0; k < PER_THREAD; ++k) {
-        const int i = tid + k * NMS_THREADS;
-        if (i >= TH * IQ) break;
-        const int iy = i / IQ, q = i - iy * IQ;
-        const int gy = ty0 + iy, gx = tx0 + 4 * q;
-        if (gy >= H || gx >= W) continue;
-        const float4 val = *reinterpret_cast<const float4 *>(v + (E + iy) * EW + E + 4 * q);
-        const float c[4] = {val.x, val.y, val.z, val.w};
-        if (VEC) {
-            st_stream_f4(reinterpret_cast<float4 *>(out + ((size_t)b * H + gy) * W + gx), val);
-        } else {
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (gx + j < W) out[((size_t)b * H + gy) * W + gx + j] = c[j];
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            if (gx + j >= W) continue;
-            kept += c[j] > 0.f;
-            unres += c[j] < 0.f;
-        }
-    }
-    int tot_kept, tot_unres;
-    int off_kept = block_exclusive_scan(kept, warp_sums, tot_kept);
-    int off_unres = block_exclusive_scan(unres, warp_sums, tot_unres);
-    if (tid == 0) {
-        bases[0] = tot_kept ? atomicAdd(surv_count + b, tot_kept) : 0;
-        bases[1] = tot_unres ? atomicAdd(work_count + b, tot_unres) : 0;
-    }
+    constexpr int KCAP = CAP, UCAP = (3 * CAP) / 2;  // uint2 over mask[], uint32 over pos/ids
+    uint2 *stg_kept = reinterpret_cast<uint2 *>(mask);
+    uint32_t *stg_un = reinterpret_cast<uint32_t *>(pos);
+    int *n_kept = &n_next[0], *n_un = &n_next[1];
+    if (tid == 0) { n_next[0] = 0; n_next[1] = 0; }
     __syncthreads();
-    if (tot_kept == 0 && tot_unres == 0) return;
-    off_kept += bases[0];
-    off_unres += bases[1];
     uint2 *surv = survivors + (size_t)b * cap;
     uint32_t *work = worklist + (size_t)b * cap;
 #pragma unroll
     for (int k = 0; k < PER_THREAD; ++k) {
-        const int i = tid + k * NMS_THREADS;
-        if (i >= TH * IQ) break;
+        const int i = tid + k * NMS_THREADS;  // TH*IQ is a multiple of NMS_THREADS for the shipped tile: no ragged warp
         const int iy = i / IQ, q = i - iy * IQ;
         const int gy = ty0 + iy, gx = tx0 + 4 * q;
-        if (gy >= H || gx >= W) continue;
-        if (kept == 0 && unres == 0) break;
-        const float *c = v + (E + iy) * EW + E + 4 * q;
+        const bool inside = i < TH * IQ && gy < H && gx < W;
+        float c[4] = {0.f, 0.f, 0.f, 0.f};
+        if (inside) {
+            const float4 val = *reinterpret_cast<const float4 *>(v + (E + iy) * EW + E + 4 * q);
+            c[0] = val.x; c[1] = val.y; c[2] = val.z; c[3] = val.w;
+            if (VEC) {
+                st_stream_f4(reinterpret_cast<float4 *>(out + ((size_t)b * H + gy) * W + gx), val);
+            } else {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            if (gx + j >= W) continue;
-            const uint32_t idx = (uint32_t)(gy * W + gx + j);
-            if (c[j] > 0.f) surv[off_kept++] = make_uint2(idx, __float_as_uint(c[j]));
-            else if (c[j] < 0.f) work[off_unres++] = idx;
+                for (int j = 0; j < 4; ++j)
+                    if (gx + j < W) out[((size_t)b * H + gy) * W + gx + j] = c[j];
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (gx + j >= W) c[j] = 0.f;
+            }
+        }
+        const int nk = (c[0] > 0.f) + (c[1] > 0.f) + (c[2] > 0.f) + (c[3] > 0.f);
+        const int nu = (c[0] < 0.f) + (c[1] < 0.f) + (c[2] < 0.f) + (c[3] < 0.f);
+        if (__any_sync(0xffffffffu, (nk | nu) != 0)) {
+            int ik = nk, iu = nu;  // inclusive warp scans
+#pragma unroll
+            for (int sft = 1; sft < 32; sft <<= 1) {
+                const int tk = __shfl_up_sync(0xffffffffu, ik, sft), tu = __shfl_up_sync(0xffffffffu, iu, sft);
+                if (lane >= sft) { ik += tk; iu += tu; }
+            }
+            int bk = 0, bu = 0;
+            if (lane == 31) {
+                if (ik) bk = atomicAdd(n_kept, ik);
+                if (iu) bu = atomicAdd(n_un, iu);
+            }
+            bk = __shfl_sync(0xffffffffu, bk, 31) + ik - nk;
+            bu = __shfl_sync(0xffffffffu, bu, 31) + iu - nu;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t idx = (uint32_t)(gy * W + gx + j);
+                if (c[j] > 0.f) {
+                    const uint2 ent = make_uint2(idx, __float_as_uint(c[j]));
+                    if (bk < KCAP) stg_kept[bk] = ent;
+                    else surv[atomicAdd(surv_count + b, 1)] = ent;   // staging full (tiny boxes): rare
+                    ++bk;
+                } else if (c[j] < 0.f) {
+                    if (bu < UCAP) stg_un[bu] = idx;
+                    else work[atomicAdd(work_count + b, 1)] = idx;
+                    ++bu;
+                }
+            }
         }
     }
+    __syncthreads();
+    const int tk = min(*n_kept, KCAP), tu = min(*n_un, UCAP);
+    if (tid == 0) {
+        bases[0] = tk ? atomicAdd(surv_count + b, tk) : 0;
+        bases[1] = tu ? atomicAdd(work_count + b, tu) : 0;
+    }
+    __syncthreads();
+    for (int i = tid; i < tk; i += NMS_THREADS) surv[bases[0] + i] = stg_kept[i];
+    for (int i = tid; i < tu; i += NMS_THREADS) work[bases[1] + i] = stg_un[i];
 }
 
 // One CTA per image: resolve the pixels whose dependency chain left their tile's apron.
@@ -647,15 +681,34 @@ __device__ void emit_from_bitmap(const uint32_t *bitmap, int words, int W, const
 }
 
 // One CTA per image: top-k (optional) + ordered compaction.
+// Top-k = the k smallest keys (~score_bits, index), i.e. highest scores first, ties to the lower
+// row-major index (the stable order of torchvision's sort).  MSB-first radix select with 11-bit
+// digits: three passes over the score bits; the three index passes only run when equal scores
+// straddle k.  Each thread keeps its (<= 16) survivors in registers, so the list is read once.
+constexpr int SEL_BINS = 2048, SEL_CACHE = 16;
+
+// Which bin holds the `remaining`-th entry when bins are visited in descending (DESC) or ascending
+// order?  Thread t owns two adjacent bins; one block scan gives the count ahead of them.
+template <bool DESC>
+__device__ __forceinline__ void select_find_bin(const int *hist, int remaining, int *warp_sums, int *out_bin, int *out_remaining) {
+    const int t = threadIdx.x;
+    const int d_first = DESC ? SEL_BINS - 1 - 2 * t : 2 * t, d_second = DESC ? d_first - 1 : d_first + 1;
+    const int h1 = hist[d_first], h2 = hist[d_second];
+    int total;
+    const int ahead = block_exclusive_scan(h1 + h2, warp_sums, total);
+    if (ahead < remaining && remaining <= ahead + h1) { *out_bin = d_first; *out_remaining = remaining - ahead; }
+    else if (ahead + h1 < remaining && remaining <= ahead + h1 + h2) { *out_bin = d_second; *out_remaining = remaining - ahead - h1; }
+    __syncthreads();
+}
+
 __global__ void __launch_bounds__(1024)
 nms_select_kernel(float *__restrict__ out, int H, int W, int keep_top_k, const uint2 *__restrict__ survivors,
                   const int *__restrict__ surv_count, int cap, uint32_t *__restrict__ bitmaps, int words,
                   int64_t *__restrict__ keypoints, float *__restrict__ kp_scores, int32_t *__restrict__ kp_counts,
                   int kp_cap) {
-    __shared__ int hist[256];
+    __shared__ int hist[SEL_BINS];
     __shared__ int warp_sums[32];
-    __shared__ unsigned long long prefix_s;
-    __shared__ int remaining_s;
+    __shared__ int sel_bin, sel_remaining;
     const int b = blockIdx.x, tid = threadIdx.x;
     const int n = surv_count[b];
     const uint2 *surv = survivors + (size_t)b * cap;
@@ -663,50 +716,74 @@ nms_select_kernel(float *__restrict__ out, int H, int W, int keep_top_k, const u
     const bool want_kp = keypoints != nullptr || kp_counts != nullptr;
     uint32_t *bitmap = bitmaps ? bitmaps + (size_t)b * words : nullptr;
 
-    // key = (~score_bits, index): ascending key <=> descending score, then ascending index.
-    // positive floats order like their bit patterns.
-    unsigned long long kth = ~0ull;  // keep everything with key <= kth
+    const bool cached = n <= SEL_CACHE * 1024;
+    uint2 ent[SEL_CACHE];
+    if (cached) {
+#pragma unroll
+        for (int k = 0; k < SEL_CACHE; ++k) {
+            const int i = tid + k * 1024;
+            ent[k] = i < n ? surv[i] : make_uint2(0xffffffffu, 0u);  // score bits 0 never match a live prefix
+        }
+    }
+// visit every survivor (x = index, y = score bits) from registers, or from L2 when there are too many
+#define MP_FOR_EACH_SURVIVOR(BODY)                                         \
+    if (cached) {                                                          \
+        _Pragma("unroll") for (int k_ = 0; k_ < SEL_CACHE; ++k_) {         \
+            if (tid + k_ * 1024 < n) { const uint2 e = ent[k_]; BODY }      \
+        }                                                                  \
+    } else {                                                               \
+        for (int i_ = tid; i_ < n; i_ += 1024) { const uint2 e = surv[i_]; BODY } \
+    }
+
+    uint32_t cut_score = 0, cut_index = 0xffffffffu;  // keep: score > cut_score || (score == cut_score && index <= cut_index)
     if (keep_top_k > 0 && n > keep_top_k) {
-        // MSB-first radix select of the keep_top_k-th smallest key, 8 bits per pass
-        if (tid == 0) { prefix_s = 0; remaining_s = keep_top_k; }
-        for (int pass = 7; pass >= 0; --pass) {
-            if (tid < 256) hist[tid] = 0;
+        uint32_t prefix = 0;
+        int remaining = keep_top_k, in_bin = 0;
+        const int shifts[3] = {21, 10, 0}, widths[3] = {11, 11, 10};
+        for (int pass = 0; pass < 3; ++pass) {
+            for (int i = tid; i < SEL_BINS; i += 1024) hist[i] = 0;
             __syncthreads();
-            const unsigned long long prefix = prefix_s;
-            const int shift = pass * 8;
-            for (int i = tid; i < n; i += blockDim.x) {
-                const uint2 e = surv[i];
-                const unsigned long long key = ((unsigned long long)(~e.y) << 32) | e.x;
-                if (pass == 7 || (key >> (shift + 8)) == (prefix >> (shift + 8)))
-                    atomicAdd(&hist[(int)((key >> shift) & 0xff)], 1);
-            }
+            const int sh = shifts[pass], hi_sh = sh + widths[pass];
+            const uint32_t dmask = (1u << widths[pass]) - 1u;
+            MP_FOR_EACH_SURVIVOR(if (pass == 0 || (e.y >> hi_sh) == (prefix >> hi_sh)) atomicAdd(&hist[(e.y >> sh) & dmask], 1);)
             __syncthreads();
-            if (tid == 0) {
-                int rem = remaining_s, d = 0;
-                for (; d < 256; ++d) {
-                    if (hist[d] >= rem) break;
-                    rem -= hist[d];
-                }
-                prefix_s = prefix | ((unsigned long long)d << shift);
-                remaining_s = rem;
-            }
+            select_find_bin<true>(hist, remaining, warp_sums, &sel_bin, &sel_remaining);
+            prefix |= (uint32_t)sel_bin << sh;
+            remaining = sel_remaining;
+            in_bin = hist[sel_bin];
             __syncthreads();
         }
-        kth = prefix_s;
+        cut_score = prefix;  // the k-th highest score; `remaining` of the `in_bin` survivors with it are kept
+        if (remaining < in_bin) {
+            // equal scores straddle k: keep the `remaining` lowest indices among them
+            uint32_t iprefix = 0;
+            for (int pass = 0; pass < 3; ++pass) {
+                for (int i = tid; i < SEL_BINS; i += 1024) hist[i] = 0;
+                __syncthreads();
+                const int sh = shifts[pass], hi_sh = sh + widths[pass];
+                const uint32_t dmask = (1u << widths[pass]) - 1u;
+                MP_FOR_EACH_SURVIVOR(if (e.y == cut_score && (pass == 0 || (e.x >> hi_sh) == (iprefix >> hi_sh)))
+                                         atomicAdd(&hist[(e.x >> sh) & dmask], 1);)
+                __syncthreads();
+                select_find_bin<false>(hist, remaining, warp_sums, &sel_bin, &sel_remaining);
+                iprefix |= (uint32_t)sel_bin << sh;
+                remaining = sel_remaining;
+                __syncthreads();
+            }
+            cut_index = iprefix;
+        }
     }
     if (want_kp) {
         for (int w = tid; w < words; w += blockDim.x) bitmap[w] = 0;
         __syncthreads();
     }
-    for (int i = tid; i < n; i += blockDim.x) {
-        const uint2 e = surv[i];
-        const unsigned long long key = ((unsigned long long)(~e.y) << 32) | e.x;
-        if (key <= kth) {
+    MP_FOR_EACH_SURVIVOR(
+        if (e.y > cut_score || (e.y == cut_score && e.x <= cut_index)) {
             if (want_kp) atomicOr(&bitmap[e.x >> 5], 1u << (e.x & 31));
         } else {
             img[e.x] = 0.f;  // cut by top-k (utils.py:109-116)
-        }
-    }
+        })
+#undef MP_FOR_EACH_SURVIVOR
     if (!want_kp) return;
     __syncthreads();
     emit_from_bitmap(bitmap, words, W, img, keypoints ? keypoints + (size_t)b * kp_cap * 2 : nullptr,
