@@ -24,6 +24,7 @@
 //                        asc), then ordered (row-major) compaction of the survivors through a
 //                        bitmap into int64 (y,x) keypoints.
 #include <math.h>
+#include <stdlib.h>
 
 #include "mp_common.cuh"
 
@@ -499,6 +500,43 @@ nms_tile_fast_kernel(const float *__restrict__ prob, float *__restrict__ out, in
             n = *cnt;
             uint16_t *tmp = cur; cur = nxt; nxt = tmp;
             if (!any) break;  // what is left depends on pixels outside the apron
+            if (n <= 32) {
+                // tail: the last few pixels settle in one warp, round after round, without block-wide
+                // barriers (each costs more than the round itself once only a handful are left)
+                if (warp == 0) {
+                    int id = lane < n ? cur[lane] : -1;
+                    while (__any_sync(0xffffffffu, id >= 0)) {
+                        bool progressed = false;
+                        if (id >= 0) {
+                            const int e = pos[id];
+                            const float *vb = v + e - RM * EW - RM;
+                            const uint64_t old = mask[id];
+                            uint32_t hlo = (uint32_t)old, hhi = (uint32_t)(old >> 32);
+                            bool sup = false;
+                            for (uint32_t m = hlo; m && !sup;) {
+                                const int k = __ffs(m) - 1;
+                                m &= m - 1;
+                                const float nv = vb[(k >> 3) * EW + (k & 7)];
+                                if (nv > 0.f) sup = true;
+                                else if (nv == 0.f) hlo &= ~(1u << k);
+                            }
+                            for (uint32_t m = hhi; m && !sup;) {
+                                const int k = __ffs(m) - 1;
+                                m &= m - 1;
+                                const float nv = vb[(4 + (k >> 3)) * EW + (k & 7)];
+                                if (nv > 0.f) sup = true;
+                                else if (nv == 0.f) hhi &= ~(1u << k);
+                            }
+                            if (sup) { v[e] = 0.f; id = -1; progressed = true; }
+                            else if ((hlo | hhi) == 0) { v[e] = -v[e]; id = -1; progressed = true; }
+                            else mask[id] = ((uint64_t)hhi << 32) | hlo;
+                        }
+                        __syncwarp();
+                        if (!__any_sync(0xffffffffu, progressed)) break;
+                    }
+                }
+                break;
+            }
         }
     } else {
         // ---- 3c. dense tile: sweep the pixels of the decidable region until nothing changes ----
@@ -957,8 +995,11 @@ extern "C" int mp_box_nms_f32(const float *prob, int B, int H, int W, double siz
     const float thr = (float)min_prob;
     const bool vec = (W % 4 == 0) && (((uintptr_t)prob & 15) == 0) && (((uintptr_t)prob_nms & 15) == 0);
     int rc;
-    if (R <= 3)
+    static const int tile_variant = getenv("MP_NMS_TILE") ? atoi(getenv("MP_NMS_TILE")) : 0;  // tuning aid
+    if (R <= 3 && tile_variant == 1)
         rc = launch_tile_fast<32, 128, 8, 1920>(prob, prob_nms, B, H, W, thr, fp, surv, surv_count, work, work_count, L.cap, vec, s);
+    else if (R <= 3)
+        rc = launch_tile_fast<32, 64, 8, 960>(prob, prob_nms, B, H, W, thr, fp, surv, surv_count, work, work_count, L.cap, vec, s);
     else if (R <= 8)
         rc = launch_tile<32, 128, 8>(prob, prob_nms, B, H, W, thr, fp, surv, surv_count, work, work_count, L.cap, vec, s);
     else

@@ -133,16 +133,13 @@ match_top2_simt_kernel(const float *__restrict__ a, const int32_t *__restrict__ 
     const int n_a = na ? min(na[p], NA) : NA, n_b = nb ? min(nb[p], NB) : NB;
     if (row0 >= n_a) {  // whole CTA beyond this pair's valid rows: empty results
         if (row < NA) {
-            Top2 e;
-            e.best = -INFINITY; e.second = -INFINITY; e.best_idx = -1; e.second_idx = -1;
-            top[(size_t)p * NA + row] = e;
+            top[(size_t)p * NA + row] = top2_empty();
         }
         return;
     }
     const float *ap = a + (size_t)p * NA * D;
     const float *bp = b + (size_t)p * NB * D;
-    Top2 t;
-    t.best = -INFINITY; t.second = -INFINITY; t.best_idx = -1; t.second_idx = -1;
+    Top2 t = top2_empty();
     for (int c0 = 0; c0 < n_b; c0 += ST_COLS) {
         float acc[ST_COLS];
 #pragma unroll
@@ -175,29 +172,76 @@ match_top2_simt_kernel(const float *__restrict__ a, const int32_t *__restrict__ 
         }
     }
     if (row < NA) {
-        if (row >= n_a) { t.best = -INFINITY; t.second = -INFINITY; t.best_idx = -1; t.second_idx = -1; }
+        if (row >= n_a) t = top2_empty();
         top[(size_t)p * NA + row] = t;
     }
 }
 
 // ------------------------------------------------------------------ flag near-ties
-// One list of flagged rows per (pair, side) so the recheck can share the other set's rows
-// between the flagged queries of a group.  group = 2*pair + side; capacity N rows each.
+// Rows whose top-2 margin is inside the error bound, per (pair, side) group = 2*pair + side:
+//   pair list : the third key is clear of the bound -> only the two indexed candidates can be
+//               the true nearest neighbour: two exact keys settle it (match_recheck_pair_kernel)
+//   full list : three or more candidates within the bound (or the NN metric's clip plateau) ->
+//               exact rescan of the whole other set (match_recheck_kernel)
 __global__ void match_flag_kernel(const Top2 *__restrict__ top, int N, int P, const unsigned *__restrict__ max_a,
                                   const unsigned *__restrict__ max_b, int metric, float eps_rel, float pack_rel, int side,
-                                  int32_t *__restrict__ idx_out, int32_t *__restrict__ flagged, int *__restrict__ n_flagged) {
+                                  int32_t *__restrict__ idx_out, int32_t *__restrict__ flagged, int *__restrict__ n_flagged,
+                                  int32_t *__restrict__ pairs, int *__restrict__ n_pairs) {
     const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= (long long)P * N) return;
     const int p = (int)(g / N);
     const Top2 t = top[g];
     idx_out[g] = t.best_idx;
-    if (t.best_idx < 0) return;
+    if (t.best_idx < 0 || t.second_idx < 0) return;
     const float ma = __uint_as_float(max_a[p]), mb = __uint_as_float(max_b[p]);
     const float eps = eps_rel * fmaxf(ma * mb, 1e-30f) +
                       pack_rel * 2.f * (1.002f * ma * mb + (metric == MP_METRIC_L2 ? 0.5f * mb * mb : 0.f));
-    bool flag = (t.second_idx >= 0) && !(t.best - t.second >= 2.f * eps);  // also catches NaN keys
-    if (metric == MP_METRIC_NN && t.best >= 1.f - eps && t.second_idx >= 0) flag = true;  // clip(.,-1,1) ties
-    if (flag) flagged[(size_t)p * N + atomicAdd(n_flagged + 2 * p + side, 1)] = (int32_t)(g - (long long)p * N);
+    const bool close2 = !(t.best - t.second >= 2.f * eps);  // also catches NaN keys
+    const bool close3 = !(t.best - t.third >= 2.f * eps);
+    const bool plateau = metric == MP_METRIC_NN && t.best >= 1.f - eps;  // clip(.,-1,1) can tie many columns
+    const int row = (int)(g - (long long)p * N);
+    if (plateau || (close2 && close3)) flagged[(size_t)p * N + atomicAdd(n_flagged + 2 * p + side, 1)] = row;
+    else if (close2) pairs[(size_t)p * N + atomicAdd(n_pairs + 2 * p + side, 1)] = row;
+}
+
+// exact fp64 key of one (a, b) pair, lanes striding over D; result in every lane
+__device__ __forceinline__ double exact_key(const float *a, const float *b, int D, int metric, int lane) {
+    double acc = 0.0;
+    if (metric == MP_METRIC_NN) {
+        for (int c = lane; c < D; c += 32) acc = fma((double)a[c], (double)b[c], acc);
+    } else {
+        for (int c = lane; c < D; c += 32) { const double df = (double)a[c] - (double)b[c]; acc = fma(df, df, acc); }
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+    return metric == MP_METRIC_NN ? -fmin(1.0, fmax(-1.0, acc)) : acc;
+}
+
+// One warp per pair-flagged row: exact keys of its two candidates, the smaller wins, ties to the
+// lower index.  grid (2P groups, RP_Y); 8 warps per CTA.
+constexpr int RP_Y = 8;
+__global__ void __launch_bounds__(256)
+match_recheck_pair_kernel(const float *__restrict__ d1, int N1, const float *__restrict__ d2, int N2, int D, int metric,
+                          const Top2 *__restrict__ top12, const Top2 *__restrict__ top21,
+                          const int32_t *__restrict__ pairs1, const int32_t *__restrict__ pairs2,
+                          const int *__restrict__ n_pairs, int32_t *__restrict__ idx12, int32_t *__restrict__ idx21) {
+    const int group = blockIdx.x, p = group >> 1, side = group & 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int count = n_pairs[group];
+    const int NA = side == 0 ? N1 : N2, NB = side == 0 ? N2 : N1;
+    const float *A = side == 0 ? d1 + (size_t)p * N1 * D : d2 + (size_t)p * N2 * D;
+    const float *Bm = side == 0 ? d2 + (size_t)p * N2 * D : d1 + (size_t)p * N1 * D;
+    const int32_t *rows = (side == 0 ? pairs1 : pairs2) + (size_t)p * NA;
+    const Top2 *top = (side == 0 ? top12 : top21) + (size_t)p * NA;
+    int32_t *dst = side == 0 ? idx12 + (size_t)p * N1 : idx21 + (size_t)p * N2;
+    (void)NB;
+    for (int i = blockIdx.y * 8 + warp; i < count; i += RP_Y * 8) {
+        const int row = rows[i];
+        const int j1 = top[row].best_idx, j2 = top[row].second_idx;
+        const double k1 = exact_key(A + (size_t)row * D, Bm + (size_t)j1 * D, D, metric, lane);
+        const double k2 = exact_key(A + (size_t)row * D, Bm + (size_t)j2 * D, D, metric, lane);
+        if (lane == 0) dst[row] = (k2 < k1 || (k2 == k1 && j2 < j1)) ? j2 : j1;
+    }
 }
 
 // ------------------------------------------------------------------ exact recheck
@@ -564,7 +608,7 @@ MatchLayout::MatchLayout(int P, int N1, int N2, int D) {
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
     const size_t r1 = (size_t)P * N1, r2 = (size_t)P * N2;
-    scalars = take(sizeof(unsigned) * (4 * (size_t)P + 4));
+    scalars = take(sizeof(unsigned) * (6 * (size_t)P + 4));
     norms1 = take(sizeof(float) * r1);
     norms2 = take(sizeof(float) * r2);
     top12 = take(sizeof(Top2) * r1);
@@ -573,6 +617,8 @@ MatchLayout::MatchLayout(int P, int N1, int N2, int D) {
     idx21 = take(sizeof(int32_t) * r2);
     flagged1 = take(sizeof(int32_t) * r1);
     flagged2 = take(sizeof(int32_t) * r2);
+    pairs1 = take(sizeof(int32_t) * r1);
+    pairs2 = take(sizeof(int32_t) * r2);
     train_tmp = take(sizeof(int32_t) * r1);
     dist_tmp = take(sizeof(float) * r1);
     hi1 = take(sizeof(__nv_bfloat16) * r1 * D);
@@ -587,17 +633,18 @@ static int run_nearest(const float *d1, const int32_t *n1, int N1, const float *
                        int P, int D, int metric, int algo, const MatchLayout &L, char *ws, cudaStream_t s) {
     unsigned *scal = (unsigned *)(ws + L.scalars);
     unsigned *max1 = scal, *max2 = scal + P;
-    int *n_flagged = (int *)(scal + 2 * P);
+    int *n_flagged = (int *)(scal + 2 * P), *n_pairs = (int *)(scal + 4 * P);
     float *norms1 = (float *)(ws + L.norms1), *norms2 = (float *)(ws + L.norms2);
     Top2 *top12 = (Top2 *)(ws + L.top12), *top21 = (Top2 *)(ws + L.top21);
     int32_t *idx12 = (int32_t *)(ws + L.idx12), *idx21 = (int32_t *)(ws + L.idx21);
     int32_t *flagged1 = (int32_t *)(ws + L.flagged1), *flagged2 = (int32_t *)(ws + L.flagged2);
+    int32_t *pairs1 = (int32_t *)(ws + L.pairs1), *pairs2 = (int32_t *)(ws + L.pairs2);
     const bool tensor = algo == MP_ALGO_TENSOR;
     __nv_bfloat16 *hi1 = tensor ? (__nv_bfloat16 *)(ws + L.hi1) : nullptr, *mid1 = (__nv_bfloat16 *)(ws + L.mid1);
     __nv_bfloat16 *hi2 = tensor ? (__nv_bfloat16 *)(ws + L.hi2) : nullptr, *mid2 = (__nv_bfloat16 *)(ws + L.mid2);
     const int use_bias = metric == MP_METRIC_L2;
 
-    MP_CUDA_OK(cudaMemsetAsync(scal, 0, sizeof(unsigned) * (4 * (size_t)P + 4), s));
+    MP_CUDA_OK(cudaMemsetAsync(scal, 0, sizeof(unsigned) * (6 * (size_t)P + 4), s));
     const long long r1 = (long long)P * N1, r2 = (long long)P * N2;
     auto prep = [&](const float *d, const int32_t *n, int N, long long rows, float *norms, unsigned *mx, __nv_bfloat16 *h,
                     __nv_bfloat16 *m) {
@@ -625,10 +672,15 @@ static int run_nearest(const float *d1, const int32_t *n1, int N1, const float *
         MP_LAUNCH_OK();
     }
     const float eps_rel = tensor ? MATCH_EPS_TENSOR : MATCH_EPS_SIMT, pack_rel = tensor ? MATCH_PACK_REL : 0.f;
-    match_flag_kernel<<<(unsigned)((r1 + 255) / 256), 256, 0, s>>>(top12, N1, P, max1, max2, metric, eps_rel, pack_rel, 0, idx12, flagged1, n_flagged);
+    match_flag_kernel<<<(unsigned)((r1 + 255) / 256), 256, 0, s>>>(top12, N1, P, max1, max2, metric, eps_rel, pack_rel, 0, idx12, flagged1, n_flagged, pairs1, n_pairs);
     MP_LAUNCH_OK();
-    match_flag_kernel<<<(unsigned)((r2 + 255) / 256), 256, 0, s>>>(top21, N2, P, max2, max1, metric, eps_rel, pack_rel, 1, idx21, flagged2, n_flagged);
+    match_flag_kernel<<<(unsigned)((r2 + 255) / 256), 256, 0, s>>>(top21, N2, P, max2, max1, metric, eps_rel, pack_rel, 1, idx21, flagged2, n_flagged, pairs2, n_pairs);
     MP_LAUNCH_OK();
+    {
+        dim3 grid(2 * P, RP_Y);
+        match_recheck_pair_kernel<<<grid, 256, 0, s>>>(d1, N1, d2, N2, D, metric, top12, top21, pairs1, pairs2, n_pairs, idx12, idx21);
+        MP_LAUNCH_OK();
+    }
     if (D <= RK_MAXD) {
         dim3 grid(2 * P, RK_Z);
 #define MP_RECHECK(DPL) match_recheck_kernel<DPL><<<grid, RK_WARPS * 32, 0, s>>>(d1, n1, N1, d2, n2, N2, D, metric, flagged1, flagged2, n_flagged, idx12, idx21)

@@ -6,19 +6,31 @@
 
 namespace mp {
 
-// best / second-best similarity key of one descriptor over the other set (larger = closer)
-struct __align__(16) Top2 {
-    float best, second;
+// best / second-best / third-best similarity key of one descriptor over the other set (larger =
+// closer).  The third key has no index: it only tells whether a near-tie is confined to the two
+// indexed candidates (then two exact fp64 keys settle it) or needs a full exact rescan.
+struct Top2 {
+    float best, second, third;
     int best_idx, second_idx;
 };
+
+__device__ __forceinline__ Top2 top2_empty() {
+    Top2 t;
+    t.best = -INFINITY; t.second = -INFINITY; t.third = -INFINITY; t.best_idx = -1; t.second_idx = -1;
+    return t;
+}
 
 // ascending-index visits + strict '>' => equal keys resolve to the lowest index
 __device__ __forceinline__ void top2_update(Top2 &t, float key, int idx) {
     if (key > t.best) {
+        t.third = t.second;
         t.second = t.best; t.second_idx = t.best_idx;
         t.best = key; t.best_idx = idx;
     } else if (key > t.second) {
+        t.third = t.second;
         t.second = key; t.second_idx = idx;
+    } else if (key > t.third) {
+        t.third = key;
     }
 }
 
@@ -33,7 +45,7 @@ constexpr float MATCH_PACK_REL = 3.8147e-6f;  // 2^-18
 constexpr float MATCH_EPS_SIMT = 4e-5f;
 
 struct MatchLayout {
-    size_t scalars, norms1, norms2, top12, top21, idx12, idx21, flagged1, flagged2, train_tmp, dist_tmp, hi1, mid1, hi2, mid2, total;
+    size_t scalars, norms1, norms2, top12, top21, idx12, idx21, flagged1, flagged2, pairs1, pairs2, train_tmp, dist_tmp, hi1, mid1, hi2, mid2, total;
     MatchLayout(int P, int N1, int N2, int D);
 };
 

@@ -138,9 +138,7 @@ match_top2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
     if (m0 >= n_a || n_b <= 0) {  // nothing to search: empty results (uniform per CTA)
         for (int r = threadIdx.x; r < TC_BM; r += TC_THREADS)
             if (m0 + r < NA) {
-                Top2 e;
-                e.best = -INFINITY; e.second = -INFINITY; e.best_idx = -1; e.second_idx = -1;
-                top[(size_t)p * NA + m0 + r] = e;
+                top[(size_t)p * NA + m0 + r] = top2_empty();
             }
         return;
     }
@@ -240,7 +238,7 @@ match_top2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
         const float ma = __uint_as_float(max_a[p]), mb = __uint_as_float(max_b[p]);
         const float C = 1.002f * ma * mb + (use_bias ? 0.5f * mb * mb : 0.f) + 1e-30f;
         const float *bias = norms_b + (size_t)p * NB;
-        uint32_t best = 0, second = 0;          // packed keys; 0 = nothing yet
+        uint32_t best = 0, second = 0, third = 0;  // packed keys; 0 = nothing yet
         int best_chunk = -1, second_chunk = -1;  // global chunk index (32 columns each)
         for (int nt = 0; nt < n_tiles; ++nt) {
             const int t = nt % TC_ACC_STAGES;
@@ -257,25 +255,32 @@ match_top2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
                 float add_lane = C;
                 if (use_bias && col0 + lane < n_b) add_lane = fmaf(-0.5f, __ldg(bias + col0 + lane), C);
                 const bool full = col0 + 32 <= n_b;
-                uint32_t b4[4] = {0, 0, 0, 0}, s4[4] = {0, 0, 0, 0};
+                // sorted triples (b >= s >= t) in four independent accumulators for ILP
+                uint32_t b4[4] = {0, 0, 0, 0}, s4[4] = {0, 0, 0, 0}, t4[4] = {0, 0, 0, 0};
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     const float add = use_bias ? __shfl_sync(0xffffffffu, add_lane, j) : C;
                     uint32_t x = (__float_as_uint(v[j] + add) & ~31u) | (uint32_t)(31 - j);
                     if (!full && col0 + j >= n_b) x = 0;
+                    t4[j & 3] = max(t4[j & 3], min(x, s4[j & 3]));
                     s4[j & 3] = max(s4[j & 3], min(x, b4[j & 3]));
                     b4[j & 3] = max(b4[j & 3], x);
                 }
-                // merge the four accumulators, then into the running pair
-                uint32_t cb = max(b4[0], b4[1]), cs = max(min(b4[0], b4[1]), max(s4[0], s4[1]));
-                const uint32_t cb2 = max(b4[2], b4[3]), cs2 = max(min(b4[2], b4[3]), max(s4[2], s4[3]));
-                cs = max(min(cb, cb2), max(cs, cs2));
-                cb = max(cb, cb2);
+                // k-th largest of two sorted triples: second = max(s, s', min(b, b')),
+                // third = max(t, t', min(s, b'), min(b, s'))
+                auto merge3 = [](uint32_t &b, uint32_t &s_, uint32_t &t_, uint32_t b2, uint32_t s2, uint32_t t2) {
+                    const uint32_t nt = max(max(t_, t2), max(min(s_, b2), min(b, s2)));
+                    const uint32_t ns = max(max(s_, s2), min(b, b2));
+                    b = max(b, b2); s_ = ns; t_ = nt;
+                };
+                merge3(b4[0], s4[0], t4[0], b4[1], s4[1], t4[1]);
+                merge3(b4[2], s4[2], t4[2], b4[3], s4[3], t4[3]);
+                merge3(b4[0], s4[0], t4[0], b4[2], s4[2], t4[2]);
+                const uint32_t cb = b4[0], cs = s4[0];
                 const int chunk = col0 >> 5;
                 const uint32_t old_best = best, old_second = second;
                 const int old_best_chunk = best_chunk;
-                best = max(old_best, cb);
-                second = max(min(old_best, cb), max(old_second, cs));
+                merge3(best, second, third, cb, cs, t4[0]);
                 if (best != old_best) best_chunk = chunk;
                 if (second != old_second) second_chunk = (second == old_best && best != old_best) ? old_best_chunk : chunk;
             }
@@ -288,6 +293,7 @@ match_top2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
         if (half == 1) {
             mrg[row * 4 + 0] = best; mrg[row * 4 + 1] = second;
             mrg[row * 4 + 2] = (uint32_t)best_chunk; mrg[row * 4 + 3] = (uint32_t)second_chunk;
+            mrg[512 + row] = third;
         }
         asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_WARPS * 32) : "memory");
         if (half == 0) {
@@ -297,11 +303,12 @@ match_top2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
             uint32_t nb_, ns_; int nbc, nsc;
             if (ob > best) { nb_ = ob; nbc = obc; if (best >= os) { ns_ = best; nsc = best_chunk; } else { ns_ = os; nsc = osc; } }
             else { nb_ = best; nbc = best_chunk; if (ob >= second) { ns_ = ob; nsc = obc; } else { ns_ = second; nsc = second_chunk; } }
+            const uint32_t ot = mrg[512 + row];
+            third = max(max(third, ot), max(min(second, ob), min(best, os)));  // before best/second are overwritten
             best = nb_; best_chunk = nbc; second = ns_; second_chunk = nsc;
         }
         if (half == 0 && m0 + row < NA) {
-            Top2 out;
-            out.best = -INFINITY; out.second = -INFINITY; out.best_idx = -1; out.second_idx = -1;
+            Top2 out = top2_empty();
             if (m0 + row < n_a) {
                 if (best_chunk >= 0) {
                     out.best_idx = best_chunk * 32 + 31 - (int)(best & 31u);
@@ -311,6 +318,7 @@ match_top2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
                     out.second_idx = second_chunk * 32 + 31 - (int)(second & 31u);
                     out.second = __uint_as_float(second & ~31u) - C;
                 }
+                if (third != 0) out.third = __uint_as_float(third & ~31u) - C;
             }
             top[(size_t)p * NA + m0 + row] = out;
         }
