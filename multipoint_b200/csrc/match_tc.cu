@@ -18,6 +18,7 @@
 // The only global traffic is the bf16 operands (B re-read once per 128-row block, from L2) and
 // 16 B of result per row.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "match_internal.cuh"
 
@@ -73,6 +74,27 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uin
         "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// A operand from tensor memory (cute SM100_MMA_F16BF16_TS)
+__device__ __forceinline__ void tc_mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+          "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+          "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+          "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
     uint32_t r[32];
     asm volatile(
@@ -110,26 +132,36 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-template <int KB>
+// ATM = A operand in tensor memory: the CTA's 128 rows of A_hi / A_mid (D/2 32-bit columns each, two
+// bf16 per column, row r in TMEM lane r) are written once with tcgen05.st and every MMA reads A from
+// TMEM (tcgen05.mma ... [d], [a], b_desc).  Shared memory then only holds the B ring (six 32 KB
+// stages instead of three) and serves half the operand bytes per MMA: with both operands in shared
+// memory an M=128, N=128 MMA needs 8 KB per 64 cycles -- all of the 128 B/cycle an SM has -- on top
+// of the TMA fills.  TMEM: accumulators in columns [0, ACC*128), A in the last 64*KB columns.
+template <int KB, bool ATM>
 struct TcSmem {
-    static constexpr int B_STAGES = KB >= 4 ? 3 : 4;
-    static constexpr uint32_t A_BYTES = 2u * KB * TC_TILE_BYTES;
+    static constexpr int B_STAGES = ATM ? 6 : (KB >= 4 ? 3 : 4);
+    static constexpr int ACC_STAGES = ATM ? (512 - 64 * KB) / TC_BN : TC_ACC_STAGES;
+    static constexpr uint32_t A_COL0 = 512 - 64 * KB;   // ATM only
+    static constexpr uint32_t A_BYTES = ATM ? 0u : 2u * KB * TC_TILE_BYTES;
     static constexpr uint32_t B_STAGE_BYTES = 2u * TC_TILE_BYTES;
     static constexpr uint32_t B_OFF = A_BYTES;
     static constexpr uint32_t BAR_OFF = B_OFF + B_STAGES * B_STAGE_BYTES;
-    static constexpr int NUM_BARS = 1 + 2 * B_STAGES + 2 * TC_ACC_STAGES;
+    static constexpr int NUM_BARS = 1 + 2 * B_STAGES + 2 * ACC_STAGES;
     static constexpr uint32_t TOTAL = BAR_OFF + NUM_BARS * 8 + 16 + 1024;  // + tmem ptr + alignment slack
 };
 
-template <int KB>
+template <int KB, bool ATM>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 match_top2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_mid,
                      const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_mid,
+                     const __nv_bfloat16 *__restrict__ a_hi_ptr, const __nv_bfloat16 *__restrict__ a_mid_ptr,
                      const int32_t *__restrict__ na, int NA, const int32_t *__restrict__ nb, int NB,
                      const float *__restrict__ norms_b, int use_bias, const unsigned *__restrict__ max_a,
                      const unsigned *__restrict__ max_b, Top2 *__restrict__ top) {
-    using L = TcSmem<KB>;
+    using L = TcSmem<KB, ATM>;
     constexpr int S = L::B_STAGES;
+    constexpr int ACC = L::ACC_STAGES;
     extern __shared__ uint8_t smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int p = blockIdx.y, m0 = blockIdx.x * TC_BM;
@@ -149,16 +181,16 @@ match_top2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
     auto bar_b_full = [&](int s) { return bars + 8u * (1 + s); };
     auto bar_b_empty = [&](int s) { return bars + 8u * (1 + S + s); };
     auto bar_acc_full = [&](int t) { return bars + 8u * (1 + 2 * S + t); };
-    auto bar_acc_empty = [&](int t) { return bars + 8u * (1 + 2 * S + TC_ACC_STAGES + t); };
+    auto bar_acc_empty = [&](int t) { return bars + 8u * (1 + 2 * S + ACC + t); };
     const uint32_t tmem_ptr_addr = bars + 8u * L::NUM_BARS;
     volatile uint32_t *tmem_ptr_gen = reinterpret_cast<volatile uint32_t *>(smem_raw + (tmem_ptr_addr - smem_u32(smem_raw)));
 
     const int n_tiles = (n_b + TC_BN - 1) / TC_BN;
 
     if (warp == 0 && lane == 0) {
-        mbar_init(bar_a_full, 1);
+        mbar_init(bar_a_full, ATM ? TC_EPI_WARPS : 1);
         for (int s = 0; s < S; ++s) { mbar_init(bar_b_full(s), 1); mbar_init(bar_b_empty(s), 1); }
-        for (int t = 0; t < TC_ACC_STAGES; ++t) { mbar_init(bar_acc_full(t), 1); mbar_init(bar_acc_empty(t), TC_EPI_WARPS); }
+        for (int t = 0; t < ACC; ++t) { mbar_init(bar_acc_full(t), 1); mbar_init(bar_acc_empty(t), TC_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -174,10 +206,12 @@ match_top2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
-            mbar_expect_tx(bar_a_full, L::A_BYTES);
-            for (int kb = 0; kb < KB; ++kb) {
-                tma_load_3d(smem_a + (0 * KB + kb) * TC_TILE_BYTES, &map_a_hi, bar_a_full, kb * TC_BK, m0, p);
-                tma_load_3d(smem_a + (1 * KB + kb) * TC_TILE_BYTES, &map_a_mid, bar_a_full, kb * TC_BK, m0, p);
+            if (!ATM) {
+                mbar_expect_tx(bar_a_full, L::A_BYTES);
+                for (int kb = 0; kb < KB; ++kb) {
+                    tma_load_3d(smem_a + (0 * KB + kb) * TC_TILE_BYTES, &map_a_hi, bar_a_full, kb * TC_BK, m0, p);
+                    tma_load_3d(smem_a + (1 * KB + kb) * TC_TILE_BYTES, &map_a_mid, bar_a_full, kb * TC_BK, m0, p);
+                }
             }
             int it = 0;
             for (int nt = 0; nt < n_tiles; ++nt) {
@@ -199,24 +233,33 @@ match_top2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
             tc_fence_after();
             int it = 0;
             for (int nt = 0; nt < n_tiles; ++nt) {
-                const int t = nt % TC_ACC_STAGES;
-                mbar_wait(bar_acc_empty(t), ((nt / TC_ACC_STAGES) & 1) ^ 1);
+                const int t = nt % ACC;
+                mbar_wait(bar_acc_empty(t), ((nt / ACC) & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(t * TC_BN);
                 for (int kb = 0; kb < KB; ++kb, ++it) {
                     const int s = it % S;
                     mbar_wait(bar_b_full(s), (it / S) & 1);
                     tc_fence_after();
-                    const uint32_t a_hi = smem_a + (0 * KB + kb) * TC_TILE_BYTES, a_mid = smem_a + (1 * KB + kb) * TC_TILE_BYTES;
                     const uint32_t b_hi = smem_b + s * L::B_STAGE_BYTES, b_mid = b_hi + TC_TILE_BYTES;
 #pragma unroll
                     for (int k = 0; k < TC_BK / 16; ++k) {
                         const uint32_t ko = k * 32;  // 16 bf16 = 32 B inside the 128 B swizzle row
-                        const uint64_t da_hi = umma_desc_sw128(a_hi + ko), da_mid = umma_desc_sw128(a_mid + ko);
                         const uint64_t db_hi = umma_desc_sw128(b_hi + ko), db_mid = umma_desc_sw128(b_mid + ko);
-                        tc_mma_f16(d_tmem, da_mid, db_hi, idesc, (kb | k) != 0);  // small terms first
-                        tc_mma_f16(d_tmem, da_hi, db_mid, idesc, 1);
-                        tc_mma_f16(d_tmem, da_hi, db_hi, idesc, 1);
+                        if (ATM) {
+                            // 16 bf16 of a row = 8 TMEM columns; plane offset 32*KB columns
+                            const uint32_t ta_hi = tmem_base + L::A_COL0 + (uint32_t)(kb * 32 + k * 8);
+                            const uint32_t ta_mid = ta_hi + 32u * KB;
+                            tc_mma_f16_ts(d_tmem, ta_mid, db_hi, idesc, (kb | k) != 0);  // small terms first
+                            tc_mma_f16_ts(d_tmem, ta_hi, db_mid, idesc, 1);
+                            tc_mma_f16_ts(d_tmem, ta_hi, db_hi, idesc, 1);
+                        } else {
+                            const uint32_t a_hi = smem_a + (0 * KB + kb) * TC_TILE_BYTES, a_mid = smem_a + (1 * KB + kb) * TC_TILE_BYTES;
+                            const uint64_t da_hi = umma_desc_sw128(a_hi + ko), da_mid = umma_desc_sw128(a_mid + ko);
+                            tc_mma_f16(d_tmem, da_mid, db_hi, idesc, (kb | k) != 0);  // small terms first
+                            tc_mma_f16(d_tmem, da_hi, db_mid, idesc, 1);
+                            tc_mma_f16(d_tmem, da_hi, db_hi, idesc, 1);
+                        }
                     }
                     tc_commit(bar_b_empty(s));  // smem stage free once these MMAs have read it
                 }
@@ -235,14 +278,36 @@ match_top2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
         const int quarter = warp & 3;  // TMEM lane quarter this warp may access
         const int half = (warp - 2) >> 2;
         const int row = quarter * 32 + lane;
+        if (ATM) {
+            // stage this CTA's rows of A into tensor memory: warps with half 0 write the hi plane,
+            // half 1 the mid plane; each thread owns one row (= one TMEM lane)
+            const __nv_bfloat16 *plane = half == 0 ? a_hi_ptr : a_mid_ptr;
+            const bool live = m0 + row < NA;
+            const uint4 *src = reinterpret_cast<const uint4 *>(plane + ((size_t)p * NA + (live ? m0 + row : 0)) * (64 * KB));
+            const uint32_t col = L::A_COL0 + (uint32_t)(half * 32 * KB);
+#pragma unroll
+            for (int kb = 0; kb < KB; ++kb) {
+                uint32_t r[32];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const uint4 w = live ? __ldg(src + kb * 8 + q) : make_uint4(0u, 0u, 0u, 0u);
+                    r[4 * q + 0] = w.x; r[4 * q + 1] = w.y; r[4 * q + 2] = w.z; r[4 * q + 3] = w.w;
+                }
+                tc_st32(tmem_base + ((uint32_t)(quarter * 32) << 16) + col + (uint32_t)(kb * 32), r);
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_a_full);
+        }
         const float ma = __uint_as_float(max_a[p]), mb = __uint_as_float(max_b[p]);
         const float C = 1.002f * ma * mb + (use_bias ? 0.5f * mb * mb : 0.f) + 1e-30f;
         const float *bias = norms_b + (size_t)p * NB;
         uint32_t best = 0, second = 0, third = 0;  // packed keys; 0 = nothing yet
         int best_chunk = -1, second_chunk = -1;  // global chunk index (32 columns each)
         for (int nt = 0; nt < n_tiles; ++nt) {
-            const int t = nt % TC_ACC_STAGES;
-            mbar_wait(bar_acc_full(t), (nt / TC_ACC_STAGES) & 1);
+            const int t = nt % ACC;
+            mbar_wait(bar_acc_full(t), (nt / ACC) & 1);
             tc_fence_after();
             const int n0 = nt * TC_BN;
 #pragma unroll 1
@@ -288,8 +353,8 @@ match_top2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_acc_empty(t));
         }
-        // merge the two column subsets of each row (A's smem is free: every MMA has completed)
-        uint32_t *mrg = reinterpret_cast<uint32_t *>(smem_raw + (smem_a - smem_u32(smem_raw)));
+        // merge the two column subsets of each row (operand smem is free: every MMA has completed)
+        uint32_t *mrg = reinterpret_cast<uint32_t *>(smem_raw + (base - smem_u32(smem_raw)));
         if (half == 1) {
             mrg[row * 4 + 0] = best; mrg[row * 4 + 1] = second;
             mrg[row * 4 + 2] = (uint32_t)best_chunk; mrg[row * 4 + 3] = (uint32_t)second_chunk;
@@ -370,14 +435,16 @@ static int make_operand_map(CUtensorMap *map, const __nv_bfloat16 *ptr, int P, i
     return MP_OK;
 }
 
-template <int KB>
+template <int KB, bool ATM>
 static int launch_tc(const CUtensorMap &ah, const CUtensorMap &am, const CUtensorMap &bh, const CUtensorMap &bm,
-                     const int32_t *na, int NA, const int32_t *nb, int NB, int P, const float *norms_b, int use_bias,
-                     const unsigned *max_a, const unsigned *max_b, Top2 *top, cudaStream_t s) {
-    auto k = match_top2_tc_kernel<KB>;
-    MP_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcSmem<KB>::TOTAL));
+                     const __nv_bfloat16 *a_hi, const __nv_bfloat16 *a_mid, const int32_t *na, int NA,
+                     const int32_t *nb, int NB, int P, const float *norms_b, int use_bias, const unsigned *max_a,
+                     const unsigned *max_b, Top2 *top, cudaStream_t s) {
+    auto k = match_top2_tc_kernel<KB, ATM>;
+    MP_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcSmem<KB, ATM>::TOTAL));
     dim3 grid((NA + TC_BM - 1) / TC_BM, P);
-    k<<<grid, TC_THREADS, TcSmem<KB>::TOTAL, s>>>(ah, am, bh, bm, na, NA, nb, NB, norms_b, use_bias, max_a, max_b, top);
+    k<<<grid, TC_THREADS, TcSmem<KB, ATM>::TOTAL, s>>>(ah, am, bh, bm, a_hi, a_mid, na, NA, nb, NB, norms_b, use_bias,
+                                                        max_a, max_b, top);
     MP_LAUNCH_OK();
     return MP_OK;
 }
@@ -396,12 +463,17 @@ int match_top2_tensor(const __nv_bfloat16 *a_hi, const __nv_bfloat16 *a_mid, con
     if ((rc = make_operand_map(&am, a_mid, P, NA, D)) != MP_OK) return rc;
     if ((rc = make_operand_map(&bh, b_hi, P, NB, D)) != MP_OK) return rc;
     if ((rc = make_operand_map(&bm, b_mid, P, NB, D)) != MP_OK) return rc;
+    static const bool atm = !(getenv("MP_TC_A_SMEM") && atoi(getenv("MP_TC_A_SMEM")) == 1);  // tuning aid: 1 = A in smem
+#define MP_TC_LAUNCH(KB)                                                                                              \
+    return atm ? launch_tc<KB, true>(ah, am, bh, bm, a_hi, a_mid, na, NA, nb, NB, P, norms_b, use_bias, max_a, max_b, top, stream) \
+               : launch_tc<KB, false>(ah, am, bh, bm, a_hi, a_mid, na, NA, nb, NB, P, norms_b, use_bias, max_a, max_b, top, stream)
     switch (D / 64) {
-        case 1: return launch_tc<1>(ah, am, bh, bm, na, NA, nb, NB, P, norms_b, use_bias, max_a, max_b, top, stream);
-        case 2: return launch_tc<2>(ah, am, bh, bm, na, NA, nb, NB, P, norms_b, use_bias, max_a, max_b, top, stream);
-        case 3: return launch_tc<3>(ah, am, bh, bm, na, NA, nb, NB, P, norms_b, use_bias, max_a, max_b, top, stream);
-        default: return launch_tc<4>(ah, am, bh, bm, na, NA, nb, NB, P, norms_b, use_bias, max_a, max_b, top, stream);
+        case 1: MP_TC_LAUNCH(1);
+        case 2: MP_TC_LAUNCH(2);
+        case 3: MP_TC_LAUNCH(3);
+        default: MP_TC_LAUNCH(4);
     }
+#undef MP_TC_LAUNCH
 }
 
 }  // namespace mp
