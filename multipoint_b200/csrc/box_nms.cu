@@ -319,7 +319,8 @@ nms_tile_fast_kernel(const float *__restrict__ prob, float *__restrict__ out, in
     uint32_t *bm = reinterpret_cast<uint32_t *>(mask + CAP);           // [EH][BW] candidate bitmap
     uint16_t *pos = reinterpret_cast<uint16_t *>(bm + EH * BW);        // [CAP] position of candidate id
     uint16_t *ids_a = pos + CAP, *ids_b = ids_a + CAP;                 // undecided ids, ping / pong
-    __shared__ int n_list;
+    uint16_t *kept_pos = ids_b + CAP;                                  // interior pixels decided "kept"
+    __shared__ int n_list, n_keptpos;
     __shared__ int n_next[3];
     __shared__ int bases[2];
     __shared__ uint32_t fp7[7];
@@ -329,7 +330,7 @@ nms_tile_fast_kernel(const float *__restrict__ prob, float *__restrict__ out, in
     const int ty0 = blockIdx.y * TH, tx0 = blockIdx.x * TW;
     const int gy0 = ty0 - E, gx0 = tx0 - E;
     const float *img = prob + (size_t)b * H * W;
-    if (tid == 0) { n_list = 0; n_next[0] = n_next[1] = n_next[2] = 0; }
+    if (tid == 0) { n_list = 0; n_keptpos = 0; n_next[0] = n_next[1] = n_next[2] = 0; }
     if (tid < 7) {  // footprint rows re-centred in a 7-wide window
         const int dy = tid - RM;
         fp7[tid] = (dy >= -fp.R && dy <= fp.R) ? (fp.rows[dy + fp.R] << (RM - fp.R)) : 0u;
@@ -400,6 +401,13 @@ nms_tile_fast_kernel(const float *__restrict__ prob, float *__restrict__ out, in
     const int n0 = n_list;
 
     const int warp = tid >> 5;
+    auto note_kept = [&](int e) {  // remember interior survivors as they are decided: no rescan at the end
+        const int ey = e / EW, ex = e - ey * EW;
+        if (ey >= E && ey < E + TH && ex >= E && ex < E + TW && ty0 + ey - E < H && tx0 + ex - E < W)
+            kept_pos[atomicAdd(&n_keptpos, 1)] = (uint16_t)e;
+    };
+    int n_left = 0;               // undecided ids still listed when the rounds stop
+    const uint16_t *left = ids_a;
     if (n0 <= CAP) {
         // ---- 3a. round 0: higher-priority candidate neighbours of every candidate, once ----
         // mask bit 8*r + c  <=>  neighbour at (dy, dx) = (r - 3, c - 3); two 32-bit words (rows 0-3, 4-6)
@@ -419,21 +427,32 @@ nms_tile_fast_kernel(const float *__restrict__ prob, float *__restrict__ out, in
                     if (r < 4) lo |= win << (8 * r); else hi |= win << (8 * (r - 4));
                 }
                 const float *vb = v + e - RM * EW - RM;
+                // positive floats order like their bit patterns; neighbours earlier in row-major order
+                // (bits 0..26 of lo) win ties (>=), later ones (bits 28..30 of lo, all of hi) need >
+                const uint32_t sb = __float_as_uint(s);
                 uint32_t hlo = 0, hhi = 0;
-                while (lo) {
-                    const int k = __ffs(lo) - 1;
-                    lo &= lo - 1;
-                    const float sn = fabsf(vb[(k >> 3) * EW + (k & 7)]);  // every candidate still carries its score
-                    if (sn > s || (sn == s && k < 27)) hlo |= 1u << k;     // k < 27 <=> earlier in row-major order
+                for (uint32_t m = lo & 0x07ffffffu; m;) {
+                    const int k = __ffs(m) - 1;
+                    m &= m - 1;
+                    const uint32_t nb_ = __float_as_uint(vb[(k >> 3) * EW + (k & 7)]) & 0x7fffffffu;  // every candidate still carries its score
+                    if (nb_ >= sb) hlo |= 1u << k;
                 }
-                while (hi) {
-                    const int k = __ffs(hi) - 1;
-                    hi &= hi - 1;
-                    const float sn = fabsf(vb[(4 + (k >> 3)) * EW + (k & 7)]);
-                    if (sn > s) hhi |= 1u << k;
+                for (uint32_t m = lo & 0x70000000u; m;) {
+                    const int k = __ffs(m) - 1;
+                    m &= m - 1;
+                    const uint32_t nb_ = __float_as_uint(vb[3 * EW + (k & 7)]) & 0x7fffffffu;
+                    if (nb_ > sb) hlo |= 1u << k;
+                }
+                for (uint32_t m = hi; m;) {
+                    const int k = __ffs(m) - 1;
+                    m &= m - 1;
+                    const uint32_t nb_ = __float_as_uint(vb[(4 + (k >> 3)) * EW + (k & 7)]) & 0x7fffffffu;
+                    if (nb_ > sb) hhi |= 1u << k;
                 }
                 if ((hlo | hhi) == 0) {
                     v[e] = s;  // local maximum: kept
+                    if (ey >= E && ey < E + TH && ex >= E && ex < E + TW && ty0 + ey - E < H && tx0 + ex - E < W)
+                        kept_pos[atomicAdd(&n_keptpos, 1)] = (uint16_t)e;
                 } else {
                     mask[id] = ((uint64_t)hhi << 32) | hlo;
                     still = true;
@@ -451,6 +470,7 @@ nms_tile_fast_kernel(const float *__restrict__ prob, float *__restrict__ out, in
         // ---- 3b. rounds over the cached masks ----
         int n = n_next[0];
         uint16_t *cur = ids_a, *nxt = ids_b;
+        n_left = n; left = cur;
         for (int round = 1; n > 0; ++round) {
             int *cnt = &n_next[round % 3];
             if (tid == 0) n_next[(round + 1) % 3] = 0;
@@ -481,7 +501,7 @@ nms_tile_fast_kernel(const float *__restrict__ prob, float *__restrict__ out, in
                         else if (nv == 0.f) hhi &= ~(1u << k);
                     }
                     if (sup) { v[e] = 0.f; changed = true; }
-                    else if ((hlo | hhi) == 0) { v[e] = -v[e]; changed = true; }
+                    else if ((hlo | hhi) == 0) { v[e] = -v[e]; changed = true; note_kept(e); }
                     else {
                         const uint64_t nm = ((uint64_t)hhi << 32) | hlo;
                         if (nm != old) mask[id] = nm;
@@ -499,6 +519,7 @@ nms_tile_fast_kernel(const float *__restrict__ prob, float *__restrict__ out, in
             const bool any = __syncthreads_or(changed);
             n = *cnt;
             uint16_t *tmp = cur; cur = nxt; nxt = tmp;
+            n_left = n; left = cur;
             if (!any) break;  // what is left depends on pixels outside the apron
             if (n <= 32) {
                 // tail: the last few pixels settle in one warp, round after round, without block-wide
@@ -528,7 +549,7 @@ nms_tile_fast_kernel(const float *__restrict__ prob, float *__restrict__ out, in
                                 else if (nv == 0.f) hhi &= ~(1u << k);
                             }
                             if (sup) { v[e] = 0.f; id = -1; progressed = true; }
-                            else if ((hlo | hhi) == 0) { v[e] = -v[e]; id = -1; progressed = true; }
+                            else if ((hlo | hhi) == 0) { v[e] = -v[e]; id = -1; progressed = true; note_kept(e); }
                             else mask[id] = ((uint64_t)hhi << 32) | hlo;
                         }
                         __syncwarp();
@@ -555,10 +576,71 @@ nms_tile_fast_kernel(const float *__restrict__ prob, float *__restrict__ out, in
     }
     __syncthreads();
 
-    // ---- 4. write the interior once; survivors / unresolved pixels are staged in shared memory (the
-    //         mask and id arrays are free now) and leave as two contiguous runs per tile ----
     constexpr int IQ = TW / 4;
     constexpr int PER_THREAD = (TH * IQ + NMS_THREADS - 1) / NMS_THREADS;
+    if (n0 <= CAP) {
+        // ---- 4a. list path: plain copy of the interior; survivors come from kept_pos, unresolved
+        //          pixels from what is left of the id list (still-undecided entries inside the tile) ----
+#pragma unroll
+        for (int k = 0; k < PER_THREAD; ++k) {
+            const int i = tid + k * NMS_THREADS;
+            const int iy = i / IQ, q = i - iy * IQ;
+            const int gy = ty0 + iy, gx = tx0 + 4 * q;
+            if (i < TH * IQ && gy < H && gx < W) {
+                const float4 val = *reinterpret_cast<const float4 *>(v + (E + iy) * EW + E + 4 * q);
+                if (VEC) {
+                    st_stream_f4(reinterpret_cast<float4 *>(out + ((size_t)b * H + gy) * W + gx), val);
+                } else {
+                    const float c[4] = {val.x, val.y, val.z, val.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (gx + j < W) out[((size_t)b * H + gy) * W + gx + j] = c[j];
+                }
+            }
+        }
+        // unresolved interior pixels: compact their global indices over the (now free) mask array
+        uint32_t *stg_un = reinterpret_cast<uint32_t *>(mask);
+        if (tid == 0) n_next[1] = 0;
+        __syncthreads();
+        for (int base = warp * 32; base < n_left; base += NMS_THREADS) {
+            const int i = base + lane;
+            uint32_t gidx = 0;
+            bool un = false;
+            if (i < n_left) {
+                const int e = pos[left[i]];
+                const int ey = e / EW, ex = e - ey * EW;
+                const int gy = ty0 + ey - E, gx = tx0 + ex - E;
+                un = v[e] < 0.f && ey >= E && ey < E + TH && ex >= E && ex < E + TW && gy < H && gx < W;
+                gidx = (uint32_t)(gy * W + gx);
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, un);
+            if (bal) {
+                int slot = 0;
+                if (lane == (__ffs(bal) - 1)) slot = atomicAdd(&n_next[1], __popc(bal));
+                slot = __shfl_sync(0xffffffffu, slot, __ffs(bal) - 1);
+                if (un) stg_un[slot + __popc(bal & ((1u << lane) - 1))] = gidx;
+            }
+        }
+        __syncthreads();
+        const int tk = n_keptpos, tu = n_next[1];
+        if (tid == 0) {
+            bases[0] = tk ? atomicAdd(surv_count + b, tk) : 0;
+            bases[1] = tu ? atomicAdd(work_count + b, tu) : 0;
+        }
+        __syncthreads();
+        uint2 *surv = survivors + (size_t)b * cap + bases[0];
+        uint32_t *work = worklist + (size_t)b * cap + bases[1];
+        for (int i = tid; i < tk; i += NMS_THREADS) {
+            const int e = kept_pos[i];
+            const int ey = e / EW, ex = e - ey * EW;
+            surv[i] = make_uint2((uint32_t)((ty0 + ey - E) * W + tx0 + ex - E), __float_as_uint(v[e]));
+        }
+        for (int i = tid; i < tu; i += NMS_THREADS) work[i] = stg_un[i];
+        return;
+    }
+
+    // ---- 4b. dense path: write the interior once; survivors / unresolved pixels are staged in shared
+    //          memory (the mask and id arrays are unused here) and leave as two contiguous runs ----
     constexpr int KCAP = CAP, UCAP = (3 * CAP) / 2;  // uint2 over mask[], uint32 over pos/ids
     uint2 *stg_kept = reinterpret_cast<uint2 *>(mask);
     uint32_t *stg_un = reinterpret_cast<uint32_t *>(pos);
@@ -915,7 +997,7 @@ static int launch_tile_fast(const float *prob, float *out, int B, int H, int W, 
                             cudaStream_t s) {
     constexpr int EH = TH + 2 * E, EW = TW + 2 * E;
     constexpr int BW = (EW + 31) / 32 + 1;
-    constexpr size_t smem = (size_t)EH * EW * sizeof(float) + (size_t)CAP * (sizeof(uint64_t) + 3 * sizeof(uint16_t)) +
+    constexpr size_t smem = (size_t)EH * EW * sizeof(float) + (size_t)CAP * (sizeof(uint64_t) + 4 * sizeof(uint16_t)) +
                             (size_t)EH * BW * sizeof(uint32_t);
     dim3 grid((W + TW - 1) / TW, (H + TH - 1) / TH, B);
     if (vec) {

@@ -95,8 +95,7 @@ __device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t (&r)[32])
           "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
         : "memory");
 }
-__device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
-    uint32_t r[32];
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -106,10 +105,9 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
           "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
           "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+// tcgen05.ld is asynchronous: the registers are valid only after this wait
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // UMMA shared-memory descriptor, K-major operand, 128-byte swizzle (cute::UMMA::SmemDescriptor):
 //   [0,14) start address >> 4   [16,30) leading byte offset >> 4 (=1, unused for swizzled K-major)
@@ -310,12 +308,20 @@ match_top2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
             mbar_wait(bar_acc_full(t), (nt / ACC) & 1);
             tc_fence_after();
             const int n0 = nt * TC_BN;
-#pragma unroll 1
-            for (int c = half; c < TC_BN / 32; c += 2) {
-                const int col0 = n0 + c * 32;
-                if (col0 >= n_b) break;
-                float v[32];
-                tc_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(t * TC_BN + c * 32), v);
+            // both of this warp's chunks are pulled out of tensor memory first, then the accumulator
+            // stage is handed back to the MMA warp before any of the arg-top-3 arithmetic runs
+            uint32_t va[32], vb[32];
+            const int c0 = half, c1 = half + 2;
+            const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(t * TC_BN);
+            const bool have0 = n0 + c0 * 32 < n_b, have1 = n0 + c1 * 32 < n_b;
+            if (have0) tc_ld32(tbase + (uint32_t)(c0 * 32), va);
+            if (have1) tc_ld32(tbase + (uint32_t)(c1 * 32), vb);
+            tc_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_acc_empty(t));
+
+            auto process = [&](const uint32_t (&v)[32], int col0) {
                 // per-column additive term: C (NN) or C - |b|^2/2 (L2); one coalesced load + shuffles
                 float add_lane = C;
                 if (use_bias && col0 + lane < n_b) add_lane = fmaf(-0.5f, __ldg(bias + col0 + lane), C);
@@ -325,7 +331,7 @@ match_top2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     const float add = use_bias ? __shfl_sync(0xffffffffu, add_lane, j) : C;
-                    uint32_t x = (__float_as_uint(v[j] + add) & ~31u) | (uint32_t)(31 - j);
+                    uint32_t x = (__float_as_uint(__uint_as_float(v[j]) + add) & ~31u) | (uint32_t)(31 - j);
                     if (!full && col0 + j >= n_b) x = 0;
                     t4[j & 3] = max(t4[j & 3], min(x, s4[j & 3]));
                     s4[j & 3] = max(s4[j & 3], min(x, b4[j & 3]));
@@ -348,10 +354,9 @@ match_top2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
                 merge3(best, second, third, cb, cs, t4[0]);
                 if (best != old_best) best_chunk = chunk;
                 if (second != old_second) second_chunk = (second == old_best && best != old_best) ? old_best_chunk : chunk;
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_acc_empty(t));
+            };
+            if (have0) process(va, n0 + c0 * 32);
+            if (have1) process(vb, n0 + c1 * 32);
         }
         // merge the two column subsets of each row (operand smem is free: every MMA has completed)
         uint32_t *mrg = reinterpret_cast<uint32_t *>(smem_raw + (base - smem_u32(smem_raw)));
