@@ -253,6 +253,7 @@ match_recheck_pair_kernel(const float *__restrict__ d1, int N1, const float *__r
 // halving exchange (18 shuffles instead of 80), so row r's total lands in the lanes with
 // ((lane >> 2) & 7) == r.
 constexpr int RK_ROWS = 8, RK_Z = 4, RK_WARPS = 8, RK_MAXD = 256;
+constexpr int RK_ROW_MAX = 16, RK_ROW_Y = 16;  // groups with <= RK_ROW_MAX rows use match_recheck_row_kernel
 
 template <int DPL>  // elements per lane: D <= 32*DPL
 __global__ void __launch_bounds__(RK_WARPS * 32)
@@ -265,7 +266,8 @@ match_recheck_kernel(const float *__restrict__ d1, const int32_t *__restrict__ n
     const int group = blockIdx.x, p = group >> 1, side = group & 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int count = n_flagged[group];
-    const int NA = side == 0 ? N1 : N2, NB = side == 0 ? N2 : N1;
+    if (count <= RK_ROW_MAX) return;  // handled by match_recheck_row_kernel
+    const int NA = side == 0 ? N1 : N2;
     const float *A = side == 0 ? d1 + (size_t)p * N1 * D : d2 + (size_t)p * N2 * D;
     const float *Bm = side == 0 ? d2 + (size_t)p * N2 * D : d1 + (size_t)p * N1 * D;
     const int32_t *rows = (side == 0 ? flagged1 : flagged2) + (size_t)p * NA;
@@ -361,6 +363,94 @@ match_recheck_kernel(const float *__restrict__ d1, const int32_t *__restrict__ n
                 if (k < bk || (k == bk && i < bi)) { bk = k; bi = i; }
             }
             dst[rows[c0 + threadIdx.x]] = bi == 0x7fffffff ? -1 : bi;
+        }
+    }
+}
+
+// Few rows on a group's full list (the usual case: a handful per call): one 1024-thread CTA per
+// row, 32 warps striding over the other set's rows two at a time with the next two prefetched.
+// The 8-row kernel above amortises the other set's traffic better but its single chunk per group
+// runs at the latency of one CTA walking 2 MB alone; it takes over when a group has more than
+// RK_ROW_MAX flagged rows.
+
+template <int DPL>
+__global__ void __launch_bounds__(1024)
+match_recheck_row_kernel(const float *__restrict__ d1, const int32_t *__restrict__ n1, int N1,
+                         const float *__restrict__ d2, const int32_t *__restrict__ n2, int N2, int D, int metric,
+                         const int32_t *__restrict__ flagged1, const int32_t *__restrict__ flagged2,
+                         const int *__restrict__ n_flagged, int32_t *__restrict__ idx12, int32_t *__restrict__ idx21) {
+    __shared__ double red_key[32];
+    __shared__ int red_idx[32];
+    const int group = blockIdx.x, p = group >> 1, side = group & 1;
+    const int count = n_flagged[group];
+    if (count == 0 || count > RK_ROW_MAX) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int NA = side == 0 ? N1 : N2;
+    const float *A = side == 0 ? d1 + (size_t)p * N1 * D : d2 + (size_t)p * N2 * D;
+    const float *Bm = side == 0 ? d2 + (size_t)p * N2 * D : d1 + (size_t)p * N1 * D;
+    const int32_t *rows = (side == 0 ? flagged1 : flagged2) + (size_t)p * NA;
+    int32_t *dst = side == 0 ? idx12 + (size_t)p * N1 : idx21 + (size_t)p * N2;
+    const int nb = side == 0 ? (n2 ? min(n2[p], N2) : N2) : (n1 ? min(n1[p], N1) : N1);
+    for (int item = blockIdx.y; item < count; item += RK_ROW_Y) {
+        const int row = rows[item];
+        double a[DPL];
+#pragma unroll
+        for (int i = 0; i < DPL; ++i) {
+            const int k = lane + 32 * i;
+            a[i] = k < D ? (double)A[(size_t)row * D + k] : 0.0;
+        }
+        auto fetch = [&](int j, float (&dstv)[DPL]) {
+#pragma unroll
+            for (int i = 0; i < DPL; ++i) {
+                const int k = lane + 32 * i;
+                dstv[i] = (j < nb && k < D) ? __ldg(Bm + (size_t)j * D + k) : 0.f;
+            }
+        };
+        float nx[2][DPL];
+        fetch(warp * 2, nx[0]);
+        fetch(warp * 2 + 1, nx[1]);
+        double best = INFINITY;
+        int bidx = 0x7fffffff;
+        for (int j = warp * 2; j < nb; j += 64) {
+            float cur[2][DPL];
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+#pragma unroll
+                for (int i = 0; i < DPL; ++i) cur[c][i] = nx[c][i];
+            fetch(j + 64, nx[0]);
+            fetch(j + 65, nx[1]);
+            double acc[2] = {0.0, 0.0};
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                if (metric == MP_METRIC_NN) {
+#pragma unroll
+                    for (int i = 0; i < DPL; ++i) acc[c] = fma(a[i], (double)cur[c][i], acc[c]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < DPL; ++i) { const double df = a[i] - (double)cur[c][i]; acc[c] = fma(df, df, acc[c]); }
+                }
+            }
+#pragma unroll
+            for (int sft = 16; sft > 0; sft >>= 1) {
+                acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], sft);
+                acc[1] += __shfl_xor_sync(0xffffffffu, acc[1], sft);
+            }
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                double key = acc[c];
+                if (metric == MP_METRIC_NN) key = -fmin(1.0, fmax(-1.0, key));
+                if (j + c < nb && key < best) { best = key; bidx = j + c; }
+            }
+        }
+        __syncthreads();
+        if (lane == 0) { red_key[warp] = best; red_idx[warp] = bidx; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double bk = INFINITY;
+            int bi = 0x7fffffff;
+            for (int w = 0; w < 32; ++w)
+                if (red_key[w] < bk || (red_key[w] == bk && red_idx[w] < bi)) { bk = red_key[w]; bi = red_idx[w]; }
+            dst[row] = bi == 0x7fffffff ? -1 : bi;
         }
     }
 }
@@ -688,6 +778,13 @@ static int run_nearest(const float *d1, const int32_t *n1, int N1, const float *
         else if (D <= 128) MP_RECHECK(4);
         else MP_RECHECK(8);
 #undef MP_RECHECK
+        MP_LAUNCH_OK();
+        dim3 grid_row(2 * P, RK_ROW_Y);
+#define MP_RECHECK_ROW(DPL) match_recheck_row_kernel<DPL><<<grid_row, 1024, 0, s>>>(d1, n1, N1, d2, n2, N2, D, metric, flagged1, flagged2, n_flagged, idx12, idx21)
+        if (D <= 64) MP_RECHECK_ROW(2);
+        else if (D <= 128) MP_RECHECK_ROW(4);
+        else MP_RECHECK_ROW(8);
+#undef MP_RECHECK_ROW
     } else {
         dim3 grid(2 * P, 32);
         match_recheck_generic_kernel<<<grid, 256, sizeof(double) * D, s>>>(d1, n1, N1, d2, n2, N2, D, metric, flagged1, flagged2, n_flagged, idx12, idx21);

@@ -290,6 +290,24 @@ def test_nearest_equals_fp64_truth(ops, oracle, algo, metric):
         assert np.abs(res["best12"][0].cpu().numpy() - best).max() < 4e-5
 
 
+@pytest.mark.parametrize("algo", ["simt", "tensor"])
+def test_nearest_with_heavy_exact_ties(ops, oracle, algo):
+    """Every descriptor of set 2 appears four times (exact 4-way ties for every query, the lowest
+    index must win) and a few only twice: exercises the full-rescan kernels (many rows per group,
+    and few rows per group) and the two-candidate exact recheck."""
+    a, b0 = syn.descriptor_sets(411, 200, 60, 64, 0.05)
+    b = np.concatenate([b0, b0, b0, b0])                       # 240 rows: 4 copies each
+    a2, c0 = syn.descriptor_sets(412, 150, 150, 64, 0.05)
+    c = c0.copy(); c[100:110] = c0[20:30]                      # ten 2-way ties
+    d = c0.copy(); d[100:103] = c0[5:8]; d[120:123] = c0[5:8]  # three 3-way ties: few full-list rows
+    for x, y in ((a, b), (a2, c), (a2, d)):
+        for metric, mode in (("nn", "nn"), ("l2", "bf")):
+            res = ops.nearest(cu(x), cu(y), metric=metric, algo=algo)
+            want = oracle.nearest(x, y, mode, f64=True)
+            np.testing.assert_array_equal(res["idx12"][0].cpu().numpy(), want["idx12"])
+            np.testing.assert_array_equal(res["idx21"][0].cpu().numpy(), want["idx21"])
+
+
 def test_matching_batched_counts_and_empty(ops, oracle):
     """P pairs in one call with per-pair valid counts (the pipeline's layout), vs per-pair oracle."""
     P, N, D = 3, 384, 64
