@@ -353,12 +353,57 @@ def main():
     except Exception:
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    dom = "nms_tile(+fixup launch)"
-    roofline = {"kernel": "nms_tile_kernel<32,128,8> (timed as mp_box_nms_f32 without top-k: tile kernel + the fix-up launch that exits immediately)",
-                "bound": "hbm", "achieved": kernels[dom]["algorithmic_GBps"], "peak": hbm_peak, "unit": "GB/s",
-                "frac": kernels[dom]["algorithmic_GBps"] / hbm_peak,
-                "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
-                "algorithmic_bytes_per_launch": B2 * 2 * H * W * 4, "traffic": None}
+    tf_peak = float(peaks.get("bf16_tflops", 1590.0))
+    peak_src = "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md: 6650 GB/s, 1590 TFLOP/s)"
+
+    # ---- per-kernel durations: CUDA events recorded by the library on the launching stream, after
+    #      every one of its kernels, over K more hot-path steps (mp_profile_begin / mp_profile_end)
+    hot()
+    torch.cuda.synchronize()
+    _lib.profile_begin()
+    for _ in range(K):
+        hot()
+    torch.cuda.synchronize()
+    prof = _lib.profile_end()
+    Kp, Dd = args.topk, args.desc
+    algorithmic = {  # per launch: ("hbm", bytes) or ("tensor", flops); SURVEY.md 8d / DESIGN.md section 4
+        "detector_head_kernel": ("hbm", B2 * (65 * 5120 * 4 + H * W * 4)),
+        "nms_tile_fast_kernel": ("hbm", B2 * 2 * H * W * 4),
+        "normalize_desc_kernel": ("hbm", B2 * 2 * 4 * Dd * 5120),
+        "sample_descriptors_kernel": ("hbm", B2 * (min(16 * Kp * Dd, 4 * Dd * 5120) + 4 * Kp * Dd + 16 * Kp)),
+        "match_prep_vec_kernel": ("hbm", P * Kp * Dd * (4 + 2 + 2)),
+        "match_top2_tc_kernel": ("tensor", 2.0 * P * Kp * Kp * Dd),
+    }
+    kernel_rows = []
+    for name, rec in sorted(prof.items(), key=lambda kv: -kv[1]["total_ms"]):
+        avg_ms = rec["total_ms"] / max(rec["launches"], 1)
+        row = {"kernel": name, "launches_per_step": rec["launches"] / K, "avg_us": round(avg_ms * 1e3, 2),
+               "ms_per_step": round(rec["total_ms"] / K, 4)}
+        if name in algorithmic:
+            kind, work = algorithmic[name]
+            row["bound"] = kind
+            if kind == "hbm":
+                row.update(algorithmic_bytes_per_launch=work, achieved_GBps=round(work / avg_ms / 1e6, 1),
+                           frac=round(work / avg_ms / 1e6 / hbm_peak, 4))
+            else:
+                row.update(algorithmic_flop_per_launch=work, achieved_TFLOPs=round(work / avg_ms / 1e9, 1),
+                           frac=round(work / avg_ms / 1e9 / tf_peak, 4),
+                           executed_TFLOPs=round(3 * work / avg_ms / 1e9, 1), executed_frac=round(3 * work / avg_ms / 1e9 / tf_peak, 4))
+        kernel_rows.append(row)
+    dom = next((r for r in kernel_rows if "bound" in r), None)   # the largest share of the hot path among the kernels with a roofline
+    if dom is not None and dom["bound"] == "tensor":
+        roofline = {"kernel": dom["kernel"], "bound": "tensor", "achieved": dom["achieved_TFLOPs"], "peak": tf_peak, "unit": "TFLOP/s",
+                    "frac": dom["frac"], "traffic": None, "avg_launch_us": dom["avg_us"], "launches_per_step": dom["launches_per_step"],
+                    "algorithmic_flop_per_launch": dom["algorithmic_flop_per_launch"],
+                    "executed": {"TFLOP/s": dom["executed_TFLOPs"], "frac": dom["executed_frac"],
+                                 "note": "3 bf16 MMA passes (hi*hi, hi*mid, mid*hi) per algorithmic fp32 product"},
+                    "peak_source": peak_src + " bf16_tflops (burst)"}
+    elif dom is not None:
+        roofline = {"kernel": dom["kernel"], "bound": "hbm", "achieved": dom["achieved_GBps"], "peak": hbm_peak, "unit": "GB/s",
+                    "frac": dom["frac"], "traffic": None, "avg_launch_us": dom["avg_us"], "launches_per_step": dom["launches_per_step"],
+                    "algorithmic_bytes_per_launch": dom["algorithmic_bytes_per_launch"], "peak_source": peak_src + " hbm_gbs"}
+    else:
+        roofline = None
 
     line = {"metric": METRIC, "value": P * world * 1000.0 / ms_value, "unit": "pairs/s", "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": ms_value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -367,9 +412,18 @@ def main():
                     "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},
             "gpu_launches": int(launches),
             "hot_path": {"value": P * world * 1000.0 / ms_hot, "unit": "pairs/s", "ms_per_step": ms_hot,
-                         "note": "backbone outputs resident in HBM; everything after cuDNN", "stages": kernels},
+                         "note": "backbone outputs resident in HBM; everything after cuDNN", "stages": kernels,
+                         "kernels": kernel_rows},
             "roofline": roofline,
             "result_check": {"keypoints_per_step": n_kp, "matches_per_step": n_matches}}
+
+    # context only (not the headline): the same resident step with cuDNN allowed to use TF32 tensor cores
+    # for the backbone convolutions -- PyTorch's own default, and what the reference would run on a GPU
+    torch.backends.cudnn.allow_tf32 = True
+    ms_tf32 = timed(step_resident, max(3, K // 2), 3)
+    torch.backends.cudnn.allow_tf32 = False
+    line["backbone_tf32_context"] = {"value": P * world * 1000.0 / ms_tf32, "unit": "pairs/s", "ms_per_step": ms_tf32,
+                                     "note": "cudnn.allow_tf32=True for the backbone only; reported for context, headline stays fp32"}
 
     if world == 1 and rank == 0 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1

@@ -42,6 +42,13 @@ MP_API int mp_version(void);
 MP_API const char *mp_last_error_string(void);
 /* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
 MP_API unsigned long long mp_launch_count(void);
+/* Per-kernel timing (bench.py's roofline): between mp_profile_begin and mp_profile_end every kernel
+ * launch of this library is followed by a CUDA event on its launching stream and every API call
+ * starts with one; a kernel's duration is the gap to the previous event on that stream.
+ * mp_profile_end synchronises those events, writes {"kernel": {"launches": n, "total_ms": t}, ...}
+ * as JSON into buf (truncated to cap) and returns the size needed. */
+MP_API int mp_profile_begin(void);
+MP_API size_t mp_profile_end(char *buf, size_t cap);
 
 /* ---- row 1: MultiPoint.detector_head, multipoint/models/MultiPoint.py:150-158 ------------
  * softmax over 65 channels, dustbin drop, PixelShuffle(8):

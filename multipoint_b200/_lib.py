@@ -19,6 +19,8 @@ SIGNATURES = {
     "mp_version": (_i, []),
     "mp_last_error_string": (_c.c_char_p, []),
     "mp_launch_count": (_c.c_ulonglong, []),
+    "mp_profile_begin": (_i, []),
+    "mp_profile_end": (_sz, [_c.c_char_p, _sz]),
     "mp_detector_head_f32": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
     "mp_depth_to_space_f32": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "mp_normalize_descriptors_f32": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
@@ -74,3 +76,16 @@ def check(status, what):
 
 def launch_count():
     return int(load().mp_launch_count())
+
+
+def profile_begin():
+    load().mp_profile_begin()
+
+
+def profile_end():
+    """-> {kernel_name: {"launches": n, "total_ms": t}} measured with CUDA events on the launching stream."""
+    import json
+    lib = load()
+    buf = ctypes.create_string_buffer(1 << 16)
+    lib.mp_profile_end(buf, len(buf))
+    return json.loads(buf.value.decode() or "{}")

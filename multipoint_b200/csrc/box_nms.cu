@@ -987,7 +987,7 @@ static int launch_tile(const float *prob, float *out, int B, int H, int W, float
         MP_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k<<<grid, NMS_THREADS, smem, s>>>(prob, out, H, W, thr, fp, surv, surv_count, work, work_count, cap);
     }
-    MP_LAUNCH_OK();
+    MP_LAUNCH_OK_S("nms_tile_kernel", s);
     return MP_OK;
 }
 
@@ -1009,7 +1009,7 @@ static int launch_tile_fast(const float *prob, float *out, int B, int H, int W, 
         MP_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k<<<grid, NMS_THREADS, smem, s>>>(prob, out, H, W, thr, fp, surv, surv_count, work, work_count, cap);
     }
-    MP_LAUNCH_OK();
+    MP_LAUNCH_OK_S("nms_tile_fast_kernel", s);
     return MP_OK;
 }
 
@@ -1024,6 +1024,7 @@ extern "C" int mp_box_nms_f32(const float *prob, int B, int H, int W, double siz
                               double iou, int keep_top_k, float *prob_nms, int64_t *keypoints,
                               float *kp_scores, int32_t *kp_counts, int kp_cap, void *workspace,
                               size_t workspace_bytes, mp_stream_t stream) {
+    mp::prof_entry((cudaStream_t)stream);
     using namespace mp;
     MP_CHECK_ARG(B >= 0 && H > 0 && W > 0, "mp_box_nms_f32: bad shape B=%d H=%d W=%d", B, H, W);
     MP_CHECK_ARG((long long)H * W < (1ll << 31), "mp_box_nms_f32: image too large");
@@ -1089,12 +1090,12 @@ extern "C" int mp_box_nms_f32(const float *prob, int B, int H, int W, double siz
     if (rc != MP_OK) return rc;
 
     nms_fixup_kernel<<<B, 1024, 0, s>>>(prob_nms, H, W, fp, surv, surv_count, work, work_count, L.cap);
-    MP_LAUNCH_OK();
+    MP_LAUNCH_OK_S("nms_fixup_kernel", s);
 
     if (keep_top_k > 0 || keypoints != nullptr || kp_counts != nullptr) {
         nms_select_kernel<<<B, 1024, 0, s>>>(prob_nms, H, W, keep_top_k, surv, surv_count, L.cap, bitmaps, L.words,
                                              keypoints, kp_scores, kp_counts, kp_cap);
-        MP_LAUNCH_OK();
+        MP_LAUNCH_OK_S("nms_select_kernel", s);
     }
     return MP_OK;
 }
@@ -1108,6 +1109,7 @@ extern "C" int mp_extract_keypoints_f32(const float *prob, const uint8_t *mask, 
                                         double threshold, int64_t *keypoints, float *kp_scores,
                                         int32_t *kp_counts, int kp_cap, void *workspace,
                                         size_t workspace_bytes, mp_stream_t stream) {
+    mp::prof_entry((cudaStream_t)stream);
     using namespace mp;
     MP_CHECK_ARG(B >= 0 && H > 0 && W > 0 && kp_cap >= 0, "mp_extract_keypoints_f32: bad shape");
     MP_CHECK_ARG((long long)H * W < (1ll << 31), "mp_extract_keypoints_f32: image too large");
@@ -1123,8 +1125,8 @@ extern "C" int mp_extract_keypoints_f32(const float *prob, const uint8_t *mask, 
     cudaStream_t s = (cudaStream_t)stream;
     dim3 grid((HW + 255) / 256, B);
     threshold_bitmap_kernel<<<grid, 256, 0, s>>>(prob, mask, HW, (float)threshold, bitmaps, words);
-    MP_LAUNCH_OK();
+    MP_LAUNCH_OK_S("threshold_bitmap_kernel", s);
     emit_keypoints_kernel<<<B, 1024, 0, s>>>(prob, H, W, bitmaps, words, keypoints, kp_scores, kp_counts, kp_cap);
-    MP_LAUNCH_OK();
+    MP_LAUNCH_OK_S("emit_keypoints_kernel", s);
     return MP_OK;
 }

@@ -93,6 +93,7 @@ __global__ void normalize_desc_generic_kernel(const float *__restrict__ x, float
 
 extern "C" int mp_normalize_descriptors_f32(const float *x, int B, int D, int HW, float *out_nchw,
                                             float *out_nhwc, mp_stream_t stream) {
+    mp::prof_entry((cudaStream_t)stream);
     MP_CHECK_ARG(x != nullptr, "mp_normalize_descriptors_f32: null input");
     MP_CHECK_ARG(out_nchw || out_nhwc, "mp_normalize_descriptors_f32: no output requested");
     MP_CHECK_ARG(B >= 0 && D > 0 && HW > 0, "mp_normalize_descriptors_f32: bad shape B=%d D=%d HW=%d", B, D, HW);
@@ -111,6 +112,6 @@ extern "C" int mp_normalize_descriptors_f32(const float *x, int B, int D, int HW
         const long long total = (long long)B * HW;
         mp::normalize_desc_generic_kernel<<<(unsigned)((total + 127) / 128), 128, 0, s>>>(x, out_nchw, out_nhwc, B, D, HW);
     }
-    MP_LAUNCH_OK();
+    MP_LAUNCH_OK_S("normalize_desc_kernel", s);
     return MP_OK;
 }

@@ -119,6 +119,7 @@ __global__ void depth_to_space_kernel(const float *__restrict__ x, float *__rest
 
 extern "C" int mp_detector_head_f32(const float *logits, int B, int Hc, int Wc,
                                     const uint8_t *valid_mask, float *prob, mp_stream_t stream) {
+    mp::prof_entry((cudaStream_t)stream);
     MP_CHECK_ARG(logits && prob, "mp_detector_head_f32: null pointer");
     MP_CHECK_ARG(B >= 0 && Hc > 0 && Wc > 0, "mp_detector_head_f32: bad shape B=%d Hc=%d Wc=%d", B, Hc, Wc);
     MP_CHECK_ARG(((uintptr_t)prob & 15) == 0, "mp_detector_head_f32: prob must be 16-byte aligned");
@@ -130,18 +131,19 @@ extern "C" int mp_detector_head_f32(const float *logits, int B, int Hc, int Wc,
     const unsigned grid = (unsigned)((units + mp::DH_WARPS - 1) / mp::DH_WARPS);
     mp::detector_head_kernel<<<grid, mp::DH_WARPS * 32, 0, (cudaStream_t)stream>>>(
         logits, valid_mask, prob, total, Hc * Wc, Wc);
-    MP_LAUNCH_OK();
+    MP_LAUNCH_OK_S("detector_head_kernel", (cudaStream_t)stream);
     return MP_OK;
 }
 
 extern "C" int mp_depth_to_space_f32(const float *x, int B, int C, int Hc, int Wc, int block,
                                      float *out, mp_stream_t stream) {
+    mp::prof_entry((cudaStream_t)stream);
     MP_CHECK_ARG(x && out, "mp_depth_to_space_f32: null pointer");
     MP_CHECK_ARG(B >= 0 && C > 0 && Hc > 0 && Wc > 0 && block > 0, "mp_depth_to_space_f32: bad shape");
     const long long total = (long long)B * C * Hc * Wc * block * block;
     if (total == 0) return MP_OK;
     const unsigned grid = (unsigned)((total + 255) / 256);
     mp::depth_to_space_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, out, total, C, Hc, Wc, block);
-    MP_LAUNCH_OK();
+    MP_LAUNCH_OK_S("depth_to_space_kernel", (cudaStream_t)stream);
     return MP_OK;
 }

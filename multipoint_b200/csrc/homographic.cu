@@ -162,6 +162,7 @@ ha_aggregate_kernel(const float *__restrict__ prob0, const float *__restrict__ p
 extern "C" int mp_warp_f32(const float *src, int N, int n_mats, int H, int W, const float *A,
                            const float *xs, const float *ys, int mode, int padding, float *out,
                            mp_stream_t stream) {
+    mp::prof_entry((cudaStream_t)stream);
     MP_CHECK_ARG(N >= 0 && n_mats >= 0 && H > 0 && W > 0, "mp_warp_f32: bad shape");
     MP_CHECK_ARG(mode == MP_BILINEAR || mode == MP_NEAREST, "mp_warp_f32: bad mode %d", mode);
     MP_CHECK_ARG(padding == MP_PAD_ZEROS || padding == MP_PAD_REFLECTION, "mp_warp_f32: bad padding %d", padding);
@@ -170,7 +171,7 @@ extern "C" int mp_warp_f32(const float *src, int N, int n_mats, int H, int W, co
     MP_CHECK_ARG(src && A && xs && ys && out, "mp_warp_f32: null pointer");
     dim3 grid((W + 31) / 32, (H + 7) / 8, n_mats), block(32, 8);
     mp::warp_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(src, N, H, W, A, xs, ys, mode, padding, out);
-    MP_LAUNCH_OK();
+    MP_LAUNCH_OK_S("warp_kernel", (cudaStream_t)stream);
     return MP_OK;
 }
 
@@ -179,6 +180,7 @@ extern "C" int mp_ha_aggregate_f32(const float *prob0, const float *probw_a, con
                                    const float *xs, const float *ys, int aggregation, int min_count,
                                    int flags, float *prob_acc, float *count_acc, float *out,
                                    mp_stream_t stream) {
+    mp::prof_entry((cudaStream_t)stream);
     using namespace mp;
     MP_CHECK_ARG(n >= 0 && B >= 0 && H > 0 && W > 0, "mp_ha_aggregate_f32: bad shape");
     MP_CHECK_ARG(aggregation == MP_AGG_NONE || aggregation == MP_AGG_PROD || aggregation == MP_AGG_SUM,
@@ -208,6 +210,6 @@ extern "C" int mp_ha_aggregate_f32(const float *prob0, const float *probw_a, con
     else if (aggregation == MP_AGG_SUM) MP_HA_LAUNCH(MP_AGG_SUM, true);
     else MP_HA_LAUNCH(MP_AGG_NONE, false);
 #undef MP_HA_LAUNCH
-    MP_LAUNCH_OK();
+    MP_LAUNCH_OK_S("ha_aggregate_kernel", s);
     return MP_OK;
 }

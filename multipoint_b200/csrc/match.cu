@@ -745,9 +745,9 @@ static int run_nearest(const float *d1, const int32_t *n1, int N1, const float *
         else match_prep_vec_kernel<1><<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(d, n, N, D, P, norms, mx, h, m);
     };
     prep(d1, n1, N1, r1, norms1, max1, hi1, mid1);
-    MP_LAUNCH_OK();
+    MP_LAUNCH_OK_S("match_prep_vec_kernel", s);
     prep(d2, n2, N2, r2, norms2, max2, hi2, mid2);
-    MP_LAUNCH_OK();
+    MP_LAUNCH_OK_S("match_prep_vec_kernel", s);
 
     if (tensor) {
         int rc = match_top2_tensor(hi1, mid1, n1, N1, hi2, mid2, n2, N2, P, D, norms2, use_bias, max1, max2, top12, s);
@@ -757,19 +757,19 @@ static int run_nearest(const float *d1, const int32_t *n1, int N1, const float *
     } else {
         dim3 g1((N1 + ST_ROWS - 1) / ST_ROWS, P), g2((N2 + ST_ROWS - 1) / ST_ROWS, P);
         match_top2_simt_kernel<<<g1, ST_ROWS, 0, s>>>(d1, n1, N1, d2, n2, N2, D, norms2, use_bias, top12);
-        MP_LAUNCH_OK();
+        MP_LAUNCH_OK_S("match_top2_simt_kernel", s);
         match_top2_simt_kernel<<<g2, ST_ROWS, 0, s>>>(d2, n2, N2, d1, n1, N1, D, norms1, use_bias, top21);
-        MP_LAUNCH_OK();
+        MP_LAUNCH_OK_S("match_top2_simt_kernel", s);
     }
     const float eps_rel = tensor ? MATCH_EPS_TENSOR : MATCH_EPS_SIMT, pack_rel = tensor ? MATCH_PACK_REL : 0.f;
     match_flag_kernel<<<(unsigned)((r1 + 255) / 256), 256, 0, s>>>(top12, N1, P, max1, max2, metric, eps_rel, pack_rel, 0, idx12, flagged1, n_flagged, pairs1, n_pairs);
-    MP_LAUNCH_OK();
+    MP_LAUNCH_OK_S("match_flag_kernel", s);
     match_flag_kernel<<<(unsigned)((r2 + 255) / 256), 256, 0, s>>>(top21, N2, P, max2, max1, metric, eps_rel, pack_rel, 1, idx21, flagged2, n_flagged, pairs2, n_pairs);
-    MP_LAUNCH_OK();
+    MP_LAUNCH_OK_S("match_flag_kernel", s);
     {
         dim3 grid(2 * P, RP_Y);
         match_recheck_pair_kernel<<<grid, 256, 0, s>>>(d1, N1, d2, N2, D, metric, top12, top21, pairs1, pairs2, n_pairs, idx12, idx21);
-        MP_LAUNCH_OK();
+        MP_LAUNCH_OK_S("match_recheck_pair_kernel", s);
     }
     if (D <= RK_MAXD) {
         dim3 grid(2 * P, RK_Z);
@@ -778,18 +778,19 @@ static int run_nearest(const float *d1, const int32_t *n1, int N1, const float *
         else if (D <= 128) MP_RECHECK(4);
         else MP_RECHECK(8);
 #undef MP_RECHECK
-        MP_LAUNCH_OK();
+        MP_LAUNCH_OK_S("match_recheck_kernel", s);
         dim3 grid_row(2 * P, RK_ROW_Y);
 #define MP_RECHECK_ROW(DPL) match_recheck_row_kernel<DPL><<<grid_row, 1024, 0, s>>>(d1, n1, N1, d2, n2, N2, D, metric, flagged1, flagged2, n_flagged, idx12, idx21)
         if (D <= 64) MP_RECHECK_ROW(2);
         else if (D <= 128) MP_RECHECK_ROW(4);
         else MP_RECHECK_ROW(8);
 #undef MP_RECHECK_ROW
+        MP_LAUNCH_OK_S("match_recheck_row_kernel", s);
     } else {
         dim3 grid(2 * P, 32);
         match_recheck_generic_kernel<<<grid, 256, sizeof(double) * D, s>>>(d1, n1, N1, d2, n2, N2, D, metric, flagged1, flagged2, n_flagged, idx12, idx21);
+        MP_LAUNCH_OK_S("match_recheck_generic_kernel", s);
     }
-    MP_LAUNCH_OK();
     return MP_OK;
 }
 
@@ -829,6 +830,7 @@ extern "C" int mp_nearest_f32(const float *d1, const int32_t *n1, int N1, const 
                               int32_t *idx12, float *best12, float *second12, int32_t *idx21,
                               float *best21, float *second21, void *workspace,
                               size_t workspace_bytes, mp_stream_t stream) {
+    mp::prof_entry((cudaStream_t)stream);
     using namespace mp;
     const MatchLayout L(P > 0 ? P : 0, N1 > 0 ? N1 : 0, N2 > 0 ? N2 : 0, D > 0 ? D : 1);
     int rc = check_match_args("mp_nearest_f32", d1, N1, d2, N2, P, D, metric, algo, workspace, workspace_bytes, L);
@@ -836,8 +838,8 @@ extern "C" int mp_nearest_f32(const float *d1, const int32_t *n1, int N1, const 
     cudaStream_t s = (cudaStream_t)stream;
     const long long r1 = (long long)P * N1, r2 = (long long)P * N2;
     if (r1 == 0 || r2 == 0) {  // one side empty: no neighbours
-        if (r1 && idx12) { fill_i32_kernel<<<(unsigned)((r1 + 255) / 256), 256, 0, s>>>(idx12, r1, -1); MP_LAUNCH_OK(); }
-        if (r2 && idx21) { fill_i32_kernel<<<(unsigned)((r2 + 255) / 256), 256, 0, s>>>(idx21, r2, -1); MP_LAUNCH_OK(); }
+        if (r1 && idx12) { fill_i32_kernel<<<(unsigned)((r1 + 255) / 256), 256, 0, s>>>(idx12, r1, -1); MP_LAUNCH_OK_S("fill_i32_kernel", s); }
+        if (r2 && idx21) { fill_i32_kernel<<<(unsigned)((r2 + 255) / 256), 256, 0, s>>>(idx21, r2, -1); MP_LAUNCH_OK_S("fill_i32_kernel", s); }
         return MP_OK;
     }
     char *ws = (char *)workspace;
@@ -848,11 +850,11 @@ extern "C" int mp_nearest_f32(const float *d1, const int32_t *n1, int N1, const 
     const int use_bias = metric == MP_METRIC_L2;
     if (best12 || second12) {
         match_export_kernel<<<(unsigned)((r1 + 255) / 256), 256, 0, s>>>((Top2 *)(ws + L.top12), (float *)(ws + L.norms2), N1, N2, P, use_bias, best12, second12);
-        MP_LAUNCH_OK();
+        MP_LAUNCH_OK_S("match_export_kernel", s);
     }
     if (best21 || second21) {
         match_export_kernel<<<(unsigned)((r2 + 255) / 256), 256, 0, s>>>((Top2 *)(ws + L.top21), (float *)(ws + L.norms1), N2, N1, P, use_bias, best21, second21);
-        MP_LAUNCH_OK();
+        MP_LAUNCH_OK_S("match_export_kernel", s);
     }
     return MP_OK;
 }
@@ -862,6 +864,7 @@ extern "C" int mp_match_f32(const float *d1, const int32_t *n1, int N1, const fl
                             int cross_check, double threshold, double ratio, int32_t *query,
                             int32_t *train, float *dist, int32_t *counts, void *workspace,
                             size_t workspace_bytes, mp_stream_t stream) {
+    mp::prof_entry((cudaStream_t)stream);
     using namespace mp;
     const MatchLayout L(P > 0 ? P : 0, N1 > 0 ? N1 : 0, N2 > 0 ? N2 : 0, D > 0 ? D : 1);
     int rc = check_match_args("mp_match_f32", d1, N1, d2, N2, P, D, metric, algo, workspace, workspace_bytes, L);
@@ -884,9 +887,9 @@ extern "C" int mp_match_f32(const float *d1, const int32_t *n1, int N1, const fl
     match_decide_kernel<<<(unsigned)((r1 + 7) / 8), 256, 0, s>>>(d1, n1, N1, d2, N2, P, D, metric, kind, cross_check,
                                                                (float)threshold, (float)ratio, (int32_t *)(ws + L.idx12),
                                                                (int32_t *)(ws + L.idx21), (Top2 *)(ws + L.top12), train_tmp, dist_tmp);
-    MP_LAUNCH_OK();
+    MP_LAUNCH_OK_S("match_decide_kernel", s);
     match_compact_kernel<<<P, 1024, 0, s>>>(train_tmp, dist_tmp, N1, query, train, dist, counts);
-    MP_LAUNCH_OK();
+    MP_LAUNCH_OK_S("match_compact_kernel", s);
     return MP_OK;
 }
 
@@ -894,6 +897,7 @@ extern "C" int mp_match_threshold_f32(const float *d1, int N1, const float *d2, 
                                       double threshold, int32_t *query, int32_t *train, float *dist,
                                       int64_t cap, int64_t *total_host, void *workspace,
                                       size_t workspace_bytes, mp_stream_t stream) {
+    mp::prof_entry((cudaStream_t)stream);
     using namespace mp;
     MP_CHECK_ARG(N1 >= 0 && N2 >= 0 && D > 0 && cap >= 0, "mp_match_threshold_f32: bad shape");
     MP_CHECK_ARG(total_host != nullptr, "mp_match_threshold_f32: total_host is required");
@@ -909,13 +913,13 @@ extern "C" int mp_match_threshold_f32(const float *d1, int N1, const float *d2, 
     long long *row_counts = (long long *)workspace, *row_offsets = row_counts + N1, *total = row_offsets + N1;
     const unsigned grid = (unsigned)((N1 + 7) / 8);
     threshold_rows_kernel<<<grid, 256, 0, s>>>(d1, N1, d2, N2, D, (float)threshold, nullptr, row_counts, nullptr, nullptr, nullptr, 0);
-    MP_LAUNCH_OK();
+    MP_LAUNCH_OK_S("threshold_rows_kernel", s);
     exclusive_scan_ll_kernel<<<1, 1024, 0, s>>>(row_counts, row_offsets, N1, total);
-    MP_LAUNCH_OK();
+    MP_LAUNCH_OK_S("exclusive_scan_ll_kernel", s);
     if (cap > 0) {
         MP_CHECK_ARG(query && train && dist, "mp_match_threshold_f32: null output pointer");
         threshold_rows_kernel<<<grid, 256, 0, s>>>(d1, N1, d2, N2, D, (float)threshold, row_offsets, nullptr, query, train, dist, cap);
-        MP_LAUNCH_OK();
+        MP_LAUNCH_OK_S("threshold_rows_kernel", s);
     }
     long long t = 0;
     MP_CUDA_OK(cudaMemcpyAsync(&t, total, sizeof(long long), cudaMemcpyDeviceToHost, s));

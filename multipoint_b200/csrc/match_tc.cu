@@ -455,7 +455,7 @@ static int launch_tc(const CUtensorMap &ah, const CUtensorMap &am, const CUtenso
     dim3 grid((NA + TC_BM - 1) / TC_BM, P);
     k<<<grid, TC_THREADS, TcSmem<KB, ATM>::TOTAL, s>>>(ah, am, bh, bm, a_hi, a_mid, na, NA, nb, NB, norms_b, use_bias,
                                                         max_a, max_b, top);
-    MP_LAUNCH_OK();
+    MP_LAUNCH_OK_S("match_top2_tc_kernel", s);
     return MP_OK;
 }
 

@@ -11,6 +11,10 @@ namespace mp {
 // ---- error reporting across the C ABI: thread-local message, integer status ----
 void set_error(const char *fmt, ...);
 void count_launch(unsigned n = 1);
+// profiling (mp_profile_begin / mp_profile_end): an event after each launch, one at each API entry;
+// a kernel's duration is the time between its event and the previous one on the same stream
+void prof_mark(const char *name, cudaStream_t stream);
+inline void prof_entry(cudaStream_t stream) { prof_mark(nullptr, stream); }
 
 #define MP_CHECK_ARG(cond, ...)                 \
     do {                                        \
@@ -29,9 +33,12 @@ void count_launch(unsigned n = 1);
         }                                                                                  \
     } while (0)
 
-#define MP_LAUNCH_OK()                                                                     \
+// after every kernel launch: count it, (when profiling) drop a CUDA event behind it on the launching
+// stream, and surface launch errors
+#define MP_LAUNCH_OK_S(name, stream)                                                       \
     do {                                                                                   \
         mp::count_launch();                                                                \
+        mp::prof_mark(name, (cudaStream_t)(stream));                                       \
         cudaError_t e__ = cudaGetLastError();                                              \
         if (e__ != cudaSuccess) {                                                          \
             mp::set_error("%s:%d: kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(e__)); \

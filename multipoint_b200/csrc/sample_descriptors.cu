@@ -160,6 +160,7 @@ sample_descriptors_nhwc_vec_kernel(const int64_t *__restrict__ kp, const int32_t
 extern "C" int mp_sample_descriptors_f32(const int64_t *keypoints, const int32_t *kp_counts, int B,
                                          int K, const float *desc, int D, int Hc, int Wc, int layout,
                                          int H, int W, float *out, mp_stream_t stream) {
+    mp::prof_entry((cudaStream_t)stream);
     MP_CHECK_ARG(B >= 0 && K >= 0 && D > 0 && Hc > 0 && Wc > 0 && H > 0 && W > 0,
                  "mp_sample_descriptors_f32: bad shape");
     MP_CHECK_ARG(D <= 32 * mp::SD_MAX_CPL, "mp_sample_descriptors_f32: D=%d > %d unsupported", D, 32 * mp::SD_MAX_CPL);
@@ -181,6 +182,6 @@ extern "C" int mp_sample_descriptors_f32(const int64_t *keypoints, const int32_t
     else
         mp::sample_descriptors_kernel<MP_LAYOUT_NCHW><<<grid, mp::SD_WARPS * 32, 0, (cudaStream_t)stream>>>(
             keypoints, kp_counts, desc, out, B, K, D, Hc, Wc, hh, hw);
-    MP_LAUNCH_OK();
+    MP_LAUNCH_OK_S("sample_descriptors_kernel", s);
     return MP_OK;
 }
