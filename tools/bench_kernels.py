@@ -73,6 +73,15 @@ def main():
     add("box_nms + top-k 2048 + keypoints B=128",
         timed(lambda: ops.box_nms(prob, 4, 0.015, keep_top_k=2048, want_keypoints=True, kp_cap=2048)), B * (2 * H * W * 4 + 20 * 2048))
     add("extract_keypoints B=128", timed(lambda: ops.extract_keypoints(prob, 0.2, kp_cap=4096)), B * H * W * 4)
+    # the same NMS on a sparser heatmap (a trained detector: ~2 % of the pixels above the threshold instead of the
+    # 12.8 % of the synthetic sigma=2 logits): the kernel is instruction-bound on candidates, not on pixels
+    for sigma, bias in ((3.0, 9.0), (4.0, 14.0)):
+        lg2 = torch.randn((B, 65, 64, 80), generator=g, device=dev) * sigma
+        lg2[:, 64] += bias
+        pr2 = ops.detector_head(lg2).reshape(B, H, W)
+        frac = float((pr2 > 0.015).float().mean())
+        add("box_nms dense B=128, %.1f%% candidates" % (100 * frac), timed(lambda: ops.box_nms(pr2, 4, 0.015)), B * 2 * H * W * 4)
+        del lg2, pr2
     for D in (256, 64):
         raw = torch.randn((B, D, 64, 80), generator=g, device=dev)
         add("normalize_descriptors NCHW D=%d" % D, timed(lambda: ops.normalize_descriptors(raw, True, False)), B * 2 * 4 * D * 5120)
