@@ -374,6 +374,17 @@ def main():
         "match_prep_vec_kernel": ("hbm", P * Kp * Dd * (4 + 2 + 2)),
         "match_top2_tc_kernel": ("tensor", 2.0 * P * Kp * Kp * Dd),
     }
+    # DRAM bytes per launch from the committed ncu --set full capture of this same workload (bench.py --only-hot);
+    # only meaningful at the default sizes the capture was taken at
+    traffic = {}
+    if (P, Kp, Dd, H, W) == (64, 2048, 256, 512, 640):
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")))
+            traffic = {k: v["dram_bytes"] for k, v in tj["per_launch"].items()}
+            traffic["sample_descriptors_kernel"] = traffic.get("sample_descriptors_nhwc_vec_kernel")
+            traffic_src = tj["source"]
+        except Exception:
+            traffic = {}
     kernel_rows = []
     for name, rec in sorted(prof.items(), key=lambda kv: -kv[1]["total_ms"]):
         avg_ms = rec["total_ms"] / max(rec["launches"], 1)
@@ -389,21 +400,26 @@ def main():
                 row.update(algorithmic_flop_per_launch=work, achieved_TFLOPs=round(work / avg_ms / 1e9, 1),
                            frac=round(work / avg_ms / 1e9 / tf_peak, 4),
                            executed_TFLOPs=round(3 * work / avg_ms / 1e9, 1), executed_frac=round(3 * work / avg_ms / 1e9 / tf_peak, 4))
+        if traffic.get(name):
+            row["traffic"] = traffic[name]
         kernel_rows.append(row)
     dom = next((r for r in kernel_rows if "bound" in r), None)   # the largest share of the hot path among the kernels with a roofline
     if dom is not None and dom["bound"] == "tensor":
         roofline = {"kernel": dom["kernel"], "bound": "tensor", "achieved": dom["achieved_TFLOPs"], "peak": tf_peak, "unit": "TFLOP/s",
-                    "frac": dom["frac"], "traffic": None, "avg_launch_us": dom["avg_us"], "launches_per_step": dom["launches_per_step"],
+                    "frac": dom["frac"], "traffic": dom.get("traffic"), "avg_launch_us": dom["avg_us"], "launches_per_step": dom["launches_per_step"],
                     "algorithmic_flop_per_launch": dom["algorithmic_flop_per_launch"],
                     "executed": {"TFLOP/s": dom["executed_TFLOPs"], "frac": dom["executed_frac"],
                                  "note": "3 bf16 MMA passes (hi*hi, hi*mid, mid*hi) per algorithmic fp32 product"},
                     "peak_source": peak_src + " bf16_tflops (burst)"}
     elif dom is not None:
         roofline = {"kernel": dom["kernel"], "bound": "hbm", "achieved": dom["achieved_GBps"], "peak": hbm_peak, "unit": "GB/s",
-                    "frac": dom["frac"], "traffic": None, "avg_launch_us": dom["avg_us"], "launches_per_step": dom["launches_per_step"],
+                    "frac": dom["frac"], "traffic": dom.get("traffic"), "avg_launch_us": dom["avg_us"], "launches_per_step": dom["launches_per_step"],
                     "algorithmic_bytes_per_launch": dom["algorithmic_bytes_per_launch"], "peak_source": peak_src + " hbm_gbs"}
     else:
         roofline = None
+    if roofline is not None and roofline["traffic"] is not None:
+        roofline["traffic_unit"] = "B per launch (dram__bytes_read.sum + dram__bytes_write.sum)"
+        roofline["traffic_source"] = traffic_src
 
     line = {"metric": METRIC, "value": P * world * 1000.0 / ms_value, "unit": "pairs/s", "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": ms_value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",

@@ -58,6 +58,12 @@ MP_API size_t mp_profile_end(char *buf, size_t cap);
 MP_API int mp_detector_head_f32(const float *logits, int B, int Hc, int Wc,
                                 const uint8_t *valid_mask, float *prob, mp_stream_t stream);
 
+/* SuperPointMagicLeap.generate_heatmap, multipoint/models/SuperPointMagicLeap.py:68-85:
+ * the same index map with the MagicLeap arithmetic, dense = exp(semi) / (sum_c exp(semi) + 1e-5), no
+ * max subtraction, dustbin dropped.  semi (B,65,Hc,Wc); prob (B,1,8Hc,8Wc).  Replaces a per-sample
+ * device->numpy->device round trip. */
+MP_API int mp_heatmap_magicleap_f32(const float *semi, int B, int Hc, int Wc, float *prob, mp_stream_t stream);
+
 /* utils.depth_to_space(x, block) / PixelShuffle, multipoint/utils/utils.py:64-69:
  * x (B, C*block^2, Hc, Wc) -> out (B, C, Hc*block, Wc*block). */
 MP_API int mp_depth_to_space_f32(const float *x, int B, int C, int Hc, int Wc, int block,

@@ -22,6 +22,7 @@ SIGNATURES = {
     "mp_profile_begin": (_i, []),
     "mp_profile_end": (_sz, [_c.c_char_p, _sz]),
     "mp_detector_head_f32": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
+    "mp_heatmap_magicleap_f32": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "mp_depth_to_space_f32": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "mp_normalize_descriptors_f32": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
     "mp_box_nms_workspace_bytes": (_sz, [_i, _i, _i]),

@@ -14,6 +14,9 @@ namespace mp {
 
 constexpr int DH_WARPS = 8;
 
+// ML = SuperPointMagicLeap.generate_heatmap (multipoint/models/SuperPointMagicLeap.py:68-85): the same
+// index map with exp(x) / (sum exp(x) + 1e-5) and no max subtraction (overflows like the reference).
+template <bool ML>
 __global__ void __launch_bounds__(DH_WARPS * 32, 3)
 detector_head_kernel(const float *__restrict__ logits, const uint8_t *__restrict__ mask,
                      float *__restrict__ prob, long long total_cells, int cells, int Wc) {
@@ -36,9 +39,12 @@ detector_head_kernel(const float *__restrict__ logits, const uint8_t *__restrict
 #pragma unroll
         for (int c = 0; c < 65; ++c) x[c] = 0.f;
     }
-    float m = x[0];
+    float m = 0.f;
+    if (!ML) {
+        m = x[0];
 #pragma unroll
-    for (int c = 1; c < 65; ++c) m = fmaxf(m, x[c]);
+        for (int c = 1; c < 65; ++c) m = fmaxf(m, x[c]);
+    }
     // exp(d) = 2^(d*log2(e)) with log2(e) split hi/lo so the argument keeps ~2^-30 relative
     // accuracy, then ex2.approx (2^-22.5): ~3e-7 relative overall, 4 instructions instead of ~10.
     // One reciprocal replaces 64 IEEE divisions (<= 1 ulp each).  Both sit well inside the 1e-5
@@ -54,7 +60,7 @@ detector_head_kernel(const float *__restrict__ logits, const uint8_t *__restrict
         x[c] = e;
         sum += e;  // channel order, like the oracle
     }
-    const float inv = __frcp_rn(sum);
+    const float inv = __frcp_rn(ML ? __fadd_rn(sum, 1e-5f) : sum);
 
     // the two float4 this lane stores per output row: float4 index f -> cell f/2, half f&1
     const int W = Wc * 8;
@@ -129,8 +135,23 @@ extern "C" int mp_detector_head_f32(const float *logits, int B, int Hc, int Wc,
     const long long total = (long long)B * Hc * Wc;
     const long long units = (total + 31) / 32;
     const unsigned grid = (unsigned)((units + mp::DH_WARPS - 1) / mp::DH_WARPS);
-    mp::detector_head_kernel<<<grid, mp::DH_WARPS * 32, 0, (cudaStream_t)stream>>>(
+    mp::detector_head_kernel<false><<<grid, mp::DH_WARPS * 32, 0, (cudaStream_t)stream>>>(
         logits, valid_mask, prob, total, Hc * Wc, Wc);
+    MP_LAUNCH_OK_S("detector_head_kernel", (cudaStream_t)stream);
+    return MP_OK;
+}
+
+extern "C" int mp_heatmap_magicleap_f32(const float *semi, int B, int Hc, int Wc, float *prob, mp_stream_t stream) {
+    mp::prof_entry((cudaStream_t)stream);
+    MP_CHECK_ARG(semi && prob, "mp_heatmap_magicleap_f32: null pointer");
+    MP_CHECK_ARG(B >= 0 && Hc > 0 && Wc > 0, "mp_heatmap_magicleap_f32: bad shape B=%d Hc=%d Wc=%d", B, Hc, Wc);
+    MP_CHECK_ARG(((uintptr_t)prob & 15) == 0, "mp_heatmap_magicleap_f32: prob must be 16-byte aligned");
+    if (B == 0) return MP_OK;
+    const long long total = (long long)B * Hc * Wc;
+    const long long units = (total + 31) / 32;
+    const unsigned grid = (unsigned)((units + mp::DH_WARPS - 1) / mp::DH_WARPS);
+    mp::detector_head_kernel<true><<<grid, mp::DH_WARPS * 32, 0, (cudaStream_t)stream>>>(
+        semi, nullptr, prob, total, Hc * Wc, Wc);
     MP_LAUNCH_OK_S("detector_head_kernel", (cudaStream_t)stream);
     return MP_OK;
 }

@@ -160,3 +160,39 @@ class MultiPoint(nn.Module):
         logits = self.detector_head_convolutions(x).to(torch.float)
         raw = self.descriptor_head_convolutions(x).to(torch.float) if self.config['descriptor_head'] else None
         return logits, raw
+
+
+class SuperPointMagicLeap(nn.Module):
+    """Mirror of multipoint/models/SuperPointMagicLeap.py:5-66: the pretrained
+    MagicLeap SuperPoint layout (same attribute names, so its state dict loads) with the heatmap
+    built on the device by ops.heatmap_magicleap instead of the reference's per-sample
+    tensor -> numpy -> tensor loop (generate_heatmap, :68-85)."""
+
+    def __init__(self, config=None):
+        super().__init__()
+        self.relu = nn.ReLU(inplace=True)
+        self.pool = nn.MaxPool2d(kernel_size=2, stride=2)
+        # creation order = the reference's, so a seeded random init draws the same weights
+        layers = [('1a', 1, 64, 3), ('1b', 64, 64, 3), ('2a', 64, 64, 3), ('2b', 64, 64, 3), ('3a', 64, 128, 3),
+                  ('3b', 128, 128, 3), ('4a', 128, 128, 3), ('4b', 128, 128, 3), ('Pa', 128, 256, 3), ('Pb', 256, 65, 1),
+                  ('Da', 128, 256, 3), ('Db', 256, 256, 1)]
+        for tag, cin, cout, k in layers:
+            setattr(self, 'conv' + tag, nn.Conv2d(cin, cout, kernel_size=k, stride=1, padding=k // 2))
+
+    def forward(self, data):
+        x = data['image']
+        for stage in ('1', '2', '3', '4'):
+            x = self.relu(getattr(self, 'conv%sa' % stage)(x))
+            x = self.relu(getattr(self, 'conv%sb' % stage)(x))
+            if stage != '4':
+                x = self.pool(x)
+        semi = self.convPb(self.relu(self.convPa(x)))
+        desc = self.convDb(self.relu(self.convDa(x)))
+        desc = desc.div(torch.unsqueeze(torch.norm(desc, p=2, dim=1), 1))  # no eps clamp, like :59-60
+        return {'logits': semi, 'desc': desc, 'prob': self.generate_heatmap(semi, data['image'].shape)}
+
+    def generate_heatmap(self, semi, shape):
+        prob = ops.heatmap_magicleap(semi)
+        if tuple(prob.shape) != tuple(shape):
+            raise ValueError("image shape %s does not match 8x the logits grid %s" % (tuple(shape), tuple(prob.shape)))
+        return prob

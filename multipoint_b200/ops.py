@@ -56,6 +56,19 @@ def detector_head(logits, valid_mask=None):
     return prob
 
 
+def heatmap_magicleap(semi):
+    """SuperPointMagicLeap.generate_heatmap: (B,65,Hc,Wc) -> (B,1,8Hc,8Wc), exp(x)/(sum exp + 1e-5), no dustbin."""
+    semi = _cuda(semi, torch.float32, "semi")
+    if semi.dim() != 4 or semi.shape[1] != 65:
+        raise ValueError("semi must be (B,65,Hc,Wc), got %s" % (tuple(semi.shape),))
+    B, _, Hc, Wc = semi.shape
+    prob = torch.empty((B, 1, Hc * 8, Wc * 8), dtype=torch.float32, device=semi.device)
+    with torch.cuda.device(semi.device):
+        _lib.check(_lib.load().mp_heatmap_magicleap_f32(_ptr(semi), B, Hc, Wc, _ptr(prob), _stream(semi)),
+                   "mp_heatmap_magicleap_f32")
+    return prob
+
+
 def depth_to_space(x, block_size):
     x = _cuda(x, torch.float32, "x")
     N, C, H, W = x.shape

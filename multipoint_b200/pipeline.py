@@ -17,31 +17,18 @@ class KeypointPipeline:
             raise ValueError("KeypointPipeline needs topk > 0 (fixed-capacity keypoint buffers)")
         self.net, self.nms, self.thr, self.topk, self.iou = net, nms, detection_threshold, int(topk), iou
         self.metric, self.cross_check, self.match_threshold, self.algo = metric, cross_check, match_threshold, algo
-        self._side = {}  # one side stream per device
-
-    def _side_stream(self, device):
-        key = (device.type, device.index)
-        if key not in self._side:
-            self._side[key] = torch.cuda.Stream(device=device)
-        return self._side[key]
 
     @torch.no_grad()
     def extract_from_backbone(self, logits, raw_desc, H, W, valid_mask=None):
         """Hot path proper: backbone outputs -> keypoints + descriptors (no host sync).
-        The descriptor normalise (HBM-bound) runs on a side stream next to the detector head + NMS
-        chain (instruction-bound), which does not depend on it; the two join before the sampling."""
-        cur = torch.cuda.current_stream(raw_desc.device)
-        side = self._side_stream(raw_desc.device)
-        side.wait_stream(cur)
-        with torch.cuda.stream(side):
-            _, desc_nhwc = ops.normalize_descriptors(raw_desc, nchw=False, nhwc=True)
+        One stream: running the HBM-bound descriptor normalise on a second stream next to the
+        (instruction-bound) NMS kernel was measured at 2.02-2.15 ms per step against 1.90 ms in
+        sequence -- the NMS loses more from sharing its SMs than the overlap wins."""
+        _, desc_nhwc = ops.normalize_descriptors(raw_desc, nchw=False, nhwc=True)
         prob = ops.detector_head(logits, valid_mask)
         B = prob.shape[0]
         dense, kp, scores, counts = ops.box_nms(prob.reshape(B, H, W), self.nms, self.thr, iou=self.iou,
                                                 keep_top_k=self.topk, want_keypoints=True, kp_cap=self.topk)
-        cur.wait_stream(side)
-        desc_nhwc.record_stream(cur)
-        raw_desc.record_stream(side)
         desc = ops.sample_descriptors(kp, desc_nhwc, H, W, counts=counts, channels_last=True)
         return {'prob': prob, 'prob_nms': dense.reshape(B, 1, H, W), 'keypoints': kp, 'scores': scores,
                 'counts': counts, 'desc': desc}

@@ -79,6 +79,23 @@ def gen_heads():
          full_sum=np.array(pf.astype(np.float64).sum()))
 
 
+# ---------------------------------------------------------------- MagicLeap heatmap
+def gen_magicleap():
+    semi = syn.logits(21, 2, 8, 10, sigma=3.0, bias=6.0)
+    semi[0, 5, 0, 0] = 40.0   # no max subtraction in the reference: exp(40) must stay finite in fp32
+    semi[1, :, 3, 3] = -30.0  # nearly empty cell: the +1e-5 in the denominator dominates
+    net = models.SuperPointMagicLeap()
+    prob = net.generate_heatmap(torch.from_numpy(semi), (2, 1, 64, 80))
+    # whole forward on a seeded random-init net: semi/desc/prob of the reference model
+    torch.manual_seed(7)
+    net = models.SuperPointMagicLeap().eval()
+    img = syn.images(22, 1, 64, 80)
+    with torch.no_grad():
+        o = net({'image': torch.from_numpy(img)})
+    save("magicleap", semi=semi, prob=prob.numpy(), model_image=img, model_seed=np.array(7),
+         model_logits=o['logits'].numpy(), model_desc=o['desc'].numpy(), model_prob=o['prob'].numpy())
+
+
 # ---------------------------------------------------------------- row 4: box_nms
 def gen_nms():
     out = {}

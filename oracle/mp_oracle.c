@@ -64,6 +64,32 @@ MPO_API void mpo_detector_head(const float *logits, int B, int Hc, int Wc, float
 }
 
 /* ------------------------------------------------------------------------ */
+/* SuperPointMagicLeap.generate_heatmap,                    */
+/* multipoint/models/SuperPointMagicLeap.py:68-85.  dense = exp(semi) (:72),  */
+/* dense / (sum over the 65 channels + 1e-5) (:73), dustbin dropped (:75),    */
+/* cells unfolded 8x8 (:79-82) = the PixelShuffle(8) index map of row 1.      */
+/* No max subtraction: large logits overflow exactly like the reference.      */
+/* ------------------------------------------------------------------------ */
+MPO_API void mpo_heatmap_magicleap(const float *semi, int B, int Hc, int Wc, float *prob)
+{
+    const int cells = Hc * Wc, W = 8 * Wc;
+    for (int b = 0; b < B; ++b)
+        for (int h = 0; h < Hc; ++h)
+            for (int w = 0; w < Wc; ++w) {
+                const float *x = semi + (size_t)b * 65 * cells + (size_t)h * Wc + w;
+                float e[65], sum = 0.f;
+                for (int c = 0; c < 65; ++c) {
+                    e[c] = expf(x[(size_t)c * cells]);
+                    sum += e[c];
+                }
+                const float den = sum + 1e-5f;
+                float *o = prob + (size_t)b * 64 * cells;
+                for (int c = 0; c < 64; ++c)
+                    o[(size_t)(8 * h + (c >> 3)) * W + 8 * w + (c & 7)] = e[c] / den;
+            }
+}
+
+/* ------------------------------------------------------------------------ */
 /* Row 2: MultiPoint.descriptor_head tail, MultiPoint.py:160-166             */
 /* F.normalize(x, p=2, dim=1): x / max(||x||_2, 1e-12) per cell.             */
 /* x: (B,D,HW) fp32 (NCHW with the two spatial dims flattened).              */

@@ -60,6 +60,16 @@ def detector_head(logits):
     return out
 
 
+# --- SuperPointMagicLeap.generate_heatmap (SuperPointMagicLeap.py:68-85) ---
+def heatmap_magicleap(semi):
+    semi = _f32(semi)
+    B, C, Hc, Wc = semi.shape
+    assert C == 65
+    out = np.empty((B, 1, Hc * 8, Wc * 8), np.float32)
+    lib().mpo_heatmap_magicleap(_p(semi, _f32p), B, Hc, Wc, _p(out, _f32p))
+    return out
+
+
 # --- row 2: MultiPoint.descriptor_head tail (MultiPoint.py:160-166) ---
 def normalize_descriptors(x):
     x = _f32(x)

@@ -48,6 +48,26 @@ def test_detector_head_golden_and_oracle(ops, oracle):
     torch.testing.assert_close(cell, 1.0 - dust, rtol=1e-4, atol=1e-6)
 
 
+def test_heatmap_magicleap(ops, oracle):
+    """SuperPointMagicLeap.generate_heatmap on the device, vs the reference fixture and the oracle."""
+    g = load_golden("magicleap")
+    got = ops.heatmap_magicleap(cu(g["semi"])).cpu().numpy()
+    np.testing.assert_allclose(got, g["prob"], rtol=RTOL, atol=1e-12)
+    np.testing.assert_allclose(got, oracle.heatmap_magicleap(g["semi"]), rtol=RTOL, atol=1e-12)
+    lg = syn.logits(106, 3, 33, 17, sigma=3.0, bias=6.0)
+    np.testing.assert_allclose(ops.heatmap_magicleap(cu(lg)).cpu().numpy(), oracle.heatmap_magicleap(lg), rtol=RTOL, atol=1e-12)
+    # the mirrored model: same seeded weights as the reference -> same logits / descriptors / heatmap
+    from multipoint_b200.models import SuperPointMagicLeap
+    torch.manual_seed(int(g["model_seed"]))
+    net = SuperPointMagicLeap().eval().cuda()
+    with torch.no_grad():
+        o = net({'image': cu(g["model_image"])})
+    np.testing.assert_allclose(o['logits'].cpu().numpy(), g["model_logits"], rtol=1e-4, atol=1e-5)  # cuDNN vs CPU conv
+    np.testing.assert_allclose(o['desc'].cpu().numpy(), g["model_desc"], rtol=1e-3, atol=1e-5)
+    np.testing.assert_allclose(o['prob'].cpu().numpy(), oracle.heatmap_magicleap(o['logits'].cpu().numpy()), rtol=RTOL, atol=1e-12)
+    np.testing.assert_allclose(o['prob'].cpu().numpy(), g["model_prob"], rtol=1e-3, atol=1e-6)
+
+
 def test_detector_head_valid_mask(ops, oracle):
     lg = syn.logits(105, 2, 16, 20)
     mask = (np.random.default_rng(5).random((2, 1, 128, 160)) > 0.3)

@@ -41,6 +41,14 @@ def test_detector_head_matches_reference(oracle):
     np.testing.assert_array_equal(d2s, g["depth_to_space"])
 
 
+def test_heatmap_magicleap_matches_reference(oracle):
+    """SuperPointMagicLeap.generate_heatmap (numpy exp, +1e-5, no max subtraction)."""
+    g = load_golden("magicleap")
+    np.testing.assert_allclose(oracle.heatmap_magicleap(g["semi"]), g["prob"], rtol=RTOL, atol=1e-12)
+    np.testing.assert_allclose(oracle.heatmap_magicleap(g["model_logits"]), g["model_prob"], rtol=RTOL, atol=1e-12)
+    assert np.isfinite(g["prob"]).all() and g["prob"][0, 0, 0, 5] > 0.99  # the exp(40) cell
+
+
 def test_normalize_descriptors_matches_reference(oracle):
     g = load_golden("heads")
     np.testing.assert_allclose(oracle.normalize_descriptors(g["desc_in"]), g["desc"], rtol=RTOL, atol=1e-9)
