@@ -189,6 +189,17 @@ MP_API int mp_ha_aggregate_f32(const float *prob0, const float *probw_a, const f
                                int flags, float *prob_acc, float *count_acc, float *out,
                                mp_stream_t stream);
 
+/* ---- compute_valid_mask, multipoint/utils/homographies.py:375-402 ----
+ * n masks in one launch: mask[i] = erode(cv2.warpPerspective(ones(H,W), Hm[i], INTER_NEAREST)).
+ * Minv (n,3,3) float64 row-major, device: the INVERTED homographies exactly as cv2.warpPerspective
+ * computes them (cv::invert closed form; multipoint_b200.utils.invert_homographies restates it).
+ * erosion_radius r: (2r+1)^2 box minimum, r <= 31; outside-image pixels are ignored (cv2.erode's
+ * default border) unless mask_border != 0, which is the reference's one-pixel zero frame.
+ * mask (n,H,W) uint8 0/1 (4-byte aligned when W % 4 == 0).  Bit-exact with OpenCV's double
+ * arithmetic (block origin, reciprocal, round-half-even). */
+MP_API int mp_valid_mask_u8(const double *Minv, int n, int H, int W, int erosion_radius, int mask_border,
+                            uint8_t *mask, mp_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -35,6 +35,7 @@ SIGNATURES = {
     "mp_match_f32": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _d, _d, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "mp_match_threshold_f32": (_i, [_vp, _i, _vp, _i, _i, _d, _vp, _vp, _vp, _i64, _c.POINTER(_i64), _vp, _sz, _vp]),
     "mp_warp_f32": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _vp]),
+    "mp_valid_mask_u8": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "mp_ha_aggregate_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
 }
 

@@ -276,6 +276,23 @@ def warp(src, A, mode='bilinear', padding='zeros', tables=None):
     return out
 
 
+def valid_masks(Minv, H, W, erosion_radius=0, mask_border=False, device=None):
+    """(n,3,3) float64 INVERTED homographies (as cv2.warpPerspective inverts them) -> (n,H,W) uint8 valid masks."""
+    if not torch.is_tensor(Minv):
+        Minv = torch.from_numpy(np.ascontiguousarray(np.asarray(Minv, np.float64).reshape(-1, 3, 3)))
+    if not Minv.is_cuda:
+        if device is None:
+            raise RuntimeError("valid_masks needs a CUDA tensor or an explicit device")
+        Minv = Minv.to(device)
+    Minv = _cuda(Minv, torch.float64, "Minv").reshape(-1, 3, 3).contiguous()
+    n = Minv.shape[0]
+    out = torch.empty((n, int(H), int(W)), dtype=torch.uint8, device=Minv.device)
+    with torch.cuda.device(Minv.device):
+        _lib.check(_lib.load().mp_valid_mask_u8(_ptr(Minv), n, int(H), int(W), int(erosion_radius), int(bool(mask_border)),
+                                                _ptr(out), _stream(Minv)), "mp_valid_mask_u8")
+    return out
+
+
 def ha_aggregate(prob0, probw_a, probw_b, masks, Ainv, aggregation, min_count, init=True, finish=True,
                  prob_acc=None, count_acc=None, tables=None):
     """Unwarp + accumulate + finish of homographic adaptation; see mp_ha_aggregate_f32."""

@@ -60,22 +60,25 @@ def reduce_counters(counters, device=None):
 
 
 def broadcast_homographies(sample_fn, device="cpu"):
-    """Rank 0 draws (homographies (n,3,3) f64, masks (n,H,W) u8) with ``sample_fn`` -- keeping the
-    reference's numpy RNG stream on one process -- and every rank receives them."""
+    """Rank 0 draws (homographies (n,3,3) f64, masks (n,H,W) u8 or None) with ``sample_fn`` -- keeping
+    the reference's numpy RNG stream on one process -- and every rank receives them.  With masks=None
+    only the 72 B matrices travel; each rank rasters the masks of its own share on its GPU."""
     rank = dist.get_rank() if dist.is_initialized() else 0
     world = dist.get_world_size() if dist.is_initialized() else 1
     if world == 1:
         return sample_fn()
     if rank == 0:
         Hs, masks = sample_fn()
-        shape = torch.tensor(list(masks.shape), dtype=torch.int64, device=device)
+        shape = torch.tensor([Hs.shape[0]] + (list(masks.shape[1:]) if masks is not None else [0, 0]), dtype=torch.int64, device=device)
     else:
         shape = torch.zeros(3, dtype=torch.int64, device=device)
     dist.broadcast(shape, 0)
     n, H, W = (int(v) for v in shape.tolist())
     h_t = torch.from_numpy(Hs).to(device) if rank == 0 else torch.zeros((n, 3, 3), dtype=torch.float64, device=device)
-    m_t = torch.from_numpy(masks).to(device) if rank == 0 else torch.zeros((n, H, W), dtype=torch.uint8, device=device)
     dist.broadcast(h_t, 0)
+    if H == 0:
+        return h_t.cpu().numpy(), None
+    m_t = torch.from_numpy(np.asarray(masks)).to(device) if rank == 0 else torch.zeros((n, H, W), dtype=torch.uint8, device=device)
     dist.broadcast(m_t, 0)
     return h_t.cpu().numpy(), m_t.cpu().numpy()
 

@@ -61,7 +61,7 @@ def main(argv=None):
             if world > 1 and args.shard_homographies:
                 cfg = utils._check_ha_config(ha_cfg)
                 hw = tuple(batch['optical']['image'].shape[2:])
-                Hs, masks = parallel.broadcast_homographies(lambda: utils.sample_adaptation_homographies(hw, cfg), device=device)
+                Hs, masks = parallel.broadcast_homographies(lambda: utils.sample_adaptation_homographies(hw, cfg, with_masks=False), device=device)
                 shard = parallel.adaptation_shard()
             if args.single_image:
                 prob_ha = utils.homographic_adaptation(batch['optical'], net, ha_cfg, homographies=Hs, masks=masks, shard=shard)

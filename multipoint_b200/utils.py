@@ -467,16 +467,43 @@ def _check_ha_config(user_config):
     return config
 
 
-def sample_adaptation_homographies(image_hw, config, rank=0, world_size=1):
-    """Pre-sample the num-1 homographies and valid masks in the reference's RNG order
+def invert_homographies(Hs):
+    """cv::invert for 3x3 doubles (cofactors times 1/det, zeros when det == 0), vectorised over a
+    batch in the same operation order, so the result is bit-identical to what cv2.warpPerspective
+    inverts internally (checked against cv2.invert in tests/test_host.py)."""
+    S = np.asarray(Hs, np.float64).reshape(-1, 9)
+    a, b, c, d, e, f, g, h, i = (S[:, k] for k in range(9))
+    det = a * (e * i - f * h) - b * (d * i - f * g) + c * (d * h - e * g)
+    with np.errstate(divide='ignore', invalid='ignore'):
+        r = 1.0 / det
+        T = np.stack([(e * i - f * h) * r, (c * h - b * i) * r, (b * f - c * e) * r,
+                      (f * g - d * i) * r, (a * i - c * g) * r, (c * d - a * f) * r,
+                      (d * h - e * g) * r, (b * g - a * h) * r, (a * e - b * d) * r], axis=1)
+    T[det == 0.0] = 0.0
+    return T.reshape(-1, 3, 3)
+
+
+def compute_valid_masks(image_shape, homographies, erosion_radius=0, mask_border=False, device=None):
+    """Batched, device-side compute_valid_mask: (n,3,3) homographies ->
+    (n,H,W) uint8 CUDA tensor, bit-identical to the per-homography cv2 path above, one launch."""
+    dev = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+    Minv = torch.from_numpy(invert_homographies(homographies)).to(dev)
+    return ops.valid_masks(Minv, image_shape[0], image_shape[1], erosion_radius, mask_border)
+
+
+def sample_adaptation_homographies(image_hw, config, with_masks=True):
+    """Pre-sample the num-1 homographies (and valid masks) in the reference's RNG order
     (homographies.py:77-80 / :162-165: sample_homography then compute_valid_mask per iteration;
-    the mask consumes no random numbers).  Returns (H (n,3,3) float64, masks (n,H,W) uint8)."""
+    the mask consumes no random numbers).  Returns (H (n,3,3) float64, masks (n,H,W) uint8) with
+    the masks rastered by cv2 on the host, or (H, None) with ``with_masks=False``: the adaptation
+    then builds them on the device (compute_valid_masks), which is what the product path does."""
     n = config['num'] - 1
     Hs = np.zeros((n, 3, 3), np.float64)
-    masks = np.zeros((n,) + tuple(image_hw), np.uint8)
+    masks = np.zeros((n,) + tuple(image_hw), np.uint8) if with_masks else None
     for i in range(n):
         Hs[i] = sample_homography(np.array(image_hw), **config['homographies'])
-        masks[i] = compute_valid_mask(tuple(image_hw), Hs[i], config['erosion_radius'], config['mask_border']) != 0
+        if with_masks:
+            masks[i] = compute_valid_mask(tuple(image_hw), Hs[i], config['erosion_radius'], config['mask_border']) != 0
     return Hs, masks
 
 
@@ -527,7 +554,7 @@ def _adaptation_core(images, is_optical, net, config, second, homographies, mask
         prob0 = prob0.contiguous()
 
     if homographies is None:
-        homographies, masks = sample_adaptation_homographies((H, W), config)
+        homographies, masks = sample_adaptation_homographies((H, W), config, with_masks=False)
     mine = list(range(rank, n_total, world))
     tables = ops.linspace_tables(H, W, dev)
     n = len(mine)
@@ -536,7 +563,13 @@ def _adaptation_core(images, is_optical, net, config, second, homographies, mask
         Hm = torch.from_numpy(np.asarray(homographies, np.float64)[mine].astype(np.float32))
         A_warp = normalized_warp_matrix(Hm, (H, W), (H, W)).to(dev)
         A_unwarp = normalized_warp_matrix(torch.inverse(Hm), (H, W), (H, W)).to(dev)  # torch.inverse(homography) :112,:180
-        mk = torch.from_numpy(np.ascontiguousarray(np.asarray(masks)[mine])).to(dev, torch.uint8)
+        if masks is None:   # built on the device, this rank's share only
+            mk = compute_valid_masks((H, W), np.asarray(homographies, np.float64)[mine], config['erosion_radius'],
+                                     config['mask_border'], dev)
+        elif torch.is_tensor(masks):
+            mk = masks.to(dev, torch.uint8)[mine].contiguous()
+        else:
+            mk = torch.from_numpy(np.ascontiguousarray(np.asarray(masks)[mine])).to(dev, torch.uint8)
         warped = ops.warp(images[:, 0], A_warp, 'bilinear', 'reflection', tables).reshape(n * B, 1, H, W)  # :86 / :171
         pw_a = run(warped, is_optical).reshape(n, B, H, W).contiguous()
         pw_b = None

@@ -594,3 +594,167 @@ MPO_API void mpo_ha_aggregate(const float *prob0, const float *probw_a, const fl
                 if (count_out) count_out[b * HW + (size_t)y * W + x] = count;
             }
 }
+
+/* ------------------------------------------------------------------------ */
+/* compute_valid_mask,                          */
+/* multipoint/utils/homographies.py:375-402.                                  */
+/*   mask = cv2.warpPerspective(ones(H,W) float64, Hm, (W,H), INTER_NEAREST)  */
+/*   optional 1-px zero frame, cv2.erode by a (2r+1)^2 box, frame cropped.    */
+/* The arithmetic is OpenCV's (third party, opencv-python pinned 4.2.0.34 in  */
+/* requirements.txt:1, 4.13.0 installed), restated from its published         */
+/* algorithm and pinned against cv2 itself by oracle/gen_golden.py:           */
+/*  - warpPerspective inverts the matrix (cv::invert, closed form for 3x3),   */
+/*  - walks the destination in blocks of bw0 columns; for a pixel (x,y) in    */
+/*    the block starting at xb: X0 = M0*xb + M1*y + M2 (same for Y0, W0),     */
+/*    W = W0 + M6*x1, W = W ? 1/W : 0, fX = (X0 + M0*x1)*W clamped to int     */
+/*    range, X = round-half-even(fX) -- all in double,                        */
+/*  - nearest remap with constant border 0: ones inside the source, 0 outside */
+/*  - erode: minimum over the window, pixels outside the image ignored        */
+/*    (border value +max), so only the explicit zero frame erodes the edge.   */
+/* Minv: the inverted matrix as cv2.invert returns it (row-major, 9 doubles). */
+/* ------------------------------------------------------------------------ */
+MPO_API void mpo_invert3x3(const double *S, double *T)
+{
+    /* cv::invert, 3x3 closed form: cofactors times 1/det, 0 matrix if det == 0 */
+    const double d0 = S[0] * (S[4] * S[8] - S[5] * S[7]) - S[1] * (S[3] * S[8] - S[5] * S[6]) +
+                      S[2] * (S[3] * S[7] - S[4] * S[6]);
+    if (d0 == 0.) {
+        for (int i = 0; i < 9; ++i) T[i] = 0.;
+        return;
+    }
+    const double d = 1. / d0;
+    T[0] = (S[4] * S[8] - S[5] * S[7]) * d;
+    T[1] = (S[2] * S[7] - S[1] * S[8]) * d;
+    T[2] = (S[1] * S[5] - S[2] * S[4]) * d;
+    T[3] = (S[5] * S[6] - S[3] * S[8]) * d;
+    T[4] = (S[0] * S[8] - S[2] * S[6]) * d;
+    T[5] = (S[2] * S[3] - S[0] * S[5]) * d;
+    T[6] = (S[3] * S[7] - S[4] * S[6]) * d;
+    T[7] = (S[1] * S[6] - S[0] * S[7]) * d;
+    T[8] = (S[0] * S[4] - S[1] * S[3]) * d;
+}
+
+static int mpo_round_even_sat(double v)
+{
+    if (v < -2147483648.0) v = -2147483648.0;
+    if (v > 2147483647.0) v = 2147483647.0;
+    return (int)nearbyint(v); /* default rounding mode: half to even, like cvRound */
+}
+
+MPO_API void mpo_valid_mask(const double *Minv, int H, int W, int erosion_radius, int mask_border, uint8_t *mask)
+{
+    int bh0 = H < 16 ? H : 16;
+    int bw0 = 1024 / bh0;
+    if (bw0 > W) bw0 = W;
+    uint8_t *raw = (uint8_t *)malloc((size_t)H * W);
+    for (int y = 0; y < H; ++y)
+        for (int x = 0; x < W; ++x) {
+            const int xb = (x / bw0) * bw0, x1 = x - xb;
+            const double X0 = Minv[0] * xb + Minv[1] * y + Minv[2];
+            const double Y0 = Minv[3] * xb + Minv[4] * y + Minv[5];
+            const double W0 = Minv[6] * xb + Minv[7] * y + Minv[8];
+            double w = W0 + Minv[6] * x1;
+            w = w ? 1. / w : 0;
+            const int sx = mpo_round_even_sat((X0 + Minv[0] * x1) * w);
+            const int sy = mpo_round_even_sat((Y0 + Minv[3] * x1) * w);
+            raw[(size_t)y * W + x] = (sx >= 0 && sx < W && sy >= 0 && sy < H) ? 1 : 0;
+        }
+    const int r = erosion_radius;
+    if (r <= 0) {
+        memcpy(mask, raw, (size_t)H * W);
+    } else {
+        for (int y = 0; y < H; ++y)
+            for (int x = 0; x < W; ++x) {
+                uint8_t v = 1;
+                for (int dy = -r; dy <= r && v; ++dy)
+                    for (int dx = -r; dx <= r; ++dx) {
+                        const int yy = y + dy, xx = x + dx;
+                        if (yy < 0 || yy >= H || xx < 0 || xx >= W) {
+                            if (mask_border) { v = 0; break; }
+                            continue;
+                        }
+                        if (!raw[(size_t)yy * W + xx]) { v = 0; break; }
+                    }
+                mask[(size_t)y * W + x] = v;
+            }
+    }
+    free(raw);
+}
+
+/* ------------------------------------------------------------------------ */
+/* the point geometry inside compute_repeatability_multi-   */
+/* spectral (multipoint/utils/evaluation.py:148-199) and                      */
+/* compute_descriptor_metrics (:253-358).                                     */
+/* ------------------------------------------------------------------------ */
+
+/* warp_keypoints, multipoint/utils/homographies.py:331-346:                  */
+/*   cv2.perspectiveTransform([kp[:, ::-1]] as float64, Hm)[0, :, ::-1]       */
+/* OpenCV's arithmetic (third party, see the valid-mask note above), pinned   */
+/* against cv2 by oracle/gen_golden.py: w = x*m6 + y*m7 + m8; if |w| >        */
+/* FLT_EPSILON: w = 1/w, x' = (x*m0 + y*m1 + m2)*w, y' likewise; else 0.      */
+/* The installed build (4.13.0, AVX2 dispatch of matmul.simd.hpp) contracts   */
+/* x*a + y*b into fma(x, a, y*b) -- measured: that form is bit-identical on   */
+/* 15 000 random points, the uncontracted one differs in the last ulp on      */
+/* ~27 % of them.  OpenCV's result is therefore platform dependent at 1 ulp;  */
+/* this restates the FMA form.                                                */
+/* pts (N,2) int64 (y,x) -> out_f64 (N,2) double (y,x); when out_i64 != NULL  */
+/* also the reference's `.astype(int)` (C truncation toward zero).            */
+MPO_API void mpo_warp_keypoints(const int64_t *pts, int N, const double *m, double *out_f64, int64_t *out_i64)
+{
+    for (int i = 0; i < N; ++i) {
+        const double y = (double)pts[2 * i], x = (double)pts[2 * i + 1];
+        double w = fma(x, m[6], y * m[7]) + m[8];
+        double xo = 0., yo = 0.;
+        if (fabs(w) > 1.1920928955078125e-07) {
+            w = 1. / w;
+            xo = (fma(x, m[0], y * m[1]) + m[2]) * w;
+            yo = (fma(x, m[3], y * m[4]) + m[5]) * w;
+        }
+        if (out_f64) { out_f64[2 * i] = yo; out_f64[2 * i + 1] = xo; }
+        if (out_i64) { out_i64[2 * i] = (int64_t)yo; out_i64[2 * i + 1] = (int64_t)xo; }
+    }
+}
+
+/* evaluation.py:176-197 for one direction: queries = warped keypoints (already truncated to int),  */
+/* filter_points (homographies.py:358-372) keeps 0 <= y < H, 0 <= x < W; for each kept query the     */
+/* minimum over the targets of ||q - t||_2 (np.linalg.norm of an int64 difference = sqrt of an exact  */
+/* integer); min_d2[i] = that minimum squared (exact), -1 for filtered-out queries, INT64_MAX when    */
+/* there is no target.  The caller counts sqrt(min_d2) <= distance_thresh in double.                  */
+MPO_API void mpo_points_min_dist2(const int64_t *q, int Nq, const int64_t *t, int Nt, int H, int W, int64_t *min_d2)
+{
+    for (int i = 0; i < Nq; ++i) {
+        const int64_t qy = q[2 * i], qx = q[2 * i + 1];
+        if (qy < 0 || qx < 0 || qy >= H || qx >= W) { min_d2[i] = -1; continue; }
+        int64_t best = INT64_MAX;
+        for (int j = 0; j < Nt; ++j) {
+            const int64_t dy = qy - t[2 * j], dx = qx - t[2 * j + 1];
+            const int64_t d2 = dy * dy + dx * dx;
+            if (d2 < best) best = d2;
+        }
+        min_d2[i] = best;
+    }
+}
+
+/* evaluation.py:294-298,301-315: correct[i,j] = ||float32(warped[i] - kp[j])||_2 <= threshold_keypoints  */
+/* with warped in float64 (warp_keypoints(..., np.float)) and kp int64; the difference is taken in double, */
+/* rounded to fp32, the norm accumulated in fp32 (dy*dy + dx*dx, no FMA) -- torch.norm's exact reduction  */
+/* order for two elements is third-party and unpinned at 1-ulp boundaries.  row_any[i] = any_j correct     */
+/* (the rows counted by correct.sum(1).nonzero()); tp[k] = correct[mq[k], mt[k]] for the M given matches.   */
+MPO_API void mpo_points_correct(const double *qw, int Nq, const int64_t *t, int Nt, float thr, uint8_t *row_any,
+                                const int32_t *mq, const int32_t *mt, int M, uint8_t *tp)
+{
+    for (int i = 0; i < Nq; ++i) {
+        uint8_t any = 0;
+        for (int j = 0; j < Nt && !any; ++j) {
+            const float dy = (float)(qw[2 * i] - (double)t[2 * j]), dx = (float)(qw[2 * i + 1] - (double)t[2 * j + 1]);
+            const float d = sqrtf(dy * dy + dx * dx);
+            any = d <= thr;
+        }
+        row_any[i] = any;
+    }
+    for (int k = 0; k < M; ++k) {
+        const int i = mq[k], j = mt[k];
+        const float dy = (float)(qw[2 * i] - (double)t[2 * j]), dx = (float)(qw[2 * i + 1] - (double)t[2 * j + 1]);
+        tp[k] = sqrtf(dy * dy + dx * dx) <= thr;
+    }
+}

@@ -262,3 +262,57 @@ def homographic_adaptation(images, net_prob, homographies, masks, min_count=2, i
     out, _ = ha_aggregate(prob0, pw_a, pw_b, masks, Ainv,
                           aggregation if images_b is not None else 'none', min_count)
     return out
+
+
+# --- compute_valid_mask (homographies.py:375-402) ---
+def invert3x3(M):
+    M = np.ascontiguousarray(M, np.float64).reshape(9)
+    out = np.empty(9, np.float64)
+    dp = ctypes.POINTER(ctypes.c_double)
+    lib().mpo_invert3x3(M.ctypes.data_as(dp), out.ctypes.data_as(dp))
+    return out.reshape(3, 3)
+
+
+def valid_mask(image_shape, homography, erosion_radius=0, mask_border=False, inverse=None):
+    """-> (H,W) uint8; ``inverse`` overrides the restated cv::invert (pass cv2.invert's output to isolate the warp)."""
+    H, W = int(image_shape[0]), int(image_shape[1])
+    Minv = invert3x3(homography) if inverse is None else np.ascontiguousarray(inverse, np.float64)
+    out = np.empty((H, W), np.uint8)
+    lib().mpo_valid_mask(Minv.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), H, W, int(erosion_radius), int(bool(mask_border)),
+                         out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)))
+    return out
+
+
+# --- SURVEY 8f rank 1: point geometry of the evaluation loops (evaluation.py:148-199, 253-358) ---
+_i64p = ctypes.POINTER(ctypes.c_int64)
+
+
+def warp_keypoints(kp, homography, as_int=True):
+    """homographies.py:331-346 (cv2.perspectiveTransform on flipped float64 points); as_int -> .astype(int)."""
+    kp = np.ascontiguousarray(kp, np.int64).reshape(-1, 2)
+    m = np.ascontiguousarray(homography, np.float64).reshape(9)
+    f = np.empty(kp.shape, np.float64)
+    i = np.empty(kp.shape, np.int64)
+    lib().mpo_warp_keypoints(kp.ctypes.data_as(_i64p), len(kp), m.ctypes.data_as(_f64p), f.ctypes.data_as(_f64p), i.ctypes.data_as(_i64p))
+    return i if as_int else f
+
+
+def points_min_dist2(q, t, H, W):
+    q = np.ascontiguousarray(q, np.int64).reshape(-1, 2)
+    t = np.ascontiguousarray(t, np.int64).reshape(-1, 2)
+    out = np.empty(len(q), np.int64)
+    lib().mpo_points_min_dist2(q.ctypes.data_as(_i64p), len(q), t.ctypes.data_as(_i64p), len(t), int(H), int(W), out.ctypes.data_as(_i64p))
+    return out
+
+
+def points_correct(qw, t, thr, mq=None, mt=None):
+    qw = np.ascontiguousarray(qw, np.float64).reshape(-1, 2)
+    t = np.ascontiguousarray(t, np.int64).reshape(-1, 2)
+    mq = np.ascontiguousarray(mq if mq is not None else [], np.int32)
+    mt = np.ascontiguousarray(mt if mt is not None else [], np.int32)
+    row_any = np.empty(len(qw), np.uint8)
+    tp = np.empty(len(mq), np.uint8)
+    i32 = ctypes.POINTER(ctypes.c_int32)
+    lib().mpo_points_correct(qw.ctypes.data_as(_f64p), len(qw), t.ctypes.data_as(_i64p), len(t), ctypes.c_float(thr),
+                             row_any.ctypes.data_as(_u8p), mq.ctypes.data_as(i32), mt.ctypes.data_as(i32), len(mq), tp.ctypes.data_as(_u8p))
+    return row_any, tp

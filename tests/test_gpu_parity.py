@@ -470,6 +470,51 @@ def test_homographic_adaptation_vs_restatement_and_oracle(utils, ops, oracle):
         utils.homographic_adaptation_multispectral(data, net, dict(cfg, num=2, aggregation='max'))
 
 
+def test_valid_masks_device(utils, ops, oracle):
+    """batched device-side compute_valid_mask, bit-exact against the reference's masks
+    (fixture), the oracle, and the host cv2 path."""
+    g = load_golden("homographies")
+    for tag in ("default", "export", "noart", "small"):
+        shape = tuple(int(v) for v in g[tag + "_shape"])
+        erosion = int(g[tag + "_seed"][1])
+        want = np.unpackbits(g[tag + "_mask"], axis=-1)[..., :shape[1]]
+        got = utils.compute_valid_masks(shape, g[tag + "_H"], erosion, True).cpu().numpy()
+        np.testing.assert_array_equal(got, want)
+    Hm = g["small_H"][:1]
+    np.testing.assert_array_equal(utils.compute_valid_masks((64, 80), Hm, 0, False).cpu().numpy()[0],
+                                  np.unpackbits(g["small_mask_e0"], axis=-1)[..., :80])
+    np.testing.assert_array_equal(utils.compute_valid_masks((64, 80), Hm, 2, False).cpu().numpy()[0],
+                                  np.unpackbits(g["small_mask_e2nb"], axis=-1)[..., :80])
+    # ragged sizes (W not a multiple of 4 / 32, H not a multiple of the row tile), every erosion mode, vs the oracle
+    rng = np.random.default_rng(11)
+    for shape in [(37, 53), (12, 20), (70, 131), (100, 64)]:
+        Hs = []
+        for _ in range(7):
+            th = rng.uniform(-0.5, 0.5)
+            Hs.append(np.array([[np.cos(th) * rng.uniform(0.8, 1.2), -np.sin(th), rng.uniform(-8, 8)],
+                                [np.sin(th), np.cos(th) * rng.uniform(0.8, 1.2), rng.uniform(-8, 8)],
+                                [rng.uniform(-2e-3, 2e-3), rng.uniform(-2e-3, 2e-3), 1.0]]))
+        Hs.append(np.eye(3))
+        Hs = np.stack(Hs)
+        for r, border in [(0, False), (1, True), (4, False), (31, True)]:
+            got = utils.compute_valid_masks(shape, Hs, r, border).cpu().numpy()
+            for i, Hm in enumerate(Hs):
+                np.testing.assert_array_equal(got[i], oracle.valid_mask(shape, Hm, r, border), err_msg=str((shape, r, border, i)))
+                if r <= 4:
+                    np.testing.assert_array_equal(got[i], utils.compute_valid_mask(shape, Hm, r, border).astype(np.uint8))
+    assert utils.compute_valid_masks((16, 16), np.zeros((0, 3, 3))).shape == (0, 16, 16)
+    with pytest.raises(NotImplementedError):
+        utils.compute_valid_masks((64, 80), np.eye(3)[None], 40, True)
+    # bench size: 99 homographies of 512x640 in one launch == the host loop on a sample of them
+    np.random.seed(4)
+    cfg = utils._check_ha_config({})
+    Hs, _ = utils.sample_adaptation_homographies((512, 640), cfg, with_masks=False)
+    got = utils.compute_valid_masks((512, 640), Hs, cfg['erosion_radius'], cfg['mask_border'])
+    assert got.shape == (99, 512, 640)
+    for i in (0, 17, 98):
+        np.testing.assert_array_equal(got[i].cpu().numpy(), utils.compute_valid_mask((512, 640), Hs[i], 5, True).astype(np.uint8))
+
+
 def test_homographic_adaptation_host_sampling_matches_reference_stream(utils):
     """With np.random.seed(5) the product draws the same homographies and masks as the reference run
     that produced the fixture, so the end-to-end call (no injected samples) matches it too."""

@@ -106,6 +106,20 @@ def test_sample_homography_and_valid_mask_match_reference():
     np.testing.assert_array_equal(masks != 0, np.unpackbits(g["small_mask"], axis=-1)[..., :80] != 0)
 
 
+def test_invert_homographies_is_cv_invert():
+    """The batched closed-form inverse fed to mp_valid_mask_u8 is bit-identical to cv2.invert (what
+    cv2.warpPerspective applies internally), including the singular case."""
+    import cv2
+    from multipoint_b200 import utils
+    g = load_golden("homographies")
+    Hs = np.concatenate([g["default_H"], g["export_H"], g["small_H"], np.zeros((1, 3, 3)), np.eye(3)[None]])
+    got = utils.invert_homographies(Hs)
+    for Hm, inv in zip(Hs, got):
+        np.testing.assert_array_equal(inv, cv2.invert(Hm)[1])
+    Hs2, none = utils.sample_adaptation_homographies((64, 80), utils._check_ha_config(dict(num=4)), with_masks=False)
+    assert none is None and Hs2.shape == (3, 3, 3)
+
+
 def test_normalized_warp_matrix_matches_restatement():
     from multipoint_b200 import utils
     g = load_golden("adaptation")

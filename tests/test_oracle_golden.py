@@ -268,3 +268,37 @@ def test_reference_port_matches_reference_fixtures():
     g = load_golden("matching")
     m = rp.get_matches_bf_crosscheck(g["m51_a"], g["m51_b"])
     assert [x.queryIdx for x in m] == list(g["m51_bf_q"]) and [x.trainIdx for x in m] == list(g["m51_bf_t"])
+
+
+def test_valid_mask_matches_reference(oracle):
+    """the restated OpenCV raster (inverse, block origin, reciprocal, half-to-even) and erosion
+    against the masks the reference's compute_valid_mask produced (tests/golden/homographies.npz)."""
+    g = load_golden("homographies")
+    for tag in ("default", "export", "noart", "small"):
+        shape = tuple(int(v) for v in g[tag + "_shape"])
+        erosion = int(g[tag + "_seed"][1])
+        want = np.unpackbits(g[tag + "_mask"], axis=-1)[..., :shape[1]]
+        for i, Hm in enumerate(g[tag + "_H"]):
+            np.testing.assert_array_equal(oracle.valid_mask(shape, Hm, erosion, True), want[i])
+    Hm = g["small_H"][0]
+    np.testing.assert_array_equal(oracle.valid_mask((64, 80), Hm, 0, False), np.unpackbits(g["small_mask_e0"], axis=-1)[..., :80])
+    np.testing.assert_array_equal(oracle.valid_mask((64, 80), Hm, 2, False), np.unpackbits(g["small_mask_e2nb"], axis=-1)[..., :80])
+    # live against OpenCV (same process, no fixture): odd sizes, every erosion mode
+    import cv2
+    rng = np.random.default_rng(9)
+    for shape in [(37, 53), (12, 20), (70, 131)]:
+        for _ in range(20):
+            th = rng.uniform(-0.5, 0.5)
+            Hm = np.array([[np.cos(th) * rng.uniform(0.8, 1.2), -np.sin(th), rng.uniform(-8, 8)],
+                           [np.sin(th), np.cos(th) * rng.uniform(0.8, 1.2), rng.uniform(-8, 8)],
+                           [rng.uniform(-2e-3, 2e-3), rng.uniform(-2e-3, 2e-3), 1.0]])
+            np.testing.assert_array_equal(oracle.invert3x3(Hm), cv2.invert(Hm)[1])
+            for r, border in [(0, False), (1, True), (4, False)]:
+                ref = cv2.warpPerspective(np.ones(shape), Hm, shape[::-1], flags=cv2.INTER_NEAREST)
+                if r > 0:
+                    if border:
+                        ref = np.pad(ref, 1)
+                    ref = cv2.erode(ref, np.ones((2 * r + 1, 2 * r + 1), np.float32), iterations=1)
+                    if border:
+                        ref = ref[1:-1, 1:-1]
+                np.testing.assert_array_equal(oracle.valid_mask(shape, Hm, r, border), ref.astype(np.uint8))

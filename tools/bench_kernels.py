@@ -131,6 +131,20 @@ def main():
         n * (2 * Bp * H * W * 4 + H * W) + 2 * Bp * H * W * 4)
     add("ha_aggregate single n=99", timed(lambda: ops.ha_aggregate(p0, pa, None, masks, A, 'none', 2)),
         n * (Bp * H * W * 4 + H * W) + 2 * Bp * H * W * 4)
+    # the 99 valid masks of one adaptation batch, device raster vs the host cv2 loop it replaces
+    import time
+    import numpy as np
+    from multipoint_b200 import utils
+    np.random.seed(0)
+    cfg = utils._check_ha_config({})
+    Hs, _ = utils.sample_adaptation_homographies((H, W), cfg, with_masks=False)
+    Minv = torch.from_numpy(utils.invert_homographies(Hs)).to(dev)
+    ms = timed(lambda: ops.valid_masks(Minv, H, W, cfg['erosion_radius'], cfg['mask_border']))
+    t0 = time.perf_counter()
+    for Hm in Hs[:20]:
+        utils.compute_valid_mask((H, W), Hm, cfg['erosion_radius'], cfg['mask_border'])
+    host_ms = (time.perf_counter() - t0) * 1e3 * len(Hs) / 20
+    add("valid_mask n=99 512x640 erosion 5 + border", ms, len(Hs) * H * W, host_cv2_loop_ms=round(host_ms, 1))
     if args.out:
         with open(args.out, "w") as f:
             json.dump(res, f, indent=1)

@@ -67,7 +67,7 @@ def main():
 
     def sample():
         np.random.seed(5)
-        return utils.sample_adaptation_homographies((64, 80), full_cfg)
+        return utils.sample_adaptation_homographies((64, 80), full_cfg, with_masks=False)
 
     Hs, masks = parallel.broadcast_homographies(sample, device=dev)
     sharded = utils.homographic_adaptation_multispectral(data, net, cfg, homographies=Hs, masks=masks, shard=parallel.adaptation_shard())
