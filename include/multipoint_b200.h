@@ -200,6 +200,32 @@ MP_API int mp_ha_aggregate_f32(const float *prob0, const float *probw_a, const f
 MP_API int mp_valid_mask_u8(const double *Minv, int n, int H, int W, int erosion_radius, int mask_border,
                             uint8_t *mask, mp_stream_t stream);
 
+/* ---- point geometry of the evaluation loops, multipoint/utils/evaluation.py ----
+ * All three take P problems (the samples of a batch) with a fixed capacity per problem and optional
+ * device-side counts (NULL = every slot is live), the layout mp_box_nms_f32 / mp_extract_keypoints_f32
+ * produce, so the stages chain without a host round trip.  Points are (y,x) like the reference's.
+ *
+ * warp_keypoints (multipoint/utils/homographies.py:331-346): cv2.perspectiveTransform of the flipped
+ * points in double, flipped back.  kp (P,cap,2) int64; Hm (P,3,3) float64; out_f64 (P,cap,2) and/or
+ * out_i64 (P,cap,2) = the reference's `.astype(int)` truncation.  Either output may be NULL. */
+MP_API int mp_warp_keypoints_i64(const int64_t *kp, const int *counts, int P, int cap, const double *Hm,
+                                 double *out_f64, int64_t *out_i64, mp_stream_t stream);
+
+/* evaluation.py:176-197 for one direction: min_d2[p,i] = min_j |q[p,i] - t[p,j]|^2 as an exact int64
+ * (np.linalg.norm of an integer difference is the square root of this), -1 where the query fails
+ * filter_points (homographies.py:358-372: 0 <= y < H, 0 <= x < W), INT64_MAX where there is no target.
+ * The repeatability count is sum(sqrt((double)min_d2) <= distance_thresh) over min_d2 >= 0. */
+MP_API int mp_points_min_dist2_i64(const int64_t *q, const int *nq, int capq, const int64_t *t, const int *nt,
+                                   int capt, int P, int H, int W, int64_t *min_d2, mp_stream_t stream);
+
+/* evaluation.py:294-315: correct[i,j] = ||float32(qw[i] - t[j])||_2 <= threshold with qw (P,capq,2)
+ * float64 warped points and t (P,capt,2) int64, never materialised: row_any[p,i] = any_j correct[i,j]
+ * (what correct.sum(1).nonzero() counts, :301-302) and tp[p,k] = correct[mq[p,k], mt[p,k]] for the
+ * matcher's pairs (:306-315; nm (P) counts or NULL, capm capacity).  row_any or tp may be NULL. */
+MP_API int mp_points_correct_f32(const double *qw, const int *nq, int capq, const int64_t *t, const int *nt, int capt,
+                                 int P, float threshold, uint8_t *row_any, const int *mq, const int *mt, const int *nm,
+                                 int capm, uint8_t *tp, mp_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

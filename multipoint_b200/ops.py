@@ -318,3 +318,62 @@ def ha_aggregate(prob0, probw_a, probw_b, masks, Ainv, aggregation, min_count, i
                                                    _ptr(prob_acc), _ptr(count_acc), _ptr(out), _stream(probw_a)),
                    "mp_ha_aggregate_f32")
     return out if finish else (prob_acc, count_acc)
+
+
+# ----------------------------------------------------------------------------- evaluation point geometry
+def _counts(c, P, name):
+    if c is None:
+        return None
+    c = _cuda(c, torch.int32, name)
+    if c.numel() != P:
+        raise ValueError("%s must have %d entries" % (name, P))
+    return c
+
+
+def warp_keypoints(kp, homographies, counts=None, as_int=True):
+    """kp (P,cap,2) int64 (y,x), homographies (P,3,3) float64 -> warped (P,cap,2): int64 (truncated, like the
+    reference's default) or float64."""
+    kp = _cuda(kp, torch.int64, "kp")
+    P, cap = kp.shape[:2]
+    Hm = _cuda(homographies, torch.float64, "homographies").reshape(P, 9)
+    counts = _counts(counts, P, "counts")
+    out = torch.zeros((P, cap, 2), dtype=torch.int64 if as_int else torch.float64, device=kp.device)
+    with torch.cuda.device(kp.device):
+        _lib.check(_lib.load().mp_warp_keypoints_i64(_ptr(kp), _ptr(counts), P, cap, _ptr(Hm), None if as_int else _ptr(out),
+                                                     _ptr(out) if as_int else None, _stream(kp)), "mp_warp_keypoints_i64")
+    return out
+
+
+def points_min_dist2(q, t, H, W, nq=None, nt=None):
+    """q (P,capq,2), t (P,capt,2) int64 -> (P,capq) int64: exact squared distance to the nearest target,
+    -1 for queries outside the (H,W) frame, INT64_MAX without targets."""
+    q = _cuda(q, torch.int64, "q")
+    t = _cuda(t, torch.int64, "t")
+    P, capq = q.shape[:2]
+    capt = t.shape[1]
+    out = torch.full((P, capq), -1, dtype=torch.int64, device=q.device)
+    with torch.cuda.device(q.device):
+        _lib.check(_lib.load().mp_points_min_dist2_i64(_ptr(q), _ptr(_counts(nq, P, "nq")), capq, _ptr(t), _ptr(_counts(nt, P, "nt")),
+                                                       capt, P, int(H), int(W), _ptr(out), _stream(q)), "mp_points_min_dist2_i64")
+    return out
+
+
+def points_correct(qw, t, threshold, nq=None, nt=None, mq=None, mt=None, nm=None):
+    """qw (P,capq,2) float64 warped points, t (P,capt,2) int64 -> (row_any (P,capq) uint8, tp (P,capm) uint8 or None)."""
+    qw = _cuda(qw, torch.float64, "qw")
+    t = _cuda(t, torch.int64, "t")
+    P, capq = qw.shape[:2]
+    capt = t.shape[1]
+    row_any = torch.zeros((P, capq), dtype=torch.uint8, device=qw.device)
+    tp = None
+    capm = 0
+    if mq is not None:
+        mq = _cuda(mq, torch.int32, "mq")
+        mt = _cuda(mt, torch.int32, "mt")
+        capm = mq.shape[1]
+        tp = torch.zeros((P, capm), dtype=torch.uint8, device=qw.device)
+    with torch.cuda.device(qw.device):
+        _lib.check(_lib.load().mp_points_correct_f32(_ptr(qw), _ptr(_counts(nq, P, "nq")), capq, _ptr(t), _ptr(_counts(nt, P, "nt")), capt,
+                                                     P, float(threshold), _ptr(row_any), _ptr(mq), _ptr(mt), _ptr(_counts(nm, P, "nm")),
+                                                     capm, _ptr(tp), _stream(qw)), "mp_points_correct_f32")
+    return row_any, tp

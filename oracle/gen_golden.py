@@ -96,6 +96,95 @@ def gen_magicleap():
          model_logits=o['logits'].numpy(), model_desc=o['desc'].numpy(), model_prob=o['prob'].numpy())
 
 
+# ---------------------------------------------------------------- evaluation loops
+def evaluation_batches():
+    """Two batches of two 128x160 pairs with canned network outputs (the net is a lookup, so the reference on
+    the CPU and the product on the GPU see identical heatmaps / descriptor maps).  Batch 0: no homography key
+    (identity path), thermal = optical shifted by a pixel here and there + descriptor noise, so many matches
+    are correct.  Batch 1: sampled homographies on both spectra and a partially masked frame."""
+    H, W, D = 128, 160, 64
+    batches = []
+    rng = np.random.default_rng(77)
+    for bi in range(2):
+        po = syn.heatmap(300 + bi, 2, H, W, squarings=5, scale=0.5)
+        do = syn.descriptor_map(310 + bi, 2, D, H // 8, W // 8)
+        do /= np.linalg.norm(do, axis=1, keepdims=True)
+        if bi == 0:
+            pt = po.copy()
+            pt[:, :, :, 80:] = np.roll(po[:, :, :, 80:], 1, axis=2)        # right half moved down one row
+            dt = do + 0.05 * rng.standard_normal(do.shape).astype(np.float32)
+        else:
+            pt = syn.heatmap(320 + bi, 2, H, W, squarings=5, scale=0.5)
+            dt = syn.descriptor_map(330 + bi, 2, D, H // 8, W // 8)
+        dt /= np.linalg.norm(dt, axis=1, keepdims=True)
+        mo = np.ones((2, 1, H, W), np.float32)
+        mt = np.ones((2, 1, H, W), np.float32)
+        if bi == 1:
+            mt[:, :, :10] = 0
+            mo[1, :, :, -7:] = 0
+        b = {'optical': {'image': np.zeros((2, 1, H, W), np.float32), 'valid_mask': mo, 'stub_prob': po, 'stub_desc': do.astype(np.float32)},
+             'thermal': {'image': np.zeros((2, 1, H, W), np.float32), 'valid_mask': mt, 'stub_prob': pt, 'stub_desc': dt.astype(np.float32)}}
+        if bi == 1:
+            np.random.seed(40)
+            cfg = dict(translation=True, rotation=True, scaling=True, perspective=True, scaling_amplitude=0.1,
+                       perspective_amplitude_x=0.1, perspective_amplitude_y=0.1, patch_ratio=0.9, max_angle=0.3,
+                       allow_artifacts=True)
+            b['optical']['homography'] = np.stack([utils.sample_homography(np.array([H, W]), **cfg) for _ in range(2)]).astype(np.float32)
+            b['thermal']['homography'] = np.stack([utils.sample_homography(np.array([H, W]), **cfg) for _ in range(2)]).astype(np.float32)
+        batches.append(b)
+    return batches
+
+
+def gen_evaluation():
+    from multipoint.utils import evaluation as ref_eval
+    batches = evaluation_batches()
+
+    def loader():
+        return [{s: {k: torch.from_numpy(v.copy()) for k, v in b[s].items()} for s in b} for b in batches]
+
+    def net(d):
+        return {'prob': d['stub_prob'].clone(), 'desc': d['stub_desc'].clone()}
+
+    out = {}
+    for bi, b in enumerate(batches):
+        for s in b:
+            for k, v in b[s].items():
+                if k != 'image':
+                    out["in%d_%s_%s" % (bi, s, k)] = v
+    for tag, topk in (("rep_top0", 0), ("rep_top150", 150)):
+        cfg = {'prediction': {'detection_threshold': 0.015, 'nms': 4, 'topk': topk, 'cpu_nms': True}}
+        mean, rep, nko, nkt = ref_eval.compute_repeatability_multispectral(net, loader(), 'cpu', cfg, distance_thresh=3)
+        out[tag] = np.array([mean] + list(rep))
+        out[tag + "_nkp"] = np.array([nko, nkt])
+    for tag, method, kwargs, topk in (("desc_bf", "bfmatcher", {'crossCheck': True}, 0), ("desc_nn", "nnmatcher", {'threshold': 0.9}, 200)):
+        cfg = {'detection_threshold': 0.015, 'nms': 4, 'topk': topk, 'cpu_nms': True, 'reprojection_threshold': 3,
+               'matching': {'method': method, 'knn_matches': False, 'method_kwargs': kwargs}}
+        res = ref_eval.compute_descriptor_metrics(net, loader(), 'cpu', cfg, threshold_keypoints=4, threshold_warp=4)
+        for k, v in res.items():
+            out[tag + "_" + k] = np.asarray(v)
+    # the point geometry on its own: reference expressions evaluated literally (evaluation.py:166-197, 288-302)
+    np.random.seed(41)
+    pts = {}
+    for i in range(6):
+        Hm = utils.sample_homography(np.array([128, 160]))
+        if i % 2:
+            Hm = Hm.astype(np.float32)                      # the loops pass fp32 matrices from torch
+        a = syn.keypoints(500 + i, 180, 128, 160)
+        b = syn.keypoints(520 + i, 150, 128, 160)
+        wi = utils.warp_keypoints(a, Hm)
+        wf = utils.warp_keypoints(a.astype(np.float32), Hm, np.float64)
+        wi_f = utils.filter_points(wi, (128, 160))
+        dist = np.linalg.norm(np.expand_dims(wi_f, 1) - np.expand_dims(b, 0), ord=None, axis=2)
+        d = torch.from_numpy(wf).unsqueeze(1) - torch.from_numpy(b).unsqueeze(0)
+        correct = torch.norm(d.float(), dim=-1) <= 4
+        pts.update({"pt%d_H" % i: Hm, "pt%d_a" % i: a, "pt%d_b" % i: b, "pt%d_warp_int" % i: wi, "pt%d_warp_f64" % i: wf,
+                    "pt%d_min_dist" % i: np.min(dist, axis=1), "pt%d_filtered" % i: wi_f,
+                    "pt%d_correct_rows" % i: correct.sum(1).nonzero()[:, 0].numpy(),
+                    "pt%d_correct_diag" % i: correct[torch.arange(150), torch.arange(150)].numpy()})
+    out.update(pts)
+    save("evaluation", **out)
+
+
 # ---------------------------------------------------------------- row 4: box_nms
 def gen_nms():
     out = {}

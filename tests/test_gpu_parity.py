@@ -651,3 +651,94 @@ def test_entry_points_run_and_agree(tmp_path, utils):
     z = np.load(out)
     assert sorted(z.files) == ['a/keypoints', 'b/keypoints'] and z['a/keypoints'].dtype == np.int64
     assert export_keypoints.main(common + ['-o', str(out), '-skip']) == {}     # resume: nothing left to do
+
+
+# ------------------------------------------------------------------ evaluation loops
+def test_evaluation_point_kernels(ops, oracle):
+    g = load_golden("evaluation")
+    # batched: the six fixture problems in one call each, ragged counts
+    P, capa, capb = 6, 190, 160
+    a = np.zeros((P, capa, 2), np.int64)
+    b = np.zeros((P, capb, 2), np.int64)
+    Hs = np.zeros((P, 3, 3), np.float64)
+    na, nb = [], []
+    for i in range(P):
+        ai, bi = g["pt%d_a" % i], g["pt%d_b" % i]
+        a[i, :len(ai)] = ai
+        b[i, :len(bi)] = bi
+        Hs[i] = g["pt%d_H" % i]
+        na.append(len(ai))
+        nb.append(len(bi))
+    ca, cb = cu(np.array(na, np.int32)), cu(np.array(nb, np.int32))
+    wi = ops.warp_keypoints(cu(a), cu(Hs), ca)
+    wf = ops.warp_keypoints(cu(a), cu(Hs), ca, as_int=False)
+    d2 = ops.points_min_dist2(wi, cu(b), 128, 160, ca, cb)
+    mq = np.tile(np.arange(150, dtype=np.int32), (P, 1))
+    row_any, tp = ops.points_correct(wf, cu(b), 4.0, ca, cb, cu(mq), cu(mq), cu(np.full(P, 150, np.int32)))
+    for i in range(P):
+        n = na[i]
+        np.testing.assert_array_equal(wi[i, :n].cpu().numpy(), g["pt%d_warp_int" % i])
+        np.testing.assert_array_equal(wf[i, :n].cpu().numpy(), g["pt%d_warp_f64" % i])       # bit-exact doubles vs cv2
+        d2i = d2[i, :n].cpu().numpy()
+        np.testing.assert_array_equal(d2i, oracle.points_min_dist2(g["pt%d_warp_int" % i], g["pt%d_b" % i], 128, 160))
+        np.testing.assert_array_equal(np.sqrt(d2i[d2i >= 0].astype(np.float64)), g["pt%d_min_dist" % i])
+        np.testing.assert_array_equal(np.flatnonzero(row_any[i, :n].cpu().numpy()), g["pt%d_correct_rows" % i])
+        np.testing.assert_array_equal(tp[i].cpu().numpy().astype(bool), g["pt%d_correct_diag" % i])
+        assert int(d2[i, n:].max()) == -1 and int(row_any[i, n:].max()) == 0                 # padding untouched
+    # no targets / no queries
+    none = ops.points_min_dist2(wi[:1], cu(np.zeros((1, 1, 2), np.int64)), 128, 160, ca[:1], cu(np.zeros(1, np.int32)))
+    inside = none[0, :na[0]].cpu().numpy()
+    assert set(np.unique(inside)) <= {-1, np.iinfo(np.int64).max}
+    # a larger random problem against the oracle
+    rng = np.random.default_rng(5)
+    q = rng.integers(-20, 660, (1, 3000, 2))
+    t = rng.integers(0, 640, (1, 2500, 2))
+    got = ops.points_min_dist2(cu(q), cu(t), 512, 640)[0].cpu().numpy()
+    np.testing.assert_array_equal(got, oracle.points_min_dist2(q[0], t[0], 512, 640))
+    qw = q[0].astype(np.float64) + rng.random((3000, 2))
+    ra, _ = ops.points_correct(cu(qw[None]), cu(t), 6.0)
+    np.testing.assert_array_equal(ra[0].cpu().numpy(), oracle.points_correct(qw, t[0], 6.0)[0])
+
+
+def _evaluation_loader(g):
+    batches = []
+    for bi in range(2):
+        b = {}
+        for s in ('optical', 'thermal'):
+            d = {'image': torch.zeros((2, 1, 128, 160))}
+            for k in ('valid_mask', 'stub_prob', 'stub_desc', 'homography'):
+                key = "in%d_%s_%s" % (bi, s, k)
+                if key in g.files:
+                    d[k] = torch.from_numpy(g[key].copy())
+            b[s] = d
+        batches.append(b)
+    return batches
+
+
+def test_evaluation_loops_match_reference():
+    """compute_repeatability_multispectral / compute_descriptor_metrics on canned network outputs: every returned
+    value equals what the reference's loops returned on the CPU (tests/golden/evaluation.npz)."""
+    from multipoint_b200 import evaluation
+    g = load_golden("evaluation")
+
+    def net(d):
+        return {'prob': d['stub_prob'].clone(), 'desc': d['stub_desc'].clone()}
+
+    for tag, topk in (("rep_top0", 0), ("rep_top150", 150)):
+        cfg = {'prediction': {'detection_threshold': 0.015, 'nms': 4, 'topk': topk, 'cpu_nms': True}}
+        mean, rep, nko, nkt = evaluation.compute_repeatability_multispectral(net, _evaluation_loader(g), 'cuda', cfg, distance_thresh=3)
+        np.testing.assert_array_equal(np.array([mean] + list(rep)), g[tag])
+        np.testing.assert_array_equal(np.array([nko, nkt]), g[tag + "_nkp"])
+    for tag, method, kwargs, topk in (("desc_bf", "bfmatcher", {'crossCheck': True}, 0), ("desc_nn", "nnmatcher", {'threshold': 0.9}, 200)):
+        cfg = {'detection_threshold': 0.015, 'nms': 4, 'topk': topk, 'cpu_nms': True, 'reprojection_threshold': 3,
+               'matching': {'method': method, 'knn_matches': False, 'method_kwargs': kwargs}}
+        res = evaluation.compute_descriptor_metrics(net, _evaluation_loader(g), 'cuda', cfg, threshold_keypoints=4, threshold_warp=4)
+        assert sorted(res.keys()) == sorted(k[len(tag) + 1:] for k in g.files if k.startswith(tag + "_"))
+        for k, v in res.items():
+            want = g[tag + "_" + k]
+            if k.startswith(('tp_', 'fp_')):
+                np.testing.assert_array_equal(np.asarray(v), want, err_msg=k)
+            elif k in ('pts_dist', 'average_h_error'):
+                np.testing.assert_allclose(np.asarray(v), want, rtol=1e-6, err_msg=k)     # RANSAC + LM refinement on the host
+            else:
+                np.testing.assert_allclose(np.asarray(v), want, rtol=1e-6, atol=1e-7, err_msg=k)

@@ -302,3 +302,22 @@ def test_valid_mask_matches_reference(oracle):
                     if border:
                         ref = ref[1:-1, 1:-1]
                 np.testing.assert_array_equal(oracle.valid_mask(shape, Hm, r, border), ref.astype(np.uint8))
+
+
+def test_evaluation_point_geometry_matches_reference(oracle):
+    """warp_keypoints / filter_points + nearest distance / correct-match flags, against the
+    reference's own expressions frozen in tests/golden/evaluation.npz."""
+    g = load_golden("evaluation")
+    for i in range(6):
+        Hm, a, b = g["pt%d_H" % i], g["pt%d_a" % i], g["pt%d_b" % i]
+        wi = oracle.warp_keypoints(a, Hm)
+        np.testing.assert_array_equal(wi, g["pt%d_warp_int" % i])
+        wf = oracle.warp_keypoints(a, Hm, as_int=False)
+        np.testing.assert_array_equal(wf, g["pt%d_warp_f64" % i])                   # bit-exact doubles
+        d2 = oracle.points_min_dist2(wi, b, 128, 160)
+        np.testing.assert_array_equal(wi[d2 >= 0], g["pt%d_filtered" % i])          # filter_points
+        np.testing.assert_array_equal(np.sqrt(d2[d2 >= 0].astype(np.float64)), g["pt%d_min_dist" % i])
+        row_any, tp = oracle.points_correct(wf, b, 4.0, np.arange(150), np.arange(150))
+        np.testing.assert_array_equal(np.flatnonzero(row_any), g["pt%d_correct_rows" % i])
+        np.testing.assert_array_equal(tp.astype(bool), g["pt%d_correct_diag" % i])
+    assert (oracle.points_min_dist2(np.array([[3, 3]]), np.zeros((0, 2)), 10, 10) == np.iinfo(np.int64).max).all()
