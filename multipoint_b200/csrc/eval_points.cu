@@ -25,7 +25,7 @@ __global__ void warp_keypoints_kernel(const int64_t *__restrict__ kp, const int 
     const double *m = Hm + (size_t)p * 9;
     const size_t o = ((size_t)p * cap + i) * 2;
     const double y = (double)kp[o], x = (double)kp[o + 1];
-    // OpenCV's perspectiveTransform_64f as built with FMA contraction (see oracle/mp_oracle.c): fma(x, a, y*b) + c
+    // OpenCV's perspectiveTransform_64f as built with FMA contraction (measured against cv2): fma(x, a, y*b) + c
     double w = __dadd_rn(__fma_rn(x, m[6], __dmul_rn(y, m[7])), m[8]);
     double xo = 0., yo = 0.;
     if (fabs(w) > 1.1920928955078125e-07) {
