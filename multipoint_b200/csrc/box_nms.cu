@@ -304,7 +304,7 @@ nms_tile_kernel(const float *__restrict__ prob, float *__restrict__ out, int H, 
 // A tile with more than CAP candidates in its decidable region (> ~32 % density) skips the lists
 // and sweeps its pixels instead (same decisions, no extra memory).
 template <int TH, int TW, int E, bool VEC, int CAP>
-__global__ void __launch_bounds__(NMS_THREADS)
+__global__ void __launch_bounds__(NMS_THREADS, (TW <= 64 ? 7 : 3))  // 32x64 tiles: 7 CTAs/SM fit in shared memory, keep <= 36 registers
 nms_tile_fast_kernel(const float *__restrict__ prob, float *__restrict__ out, int H, int W, float thr,
                      const NmsFootprint fp, uint2 *__restrict__ survivors, int *__restrict__ surv_count,
                      uint32_t *__restrict__ worklist, int *__restrict__ work_count, int cap) {
@@ -330,6 +330,35 @@ nms_tile_fast_kernel(const float *__restrict__ prob, float *__restrict__ out, in
     const int ty0 = blockIdx.y * TH, tx0 = blockIdx.x * TW;
     const int gy0 = ty0 - E, gx0 = tx0 - E;
     const float *img = prob + (size_t)b * H * W;
+    // ---- 1. stage the tile + apron.  All of a thread's global loads are issued first (one round trip instead
+    //         of one per loop iteration: with ~20 waves of short-lived CTAs that serial latency was most of the
+    //         kernel's fixed cost), the shared-memory setup overlaps them.
+    //         Thread layout for the staging: column quad q = tid % QW fixed, rows r, r + RP, r + 2 RP, ... so the
+    //         index arithmetic is done once and each pass only moves down RP rows.
+    constexpr int RP = NMS_THREADS / QW;                 // rows per pass
+    constexpr int LD_ITERS = (EH + RP - 1) / RP;
+    const int sq = tid % QW, sr = tid / QW;
+    const int sgx = gx0 + 4 * sq;
+    const bool col_ok = sr < RP && (VEC ? (sgx >= 0 && sgx < W) : (sgx + 3 >= 0 && sgx < W));
+    float4 stage[LD_ITERS];
+#pragma unroll
+    for (int k = 0; k < LD_ITERS; ++k) {
+        const int ey = sr + k * RP;
+        const int gy = gy0 + ey;
+        float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (col_ok && ey < EH && gy >= 0 && gy < H) {
+            const float *rowp = img + (size_t)gy * W;
+            if (VEC) {
+                val = ld_stream_f4(reinterpret_cast<const float4 *>(rowp + sgx));
+            } else {
+                if (sgx + 0 >= 0 && sgx + 0 < W) val.x = rowp[sgx + 0];
+                if (sgx + 1 >= 0 && sgx + 1 < W) val.y = rowp[sgx + 1];
+                if (sgx + 2 >= 0 && sgx + 2 < W) val.z = rowp[sgx + 2];
+                if (sgx + 3 >= 0 && sgx + 3 < W) val.w = rowp[sgx + 3];
+            }
+        }
+        stage[k] = val;
+    }
     if (tid == 0) { n_list = 0; n_keptpos = 0; n_next[0] = n_next[1] = n_next[2] = 0; }
     if (tid < 7) {  // footprint rows re-centred in a 7-wide window
         const int dy = tid - RM;
@@ -338,28 +367,22 @@ nms_tile_fast_kernel(const float *__restrict__ prob, float *__restrict__ out, in
     for (int i = tid; i < EH * BW; i += NMS_THREADS) bm[i] = 0;
     __syncthreads();
 
-    // ---- 1. stage the tile + apron: threshold, encode (0 nothing, -s undecided), set bitmap ----
-    for (int i = tid; i < EH * QW; i += NMS_THREADS) {
-        const int ey = i / QW, q = i - ey * QW;
-        const int gy = gy0 + ey, gx = gx0 + 4 * q;
-        float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (gy >= 0 && gy < H) {
-            if (VEC) {
-                if (gx >= 0 && gx < W) val = ld_stream_f4(reinterpret_cast<const float4 *>(img + (size_t)gy * W + gx));
-            } else {
-                const float *rowp = img + (size_t)gy * W;
-                if (gx + 0 >= 0 && gx + 0 < W) val.x = rowp[gx + 0];
-                if (gx + 1 >= 0 && gx + 1 < W) val.y = rowp[gx + 1];
-                if (gx + 2 >= 0 && gx + 2 < W) val.z = rowp[gx + 2];
-                if (gx + 3 >= 0 && gx + 3 < W) val.w = rowp[gx + 3];
-            }
+    // threshold, encode (0 nothing, -s undecided), set bitmap
+    if (sr < RP) {
+        float *vdst = v + sr * EW + 4 * sq;
+        uint32_t *bdst = bm + sr * BW + (sq >> 3);
+        const int bsh = (4 * sq) & 31;
+#pragma unroll
+        for (int k = 0; k < LD_ITERS; ++k) {
+            if (sr + k * RP >= EH) break;
+            float4 val = stage[k];
+            const uint32_t nib = (uint32_t)(val.x > thr) | ((uint32_t)(val.y > thr) << 1) | ((uint32_t)(val.z > thr) << 2) |
+                                 ((uint32_t)(val.w > thr) << 3);  // strict, fp32 (utils.py:97); NaN is not a candidate
+            val.x = (nib & 1) ? -val.x : 0.f; val.y = (nib & 2) ? -val.y : 0.f;
+            val.z = (nib & 4) ? -val.z : 0.f; val.w = (nib & 8) ? -val.w : 0.f;
+            *reinterpret_cast<float4 *>(vdst + k * RP * EW) = val;
+            if (nib) atomicOr(bdst + k * RP * BW, nib << bsh);
         }
-        const uint32_t nib = (uint32_t)(val.x > thr) | ((uint32_t)(val.y > thr) << 1) | ((uint32_t)(val.z > thr) << 2) |
-                             ((uint32_t)(val.w > thr) << 3);  // strict, fp32 (utils.py:97); NaN is not a candidate
-        val.x = (nib & 1) ? -val.x : 0.f; val.y = (nib & 2) ? -val.y : 0.f;
-        val.z = (nib & 4) ? -val.z : 0.f; val.w = (nib & 8) ? -val.w : 0.f;
-        *reinterpret_cast<float4 *>(v + ey * EW + 4 * q) = val;
-        if (nib) atomicOr(&bm[ey * BW + (q >> 3)], nib << ((4 * q) & 31));
     }
     __syncthreads();
 
