@@ -17,14 +17,11 @@ constexpr int DN_WARPS = 8;
 template <int CPT>  // channels per thread; D <= CPT * DN_WARPS
 __global__ void __launch_bounds__(DN_WARPS * 32)
 normalize_desc_kernel(const float *__restrict__ x, float *__restrict__ out_nchw,
-                      float *__restrict__ out_nhwc, int D, int HW, int tiles_per_image, int total_tiles) {
+                      float *__restrict__ out_nhwc, int D, int HW, int tiles_per_image) {
     extern __shared__ float smem[];  // [DN_WARPS][32] partials, then optional [32][D+1] tile
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // grid-stride over the tiles (the host launches one CTA per tile today; capping the grid to share the
-    // SMs with the NMS kernel on a second stream was measured and lost: profiles/README.md)
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-    const int b = t / tiles_per_image;
-    const int p0 = (t - b * tiles_per_image) * 32;
+    const int b = blockIdx.x / tiles_per_image;
+    const int p0 = (blockIdx.x - b * tiles_per_image) * 32;
     const int p = p0 + lane;
     const bool live = p < HW;
     const float *src = x + (size_t)b * D * HW + p;
@@ -70,8 +67,6 @@ normalize_desc_kernel(const float *__restrict__ x, float *__restrict__ out_nchw,
             for (int c = lane; c < D; c += 32) dst[c] = tile[cell * ld + c];
         }
     }
-    __syncthreads();  // smem is reused by the next tile
-    }
 }
 
 // any D: one thread per cell, two passes over the channels (second pass hits L2)
@@ -106,14 +101,13 @@ extern "C" int mp_normalize_descriptors_f32(const float *x, int B, int D, int HW
     cudaStream_t s = (cudaStream_t)stream;
     const int tiles = (HW + 31) / 32;
     const size_t smem = (mp::DN_WARPS * 32 + (out_nhwc ? 32 * (D + 1) : 0)) * sizeof(float);
-    const int total_tiles = B * tiles;
-    const unsigned grid = (unsigned)total_tiles;
+    const unsigned grid = (unsigned)(B * tiles);
     if (D <= 64) {
-        mp::normalize_desc_kernel<8><<<grid, mp::DN_WARPS * 32, smem, s>>>(x, out_nchw, out_nhwc, D, HW, tiles, total_tiles);
+        mp::normalize_desc_kernel<8><<<grid, mp::DN_WARPS * 32, smem, s>>>(x, out_nchw, out_nhwc, D, HW, tiles);
     } else if (D <= 128) {
-        mp::normalize_desc_kernel<16><<<grid, mp::DN_WARPS * 32, smem, s>>>(x, out_nchw, out_nhwc, D, HW, tiles, total_tiles);
+        mp::normalize_desc_kernel<16><<<grid, mp::DN_WARPS * 32, smem, s>>>(x, out_nchw, out_nhwc, D, HW, tiles);
     } else if (D <= 256) {
-        mp::normalize_desc_kernel<32><<<grid, mp::DN_WARPS * 32, smem, s>>>(x, out_nchw, out_nhwc, D, HW, tiles, total_tiles);
+        mp::normalize_desc_kernel<32><<<grid, mp::DN_WARPS * 32, smem, s>>>(x, out_nchw, out_nhwc, D, HW, tiles);
     } else {
         const long long total = (long long)B * HW;
         mp::normalize_desc_generic_kernel<<<(unsigned)((total + 127) / 128), 128, 0, s>>>(x, out_nchw, out_nhwc, B, D, HW);
