@@ -561,11 +561,11 @@ match_decide_kernel(const float *__restrict__ d1, const int32_t *__restrict__ n1
     float dist = 0.f;
     if (i < n_a) {
         j = idx12[g];
+        if (j >= 0 && kind == MP_MATCH_MUTUAL && cross_check && idx21[(size_t)p * N2 + j] != i) j = -1;  // not mutual: no distance needed
         if (j >= 0) {
             const float *a = d1 + (size_t)g * D;
             dist = pair_distance(a, d2 + ((size_t)p * N2 + j) * D, D, metric, lane);
             if (kind == MP_MATCH_MUTUAL) {
-                if (cross_check && idx21[(size_t)p * N2 + j] != i) j = -1;
                 if (threshold >= 0.f && !(dist < threshold)) j = -1;
             } else {
                 // knnMatch(k=2) + Lowe ratio (matching.py:21-28); needs a second neighbour
