@@ -369,6 +369,7 @@ def main():
     algorithmic = {  # per launch: ("hbm", bytes) or ("tensor", flops); SURVEY.md 8d / DESIGN.md section 4
         "detector_head_kernel": ("hbm", B2 * (65 * 5120 * 4 + H * W * 4)),
         "nms_tile_fast_kernel": ("hbm", B2 * 2 * H * W * 4),
+        "nms_candidates_kernel": ("hbm", B2 * 2 * H * W * 4),   # heatmap read + dense map written (the candidate list is extra)
         "normalize_desc_kernel": ("hbm", B2 * 2 * 4 * Dd * 5120),
         "sample_descriptors_kernel": ("hbm", B2 * (min(16 * Kp * Dd, 4 * Dd * 5120) + 4 * Kp * Dd + 16 * Kp)),
         "match_prep_vec_kernel": ("hbm", P * Kp * Dd * (4 + 2 + 2)),

@@ -113,6 +113,53 @@ def test_box_nms_hand_cases(utils, tag, size, topk):
     np.testing.assert_array_equal(got.numpy(), want)
 
 
+def test_box_nms_sparse_topk_path(utils, oracle):
+    """keep_top_k > 0 takes the sparse path (only the candidates that can reach the top k are settled; images it
+    cannot handle are redone by the dense kernels).  Every regime against the oracle, bit for bit."""
+    rng = np.random.default_rng(21)
+    H, W = 96, 160
+
+    def check(hm, size, k, thr=0.015):
+        got = utils.box_nms(cu(hm), size, thr, keep_top_k=k).cpu().numpy()
+        np.testing.assert_array_equal(got, oracle.box_nms(hm, size, thr, keep_top_k=k), err_msg="size %s k %d" % (size, k))
+
+    noise = syn.heatmap(901, 3, H, W)                                   # i.i.d. peaks
+    for k in (1, 7, 100, 400, 5000):                                    # 5000 > all survivors; > SP_LIST_CAP/2: dense path
+        check(noise, 4, k)
+    check(noise, 3, 50)
+    check(noise, 2.5, 50)
+    check(noise, 8, 50)                                                 # reach > 3: dense path
+    # blobs: every peak is surrounded by slightly lower candidates, so few of the admitted candidates survive and
+    # the threshold has to be lowered (retry loop)
+    yy, xx = np.mgrid[0:H, 0:W]
+    blobs = np.zeros((2, 1, H, W), np.float32)
+    for b in range(2):
+        for _ in range(60):
+            cy, cx, a = rng.integers(0, H), rng.integers(0, W), rng.uniform(0.1, 0.9)
+            blobs[b, 0] = np.maximum(blobs[b, 0], (a * np.exp(-((yy - cy) ** 2 + (xx - cx) ** 2) / 18.0)).astype(np.float32))
+    for k in (5, 40, 300):
+        check(blobs, 4, k)
+    # long dependency chains: a ramp (every pixel beats its right neighbour) -> round limit -> redone densely
+    ramp = (0.02 + 0.9 * (np.arange(H * W, dtype=np.float32)[::-1] / (H * W))).reshape(1, 1, H, W)
+    check(ramp, 4, 30)
+    # constant map: every pixel ties; more candidates than the list holds at full size -> redone densely
+    check(np.full((1, 1, H, W), 0.5, np.float32), 4, 10)
+    flat = np.full((1, 1, 512, 640), 0.25, np.float32)
+    check(flat, 4, 64)
+    # empty map, a single candidate, fewer candidates than k
+    check(np.zeros((2, 1, H, W), np.float32), 4, 10)
+    one = np.zeros((1, 1, H, W), np.float32)
+    one[0, 0, 50, 70] = 0.3
+    check(one, 4, 10)
+    # a mixed batch: image 0 goes sparse, image 1 (constant) is flagged and redone
+    mixed = np.concatenate([syn.heatmap(902, 1, 512, 640), flat])
+    check(mixed, 4, 2048)
+    # heavy ties at the cut (scores quantised to 1/64): the stable order decides, like the oracle
+    check(syn.heatmap(903, 2, H, W, quant=64), 4, 25)
+    # not a multiple of 4 wide (scalar staging path)
+    check(syn.heatmap(904, 2, 61, 75), 4, 20)
+
+
 def assert_equal_up_to_topk_ties(got, want):
     for b in range(got.shape[0]):
         gb, wb = got[b], want[b]
