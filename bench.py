@@ -229,8 +229,16 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / K
+        launches = (_lib.launch_count() - l0) // K
+        kern = None
+        if os.environ.get("MP_BENCH_HOT_KERNELS"):   # per-kernel event times of the same steps (adds an event per launch)
+            _lib.profile_begin()
+            for _ in range(K):
+                hot_only()
+            torch.cuda.synchronize()
+            kern = {k: round(v["total_ms"] * 1e3 / K, 1) for k, v in sorted(_lib.profile_end().items(), key=lambda kv: -kv[1]["total_ms"])}
         print(json.dumps({"note": "--only-hot run (profiling aid, not a bench line)", "ms_per_step": ms,
-                          "pairs_per_s": P * 1000.0 / ms, "gpu_launches_per_step": (_lib.launch_count() - l0) // K}))
+                          "pairs_per_s": P * 1000.0 / ms, "gpu_launches_per_step": launches, "kernels_us_per_step": kern}))
         return 0
 
     net = build_net(args.desc, dev)

@@ -253,7 +253,7 @@ match_recheck_pair_kernel(const float *__restrict__ d1, int N1, const float *__r
 // halving exchange (18 shuffles instead of 80), so row r's total lands in the lanes with
 // ((lane >> 2) & 7) == r.
 constexpr int RK_ROWS = 8, RK_Z = 4, RK_WARPS = 8, RK_MAXD = 256;
-constexpr int RK_ROW_MAX = 16, RK_ROW_Y = 16;  // groups with <= RK_ROW_MAX rows use match_recheck_row_kernel
+constexpr int RK_ROW_MAX = 16;  // groups with <= RK_ROW_MAX rows use match_recheck_row_kernel
 
 template <int DPL>  // elements per lane: D <= 32*DPL
 __global__ void __launch_bounds__(RK_WARPS * 32)
@@ -367,21 +367,26 @@ match_recheck_kernel(const float *__restrict__ d1, const int32_t *__restrict__ n
     }
 }
 
-// Few rows on a group's full list (the usual case: a handful per call): one 1024-thread CTA per
-// row, 32 warps striding over the other set's rows two at a time with the next two prefetched.
-// The 8-row kernel above amortises the other set's traffic better but its single chunk per group
-// runs at the latency of one CTA walking 2 MB alone; it takes over when a group has more than
-// RK_ROW_MAX flagged rows.
+// Few rows on a group's full list (the usual case: a handful per call).  The 8-row kernel above
+// amortises the other set's traffic but its single chunk per group runs at the latency of one CTA
+// walking 2 MB alone; one CTA per row was no better (58 us for ~26 rows: 32 dependent L2/DRAM round
+// trips).  Here every flagged row is cut into RK_SPLIT slices of the other set, one 8-warp CTA per
+// (group, slice) walking its slice two rows at a time with the next two prefetched (4 round trips
+// for 2048 rows); the slices' (key, index) partials meet in global memory and the last CTA to
+// arrive -- a per-row counter that it resets for the next call -- writes the winner.
+constexpr int RK_SPLIT = 32;
 
 template <int DPL>
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(256)
 match_recheck_row_kernel(const float *__restrict__ d1, const int32_t *__restrict__ n1, int N1,
                          const float *__restrict__ d2, const int32_t *__restrict__ n2, int N2, int D, int metric,
                          const int32_t *__restrict__ flagged1, const int32_t *__restrict__ flagged2,
-                         const int *__restrict__ n_flagged, int32_t *__restrict__ idx12, int32_t *__restrict__ idx21) {
-    __shared__ double red_key[32];
-    __shared__ int red_idx[32];
-    const int group = blockIdx.x, p = group >> 1, side = group & 1;
+                         const int *__restrict__ n_flagged, double *__restrict__ part_key, int *__restrict__ part_idx,
+                         int *__restrict__ row_done, int32_t *__restrict__ idx12, int32_t *__restrict__ idx21) {
+    __shared__ double red_key[8];
+    __shared__ int red_idx[8];
+    __shared__ int is_last;
+    const int group = blockIdx.x, p = group >> 1, side = group & 1, slice = blockIdx.y;
     const int count = n_flagged[group];
     if (count == 0 || count > RK_ROW_MAX) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -391,7 +396,9 @@ match_recheck_row_kernel(const float *__restrict__ d1, const int32_t *__restrict
     const int32_t *rows = (side == 0 ? flagged1 : flagged2) + (size_t)p * NA;
     int32_t *dst = side == 0 ? idx12 + (size_t)p * N1 : idx21 + (size_t)p * N2;
     const int nb = side == 0 ? (n2 ? min(n2[p], N2) : N2) : (n1 ? min(n1[p], N1) : N1);
-    for (int item = blockIdx.y; item < count; item += RK_ROW_Y) {
+    const int chunk = ((nb + RK_SPLIT - 1) / RK_SPLIT + 15) & ~15;  // multiple of the 16 rows one pass covers
+    const int j_lo = slice * chunk, j_hi = min(nb, j_lo + chunk);
+    for (int item = 0; item < count; ++item) {
         const int row = rows[item];
         double a[DPL];
 #pragma unroll
@@ -403,22 +410,22 @@ match_recheck_row_kernel(const float *__restrict__ d1, const int32_t *__restrict
 #pragma unroll
             for (int i = 0; i < DPL; ++i) {
                 const int k = lane + 32 * i;
-                dstv[i] = (j < nb && k < D) ? __ldg(Bm + (size_t)j * D + k) : 0.f;
+                dstv[i] = (j < j_hi && k < D) ? __ldg(Bm + (size_t)j * D + k) : 0.f;
             }
         };
         float nx[2][DPL];
-        fetch(warp * 2, nx[0]);
-        fetch(warp * 2 + 1, nx[1]);
+        fetch(j_lo + warp * 2, nx[0]);
+        fetch(j_lo + warp * 2 + 1, nx[1]);
         double best = INFINITY;
         int bidx = 0x7fffffff;
-        for (int j = warp * 2; j < nb; j += 64) {
+        for (int j = j_lo + warp * 2; j < j_hi; j += 16) {
             float cur[2][DPL];
 #pragma unroll
             for (int c = 0; c < 2; ++c)
 #pragma unroll
                 for (int i = 0; i < DPL; ++i) cur[c][i] = nx[c][i];
-            fetch(j + 64, nx[0]);
-            fetch(j + 65, nx[1]);
+            fetch(j + 16, nx[0]);
+            fetch(j + 17, nx[1]);
             double acc[2] = {0.0, 0.0};
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
@@ -439,18 +446,38 @@ match_recheck_row_kernel(const float *__restrict__ d1, const int32_t *__restrict
             for (int c = 0; c < 2; ++c) {
                 double key = acc[c];
                 if (metric == MP_METRIC_NN) key = -fmin(1.0, fmax(-1.0, key));
-                if (j + c < nb && key < best) { best = key; bidx = j + c; }
+                if (j + c < j_hi && key < best) { best = key; bidx = j + c; }
             }
         }
         __syncthreads();
         if (lane == 0) { red_key[warp] = best; red_idx[warp] = bidx; }
         __syncthreads();
+        const size_t slot = ((size_t)group * RK_ROW_MAX + item) * RK_SPLIT;
         if (threadIdx.x == 0) {
             double bk = INFINITY;
             int bi = 0x7fffffff;
-            for (int w = 0; w < 32; ++w)
+            for (int w = 0; w < 8; ++w)
                 if (red_key[w] < bk || (red_key[w] == bk && red_idx[w] < bi)) { bk = red_key[w]; bi = red_idx[w]; }
-            dst[row] = bi == 0x7fffffff ? -1 : bi;
+            part_key[slot + slice] = bk;
+            part_idx[slot + slice] = bi;
+            __threadfence();
+            is_last = atomicAdd(row_done + group * RK_ROW_MAX + item, 1) == RK_SPLIT - 1;
+        }
+        __syncthreads();
+        if (is_last && warp == 0) {  // uniform per CTA
+            __threadfence();
+            double bk = __ldcg(part_key + slot + lane);
+            int bi = __ldcg(part_idx + slot + lane);
+#pragma unroll
+            for (int sft = 16; sft > 0; sft >>= 1) {
+                const double ok = __shfl_xor_sync(0xffffffffu, bk, sft);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, sft);
+                if (ok < bk || (ok == bk && oi < bi)) { bk = ok; bi = oi; }
+            }
+            if (lane == 0) {
+                dst[row] = bi == 0x7fffffff ? -1 : bi;
+                row_done[group * RK_ROW_MAX + item] = 0;  // ready for the next call
+            }
         }
     }
 }
@@ -586,6 +613,87 @@ match_decide_kernel(const float *__restrict__ d1, const int32_t *__restrict__ n1
     }
 }
 
+// Mutual matching (the BFMatcher-crossCheck / NNMatcher case), D <= 256: one thread per query row for the index
+// work -- coalesced idx12, one gather from idx21, all rows of the block in flight at once -- then each warp computes
+// the exact distance of its mutual rows cooperatively, two rows per pass so that both rows' loads are issued
+// before either reduction.  The warp-per-row kernel above serialised three dependent round trips per row
+// (68 us for 131 k rows, 44 % of them mutual); arithmetic and results are identical (same per-lane order).
+template <int DPL>
+__global__ void __launch_bounds__(256)
+match_decide_mutual_kernel(const float *__restrict__ d1, const int32_t *__restrict__ n1, int N1,
+                           const float *__restrict__ d2, int N2, int P, int D, int metric, int cross_check,
+                           float threshold, const int32_t *__restrict__ idx12, const int32_t *__restrict__ idx21,
+                           int32_t *__restrict__ train_tmp, float *__restrict__ dist_tmp) {
+    const int lane = threadIdx.x & 31;
+    const long long total = (long long)P * N1;
+    const long long g = (long long)blockIdx.x * 256 + threadIdx.x;
+    const long long gw = g - lane;  // first row of this warp
+    int j = -1, p = 0;
+    if (g < total) {
+        p = (int)(g / N1);
+        const int i = (int)(g - (long long)p * N1);
+        const int n_a = n1 ? min(n1[p], N1) : N1;
+        if (i < n_a) {
+            j = idx12[g];
+            if (j >= 0 && cross_check && idx21[(size_t)p * N2 + j] != i) j = -1;
+        }
+    }
+    float dist = 0.f;
+    unsigned todo = __ballot_sync(0xffffffffu, j >= 0);
+    while (todo) {
+        const int l0 = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int l1 = todo ? __ffs(todo) - 1 : l0;  // a lone row is simply computed twice
+        todo &= todo - 1;
+        const int j0 = __shfl_sync(0xffffffffu, j, l0), j1 = __shfl_sync(0xffffffffu, j, l1);
+        const int p0 = __shfl_sync(0xffffffffu, p, l0), p1 = __shfl_sync(0xffffffffu, p, l1);
+        const float *a0 = d1 + (size_t)(gw + l0) * D, *b0 = d2 + ((size_t)p0 * N2 + j0) * D;
+        const float *a1 = d1 + (size_t)(gw + l1) * D, *b1 = d2 + ((size_t)p1 * N2 + j1) * D;
+        float va0[DPL], vb0[DPL], va1[DPL], vb1[DPL];
+#pragma unroll
+        for (int i = 0; i < DPL; ++i) {
+            const int c = lane + 32 * i;
+            const bool in = c < D;
+            va0[i] = in ? __ldg(a0 + c) : 0.f; vb0[i] = in ? __ldg(b0 + c) : 0.f;
+            va1[i] = in ? __ldg(a1 + c) : 0.f; vb1[i] = in ? __ldg(b1 + c) : 0.f;
+        }
+        double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll
+        for (int i = 0; i < DPL; ++i) {
+            if (lane + 32 * i < D) {  // same terms, same order as pair_distance
+                if (metric == MP_METRIC_NN) {
+                    acc0 += (double)va0[i] * (double)vb0[i];
+                    acc1 += (double)va1[i] * (double)vb1[i];
+                } else {
+                    const double f0 = (double)va0[i] - (double)vb0[i], f1 = (double)va1[i] - (double)vb1[i];
+                    acc0 += f0 * f0;
+                    acc1 += f1 * f1;
+                }
+            }
+        }
+#pragma unroll
+        for (int sft = 16; sft > 0; sft >>= 1) {
+            acc0 += __shfl_xor_sync(0xffffffffu, acc0, sft);
+            acc1 += __shfl_xor_sync(0xffffffffu, acc1, sft);
+        }
+        float r0, r1;
+        if (metric == MP_METRIC_NN) {
+            r0 = sqrtf(2.f - 2.f * fminf(1.f, fmaxf(-1.f, (float)acc0)));  // matching.py:51
+            r1 = sqrtf(2.f - 2.f * fminf(1.f, fmaxf(-1.f, (float)acc1)));
+        } else {
+            r0 = sqrtf((float)acc0);
+            r1 = sqrtf((float)acc1);
+        }
+        if (lane == l0) dist = r0;
+        if (lane == l1) dist = r1;
+    }
+    if (j >= 0 && threshold >= 0.f && !(dist < threshold)) j = -1;
+    if (g < total) {
+        train_tmp[g] = j;
+        dist_tmp[g] = dist;
+    }
+}
+
 // one CTA per pair: ordered compaction (ascending query index)
 __global__ void __launch_bounds__(1024)
 match_compact_kernel(const int32_t *__restrict__ train_tmp, const float *__restrict__ dist_tmp, int N1,
@@ -698,7 +806,9 @@ MatchLayout::MatchLayout(int P, int N1, int N2, int D) {
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
     const size_t r1 = (size_t)P * N1, r2 = (size_t)P * N2;
-    scalars = take(sizeof(unsigned) * (6 * (size_t)P + 4));
+    scalars = take(sizeof(unsigned) * (6 * (size_t)P + 4 + 2 * (size_t)P * RK_ROW_MAX));  // ... + row_done[2P][RK_ROW_MAX]
+    row_part_key = take(sizeof(double) * 2 * (size_t)P * RK_ROW_MAX * RK_SPLIT);
+    row_part_idx = take(sizeof(int) * 2 * (size_t)P * RK_ROW_MAX * RK_SPLIT);
     norms1 = take(sizeof(float) * r1);
     norms2 = take(sizeof(float) * r2);
     top12 = take(sizeof(Top2) * r1);
@@ -734,7 +844,7 @@ static int run_nearest(const float *d1, const int32_t *n1, int N1, const float *
     __nv_bfloat16 *hi2 = tensor ? (__nv_bfloat16 *)(ws + L.hi2) : nullptr, *mid2 = (__nv_bfloat16 *)(ws + L.mid2);
     const int use_bias = metric == MP_METRIC_L2;
 
-    MP_CUDA_OK(cudaMemsetAsync(scal, 0, sizeof(unsigned) * (6 * (size_t)P + 4), s));
+    MP_CUDA_OK(cudaMemsetAsync(scal, 0, sizeof(unsigned) * (6 * (size_t)P + 4 + 2 * (size_t)P * RK_ROW_MAX), s));
     const long long r1 = (long long)P * N1, r2 = (long long)P * N2;
     auto prep = [&](const float *d, const int32_t *n, int N, long long rows, float *norms, unsigned *mx, __nv_bfloat16 *h,
                     __nv_bfloat16 *m) {
@@ -779,8 +889,10 @@ static int run_nearest(const float *d1, const int32_t *n1, int N1, const float *
         else MP_RECHECK(8);
 #undef MP_RECHECK
         MP_LAUNCH_OK_S("match_recheck_kernel", s);
-        dim3 grid_row(2 * P, RK_ROW_Y);
-#define MP_RECHECK_ROW(DPL) match_recheck_row_kernel<DPL><<<grid_row, 1024, 0, s>>>(d1, n1, N1, d2, n2, N2, D, metric, flagged1, flagged2, n_flagged, idx12, idx21)
+        dim3 grid_row(2 * P, RK_SPLIT);
+        double *part_key = (double *)(ws + L.row_part_key);
+        int *part_idx = (int *)(ws + L.row_part_idx), *row_done = (int *)(scal + 6 * (size_t)P + 4);
+#define MP_RECHECK_ROW(DPL) match_recheck_row_kernel<DPL><<<grid_row, 256, 0, s>>>(d1, n1, N1, d2, n2, N2, D, metric, flagged1, flagged2, n_flagged, part_key, part_idx, row_done, idx12, idx21)
         if (D <= 64) MP_RECHECK_ROW(2);
         else if (D <= 128) MP_RECHECK_ROW(4);
         else MP_RECHECK_ROW(8);
@@ -884,10 +996,21 @@ extern "C" int mp_match_f32(const float *d1, const int32_t *n1, int N1, const fl
     const long long r1 = (long long)P * N1;
     int32_t *train_tmp = (int32_t *)(ws + L.train_tmp);
     float *dist_tmp = (float *)(ws + L.dist_tmp);
-    match_decide_kernel<<<(unsigned)((r1 + 7) / 8), 256, 0, s>>>(d1, n1, N1, d2, N2, P, D, metric, kind, cross_check,
-                                                               (float)threshold, (float)ratio, (int32_t *)(ws + L.idx12),
-                                                               (int32_t *)(ws + L.idx21), (Top2 *)(ws + L.top12), train_tmp, dist_tmp);
-    MP_LAUNCH_OK_S("match_decide_kernel", s);
+    if (kind == MP_MATCH_MUTUAL && D <= 256) {
+        const unsigned grid = (unsigned)((r1 + 255) / 256);
+#define MP_DECIDE(DPL) match_decide_mutual_kernel<DPL><<<grid, 256, 0, s>>>(d1, n1, N1, d2, N2, P, D, metric, cross_check, (float)threshold, \
+                                                                          (int32_t *)(ws + L.idx12), (int32_t *)(ws + L.idx21), train_tmp, dist_tmp)
+        if (D <= 64) MP_DECIDE(2);
+        else if (D <= 128) MP_DECIDE(4);
+        else MP_DECIDE(8);
+#undef MP_DECIDE
+        MP_LAUNCH_OK_S("match_decide_mutual_kernel", s);
+    } else {
+        match_decide_kernel<<<(unsigned)((r1 + 7) / 8), 256, 0, s>>>(d1, n1, N1, d2, N2, P, D, metric, kind, cross_check,
+                                                                   (float)threshold, (float)ratio, (int32_t *)(ws + L.idx12),
+                                                                   (int32_t *)(ws + L.idx21), (Top2 *)(ws + L.top12), train_tmp, dist_tmp);
+        MP_LAUNCH_OK_S("match_decide_kernel", s);
+    }
     match_compact_kernel<<<P, 1024, 0, s>>>(train_tmp, dist_tmp, N1, query, train, dist, counts);
     MP_LAUNCH_OK_S("match_compact_kernel", s);
     return MP_OK;

@@ -45,7 +45,7 @@ constexpr float MATCH_PACK_REL = 3.8147e-6f;  // 2^-18
 constexpr float MATCH_EPS_SIMT = 4e-5f;
 
 struct MatchLayout {
-    size_t scalars, norms1, norms2, top12, top21, idx12, idx21, flagged1, flagged2, pairs1, pairs2, train_tmp, dist_tmp, hi1, mid1, hi2, mid2, total;
+    size_t scalars, row_part_key, row_part_idx, norms1, norms2, top12, top21, idx12, idx21, flagged1, flagged2, pairs1, pairs2, train_tmp, dist_tmp, hi1, mid1, hi2, mid2, total;
     MatchLayout(int P, int N1, int N2, int D);
 };
 

@@ -283,15 +283,25 @@ match_top2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
             const bool live = m0 + row < NA;
             const uint4 *src = reinterpret_cast<const uint4 *>(plane + ((size_t)p * NA + (live ? m0 + row : 0)) * (64 * KB));
             const uint32_t col = L::A_COL0 + (uint32_t)(half * 32 * KB);
+            // two k-blocks (16 independent 16 B loads) per round trip: the staging is pure load latency and sits
+            // in front of the first MMA of the CTA
 #pragma unroll
-            for (int kb = 0; kb < KB; ++kb) {
-                uint32_t r[32];
+            for (int kb = 0; kb < KB; kb += 2) {
+                uint32_t r0[32], r1[32];
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
                     const uint4 w = live ? __ldg(src + kb * 8 + q) : make_uint4(0u, 0u, 0u, 0u);
-                    r[4 * q + 0] = w.x; r[4 * q + 1] = w.y; r[4 * q + 2] = w.z; r[4 * q + 3] = w.w;
+                    r0[4 * q + 0] = w.x; r0[4 * q + 1] = w.y; r0[4 * q + 2] = w.z; r0[4 * q + 3] = w.w;
                 }
-                tc_st32(tmem_base + ((uint32_t)(quarter * 32) << 16) + col + (uint32_t)(kb * 32), r);
+                if (kb + 1 < KB) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const uint4 w = live ? __ldg(src + (kb + 1) * 8 + q) : make_uint4(0u, 0u, 0u, 0u);
+                        r1[4 * q + 0] = w.x; r1[4 * q + 1] = w.y; r1[4 * q + 2] = w.z; r1[4 * q + 3] = w.w;
+                    }
+                }
+                tc_st32(tmem_base + ((uint32_t)(quarter * 32) << 16) + col + (uint32_t)(kb * 32), r0);
+                if (kb + 1 < KB) tc_st32(tmem_base + ((uint32_t)(quarter * 32) << 16) + col + (uint32_t)((kb + 1) * 32), r1);
             }
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             tc_fence_before();

@@ -16,7 +16,7 @@ timeout -k 10 600 ncu --metrics gpu__time_duration.sum --clock-control none --cs
 # full capture of one warm hot-path step (every kernel of this library)
 timeout -k 10 900 ncu --set full --clock-control none --import-source on \
     -k regex:"nms_|detector_head_kernel|normalize_desc|sample_descriptors|match_" \
-    -s 48 -c 20 -o gpurun_out/prof_hot python bench.py --only-hot --steps 1 --warmup 3 > gpurun_out/ncu_full.log 2>&1
+    -s 57 -c 19 -o gpurun_out/prof_hot python bench.py --only-hot --steps 1 --warmup 3 > gpurun_out/ncu_full.log 2>&1
 # dram traffic of the captured kernels
 python -c "
 import json; d=json.load(open('gpurun_out/bench_n1.json')); print({k:d[k] for k in ('value','ms_per_step')}, d['e2e']['value'], d['hot_path']['ms_per_step']); print(json.dumps(d['roofline']))
