@@ -60,6 +60,18 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map
         ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
+// one lane of a converged warp (cute::elect_one_sync): ptxas then knows a single thread is active and moves the
+// tcgen05 / TMA operands to uniform registers without the per-instruction waterfall it emits under `lane == 0`
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -156,7 +168,9 @@ match_top2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
                      const __nv_bfloat16 *__restrict__ a_hi_ptr, const __nv_bfloat16 *__restrict__ a_mid_ptr,
                      const int32_t *__restrict__ na, int NA, const int32_t *__restrict__ nb, int NB,
                      const float *__restrict__ norms_b, int use_bias, const unsigned *__restrict__ max_a,
-                     const unsigned *__restrict__ max_b, Top2 *__restrict__ top) {
+                     const unsigned *__restrict__ max_b, Top2 *__restrict__ top, int exp_flags) {
+    // exp_flags (MP_TC_EXP, timing experiments only -- results are wrong with any bit set):
+    //   1 skip the epilogue arithmetic, 2 load B only for the first tile, 4 skip the A staging loads, 8 issue no MMAs
     using L = TcSmem<KB, ATM>;
     constexpr int S = L::B_STAGES;
     constexpr int ACC = L::ACC_STAGES;
@@ -203,7 +217,7 @@ match_top2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
 
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
+        if (elect_one()) {
             if (!ATM) {
                 mbar_expect_tx(bar_a_full, L::A_BYTES);
                 for (int kb = 0; kb < KB; ++kb) {
@@ -212,10 +226,22 @@ match_top2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
                 }
             }
             int it = 0;
+            if (ATM) {
+                // ring items 0..KB-1 are this CTA's own rows of A (hi + mid block per k-block, the same 32 KB stage
+                // layout as B): the epilogue warps move them from shared to tensor memory.  Pulling A in with
+                // per-thread global loads took 6 us per CTA (43 us per launch) in front of the first MMA.
+                for (int kb = 0; kb < KB; ++kb, ++it) {
+                    mbar_expect_tx(bar_b_full(kb), L::B_STAGE_BYTES);
+                    const uint32_t dst = smem_b + kb * L::B_STAGE_BYTES;
+                    tma_load_3d(dst, &map_a_hi, bar_b_full(kb), kb * TC_BK, m0, p);
+                    tma_load_3d(dst + TC_TILE_BYTES, &map_a_mid, bar_b_full(kb), kb * TC_BK, m0, p);
+                }
+            }
             for (int nt = 0; nt < n_tiles; ++nt) {
                 for (int kb = 0; kb < KB; ++kb, ++it) {
                     const int s = it % S;
                     mbar_wait(bar_b_empty(s), ((it / S) & 1) ^ 1);
+                    if ((exp_flags & 2) && nt > 0) { mbar_arrive(bar_b_full(s)); continue; }
                     mbar_expect_tx(bar_b_full(s), L::B_STAGE_BYTES);
                     const uint32_t dst = smem_b + s * L::B_STAGE_BYTES;
                     tma_load_3d(dst, &map_b_hi, bar_b_full(s), kb * TC_BK, nt * TC_BN, p);
@@ -225,11 +251,14 @@ match_top2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        if (elect_one()) {
             constexpr uint32_t idesc = umma_idesc_bf16(TC_BM, TC_BN);
             mbar_wait(bar_a_full, 0);
             tc_fence_after();
             int it = 0;
+            if (ATM) {  // A has left the ring stages it arrived in: hand them back to the producer
+                for (int kb = 0; kb < KB; ++kb, ++it) mbar_arrive(bar_b_empty(kb));
+            }
             for (int nt = 0; nt < n_tiles; ++nt) {
                 const int t = nt % ACC;
                 mbar_wait(bar_acc_empty(t), ((nt / ACC) & 1) ^ 1);
@@ -242,6 +271,7 @@ match_top2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
                     const uint32_t b_hi = smem_b + s * L::B_STAGE_BYTES, b_mid = b_hi + TC_TILE_BYTES;
 #pragma unroll
                     for (int k = 0; k < TC_BK / 16; ++k) {
+                        if (exp_flags & 8) break;
                         const uint32_t ko = k * 32;  // 16 bf16 = 32 B inside the 128 B swizzle row
                         const uint64_t db_hi = umma_desc_sw128(b_hi + ko), db_mid = umma_desc_sw128(b_mid + ko);
                         if (ATM) {
@@ -279,29 +309,20 @@ match_top2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
         if (ATM) {
             // stage this CTA's rows of A into tensor memory: warps with half 0 write the hi plane,
             // half 1 the mid plane; each thread owns one row (= one TMEM lane)
-            const __nv_bfloat16 *plane = half == 0 ? a_hi_ptr : a_mid_ptr;
-            const bool live = m0 + row < NA;
-            const uint4 *src = reinterpret_cast<const uint4 *>(plane + ((size_t)p * NA + (live ? m0 + row : 0)) * (64 * KB));
             const uint32_t col = L::A_COL0 + (uint32_t)(half * 32 * KB);
-            // two k-blocks (16 independent 16 B loads) per round trip: the staging is pure load latency and sits
-            // in front of the first MMA of the CTA
 #pragma unroll
-            for (int kb = 0; kb < KB; kb += 2) {
-                uint32_t r0[32], r1[32];
+            for (int kb = 0; kb < KB; ++kb) {
+                mbar_wait(bar_b_full(kb), 0);
+                // this thread's row of the (128 x 64) bf16 block: eight 16 B chunks, chunk c at (c ^ (row & 7)) (128 B swizzle)
+                const uint32_t src = smem_b + kb * L::B_STAGE_BYTES + (uint32_t)half * TC_TILE_BYTES + (uint32_t)row * 128u;
+                uint32_t r[32];
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
-                    const uint4 w = live ? __ldg(src + kb * 8 + q) : make_uint4(0u, 0u, 0u, 0u);
-                    r0[4 * q + 0] = w.x; r0[4 * q + 1] = w.y; r0[4 * q + 2] = w.z; r0[4 * q + 3] = w.w;
+                    const uint32_t addr = src + (uint32_t)((q ^ (row & 7)) << 4);
+                    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                                 : "=r"(r[4 * q + 0]), "=r"(r[4 * q + 1]), "=r"(r[4 * q + 2]), "=r"(r[4 * q + 3]) : "r"(addr));
                 }
-                if (kb + 1 < KB) {
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const uint4 w = live ? __ldg(src + (kb + 1) * 8 + q) : make_uint4(0u, 0u, 0u, 0u);
-                        r1[4 * q + 0] = w.x; r1[4 * q + 1] = w.y; r1[4 * q + 2] = w.z; r1[4 * q + 3] = w.w;
-                    }
-                }
-                tc_st32(tmem_base + ((uint32_t)(quarter * 32) << 16) + col + (uint32_t)(kb * 32), r0);
-                if (kb + 1 < KB) tc_st32(tmem_base + ((uint32_t)(quarter * 32) << 16) + col + (uint32_t)((kb + 1) * 32), r1);
+                tc_st32(tmem_base + ((uint32_t)(quarter * 32) << 16) + col + (uint32_t)(kb * 32), r);
             }
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             tc_fence_before();
@@ -370,6 +391,7 @@ match_top2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
                 if (best != old_best) best_chunk = chunk;
                 if (second != old_second) second_chunk = (second == old_best && best != old_best) ? old_best_chunk : chunk;
             };
+            if (exp_flags & 1) continue;
             if (have0) process(va, n0 + c0 * 32, add_lane0);
             if (have1) process(vb, n0 + c1 * 32, add_lane1);
         }
@@ -463,8 +485,9 @@ static int launch_tc(const CUtensorMap &ah, const CUtensorMap &am, const CUtenso
     auto k = match_top2_tc_kernel<KB, ATM>;
     MP_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcSmem<KB, ATM>::TOTAL));
     dim3 grid((NA + TC_BM - 1) / TC_BM, P);
+    static const int exp_flags = getenv("MP_TC_EXP") ? atoi(getenv("MP_TC_EXP")) : 0;  // timing experiments (wrong results)
     k<<<grid, TC_THREADS, TcSmem<KB, ATM>::TOTAL, s>>>(ah, am, bh, bm, a_hi, a_mid, na, NA, nb, NB, norms_b, use_bias,
-                                                        max_a, max_b, top);
+                                                        max_a, max_b, top, exp_flags);
     MP_LAUNCH_OK_S("match_top2_tc_kernel", s);
     return MP_OK;
 }
