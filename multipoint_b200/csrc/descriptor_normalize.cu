@@ -15,7 +15,7 @@ namespace mp {
 constexpr int DN_WARPS = 8;
 
 template <int CPT>  // channels per thread; D <= CPT * DN_WARPS
-__global__ void __launch_bounds__(DN_WARPS * 32)
+__global__ void __launch_bounds__(DN_WARPS * 32, 4)  // <= 64 registers: 4 CTAs/SM (ncu: 80 registers held it at 3, 36 % of the warp slots)
 normalize_desc_kernel(const float *__restrict__ x, float *__restrict__ out_nchw,
                       float *__restrict__ out_nhwc, int D, int HW, int tiles_per_image) {
     extern __shared__ float smem[];  // [DN_WARPS][32] partials, then optional [32][D+1] tile
@@ -103,10 +103,16 @@ extern "C" int mp_normalize_descriptors_f32(const float *x, int B, int D, int HW
     const size_t smem = (mp::DN_WARPS * 32 + (out_nhwc ? 32 * (D + 1) : 0)) * sizeof(float);
     const unsigned grid = (unsigned)(B * tiles);
     if (D <= 64) {
+        // shared memory is the other occupancy limit (35 KB per CTA with the channels-last tile): full carve-out
+        cudaFuncSetAttribute(mp::normalize_desc_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         mp::normalize_desc_kernel<8><<<grid, mp::DN_WARPS * 32, smem, s>>>(x, out_nchw, out_nhwc, D, HW, tiles);
     } else if (D <= 128) {
+        // shared memory is the other occupancy limit (35 KB per CTA with the channels-last tile): full carve-out
+        cudaFuncSetAttribute(mp::normalize_desc_kernel<16>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         mp::normalize_desc_kernel<16><<<grid, mp::DN_WARPS * 32, smem, s>>>(x, out_nchw, out_nhwc, D, HW, tiles);
     } else if (D <= 256) {
+        // shared memory is the other occupancy limit (35 KB per CTA with the channels-last tile): full carve-out
+        cudaFuncSetAttribute(mp::normalize_desc_kernel<32>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         mp::normalize_desc_kernel<32><<<grid, mp::DN_WARPS * 32, smem, s>>>(x, out_nchw, out_nhwc, D, HW, tiles);
     } else {
         const long long total = (long long)B * HW;
