@@ -439,301 +439,6 @@ match_top2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
     }
 }
 
-// ---------------------------------------------------------------- persistent variant
-// The kernel above pays ~5.5 us per CTA outside its MMA stream (TMEM allocation, barrier set-up, A staging in
-// front of the first MMA; last tile's epilogue, merge, result write and teardown behind the last one): 38 of
-// 273 us per launch at 7 CTAs per SM.  Here one CTA per SM walks the work items (128 rows of A of one pair)
-// itself.  All pipelines run across item boundaries: the producer queues the next item's A blocks and first B
-// blocks behind the current item's last B blocks, the epilogue warps move the next A into tensor memory the
-// moment the current item's last MMA has completed -- before they read that tile's accumulator -- and do the
-// last tile's arithmetic, the merge and the result write while the next item's MMAs run.
-template <int KB>
-struct TcPersistSmem {
-    static constexpr int B_STAGES = 6;
-    static constexpr int ACC_STAGES = (512 - 64 * KB) / TC_BN;
-    static constexpr uint32_t A_COL0 = 512 - 64 * KB;
-    static constexpr uint32_t B_STAGE_BYTES = 2u * TC_TILE_BYTES;
-    static constexpr uint32_t BAR_OFF = B_STAGES * B_STAGE_BYTES;
-    static constexpr int NUM_BARS = 1 + 2 * B_STAGES + 2 * ACC_STAGES;
-    static constexpr uint32_t MRG_OFF = BAR_OFF + NUM_BARS * 8 + 16;        // + tmem pointer
-    static constexpr uint32_t TOTAL = MRG_OFF + TC_BM * 5 * 4 + 1024;       // merge scratch + alignment slack
-};
-
-template <int KB>
-__global__ void __launch_bounds__(TC_THREADS, 1)
-match_top2_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_mid,
-                             const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_mid,
-                             const int32_t *__restrict__ na, int NA, const int32_t *__restrict__ nb, int NB, int P,
-                             const float *__restrict__ norms_b, int use_bias, const unsigned *__restrict__ max_a,
-                             const unsigned *__restrict__ max_b, Top2 *__restrict__ top) {
-    using L = TcPersistSmem<KB>;
-    constexpr int S = L::B_STAGES;
-    constexpr int ACC = L::ACC_STAGES;
-    extern __shared__ uint8_t smem_raw[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t smem_b = base, bars = base + L::BAR_OFF;
-    const uint32_t bar_a_full = bars;
-    auto bar_b_full = [&](int s) { return bars + 8u * (1 + s); };
-    auto bar_b_empty = [&](int s) { return bars + 8u * (1 + S + s); };
-    auto bar_acc_full = [&](int t) { return bars + 8u * (1 + 2 * S + t); };
-    auto bar_acc_empty = [&](int t) { return bars + 8u * (1 + 2 * S + ACC + t); };
-    const uint32_t tmem_ptr_addr = bars + 8u * L::NUM_BARS;
-    volatile uint32_t *tmem_ptr_gen = reinterpret_cast<volatile uint32_t *>(smem_raw + (tmem_ptr_addr - smem_u32(smem_raw)));
-    uint32_t *mrg = reinterpret_cast<uint32_t *>(smem_raw + (base + L::MRG_OFF - smem_u32(smem_raw)));
-
-    const int tiles_m = (NA + TC_BM - 1) / TC_BM;
-    const int n_items = tiles_m * P;
-    // item w: pair w / tiles_m, rows [m0, m0 + 128).  An item with no rows or nothing to search has no pipeline
-    // work; every role skips it the same way (the epilogue warps write its empty results).
-    auto item_rows = [&](int w, int &p, int &m0, int &n_a, int &n_b) {
-        p = w / tiles_m;
-        m0 = (w - p * tiles_m) * TC_BM;
-        n_a = na ? min(na[p], NA) : NA;
-        n_b = nb ? min(nb[p], NB) : NB;
-        return m0 < n_a && n_b > 0;
-    };
-    auto next_work = [&](int w) {  // first item >= w (stepping by the grid) that has work, or n_items
-        int p, m0, n_a, n_b;
-        while (w < n_items && !item_rows(w, p, m0, n_a, n_b)) w += gridDim.x;
-        return w;
-    };
-
-    if (warp == 0 && lane == 0) {
-        mbar_init(bar_a_full, TC_EPI_WARPS);
-        for (int s = 0; s < S; ++s) { mbar_init(bar_b_full(s), 1); mbar_init(bar_b_empty(s), 1); }
-        for (int t = 0; t < ACC; ++t) { mbar_init(bar_acc_full(t), 1); mbar_init(bar_acc_empty(t), TC_EPI_WARPS); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    }
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "r"(512));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_ptr_gen;
-
-    if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (elect_one()) {
-            int it = 0;
-            for (int w = next_work(blockIdx.x); w < n_items; w = next_work(w + gridDim.x)) {
-                int p, m0, n_a, n_b;
-                item_rows(w, p, m0, n_a, n_b);
-                const int n_tiles = (n_b + TC_BN - 1) / TC_BN;
-                for (int kb = 0; kb < KB; ++kb, ++it) {  // this item's rows of A: KB ring items
-                    const int s = it % S;
-                    mbar_wait(bar_b_empty(s), ((it / S) & 1) ^ 1);
-                    mbar_expect_tx(bar_b_full(s), L::B_STAGE_BYTES);
-                    const uint32_t dst = smem_b + s * L::B_STAGE_BYTES;
-                    tma_load_3d(dst, &map_a_hi, bar_b_full(s), kb * TC_BK, m0, p);
-                    tma_load_3d(dst + TC_TILE_BYTES, &map_a_mid, bar_b_full(s), kb * TC_BK, m0, p);
-                }
-                for (int nt = 0; nt < n_tiles; ++nt)
-                    for (int kb = 0; kb < KB; ++kb, ++it) {
-                        const int s = it % S;
-                        mbar_wait(bar_b_empty(s), ((it / S) & 1) ^ 1);
-                        mbar_expect_tx(bar_b_full(s), L::B_STAGE_BYTES);
-                        const uint32_t dst = smem_b + s * L::B_STAGE_BYTES;
-                        tma_load_3d(dst, &map_b_hi, bar_b_full(s), kb * TC_BK, nt * TC_BN, p);
-                        tma_load_3d(dst + TC_TILE_BYTES, &map_b_mid, bar_b_full(s), kb * TC_BK, nt * TC_BN, p);
-                    }
-            }
-        }
-    } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (elect_one()) {
-            constexpr uint32_t idesc = umma_idesc_bf16(TC_BM, TC_BN);
-            int it = 0, tile = 0, item = 0;
-            for (int w = next_work(blockIdx.x); w < n_items; w = next_work(w + gridDim.x), ++item) {
-                int p, m0, n_a, n_b;
-                item_rows(w, p, m0, n_a, n_b);
-                const int n_tiles = (n_b + TC_BN - 1) / TC_BN;
-                mbar_wait(bar_a_full, item & 1);  // this item's A is in tensor memory
-                tc_fence_after();
-                for (int kb = 0; kb < KB; ++kb, ++it) mbar_arrive(bar_b_empty(it % S));  // its ring slots go back
-                for (int nt = 0; nt < n_tiles; ++nt, ++tile) {
-                    const int t = tile % ACC;
-                    mbar_wait(bar_acc_empty(t), ((tile / ACC) & 1) ^ 1);
-                    tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + (uint32_t)(t * TC_BN);
-                    for (int kb = 0; kb < KB; ++kb, ++it) {
-                        const int s = it % S;
-                        mbar_wait(bar_b_full(s), (it / S) & 1);
-                        tc_fence_after();
-                        const uint32_t b_hi = smem_b + s * L::B_STAGE_BYTES, b_mid = b_hi + TC_TILE_BYTES;
-#pragma unroll
-                        for (int k = 0; k < TC_BK / 16; ++k) {
-                            const uint32_t ko = k * 32;
-                            const uint64_t db_hi = umma_desc_sw128(b_hi + ko), db_mid = umma_desc_sw128(b_mid + ko);
-                            const uint32_t ta_hi = tmem_base + L::A_COL0 + (uint32_t)(kb * 32 + k * 8);
-                            const uint32_t ta_mid = ta_hi + 32u * KB;
-                            tc_mma_f16_ts(d_tmem, ta_mid, db_hi, idesc, (kb | k) != 0);  // small terms first
-                            tc_mma_f16_ts(d_tmem, ta_hi, db_mid, idesc, 1);
-                            tc_mma_f16_ts(d_tmem, ta_hi, db_hi, idesc, 1);
-                        }
-                        tc_commit(bar_b_empty(s));
-                    }
-                    tc_commit(bar_acc_full(t));
-                }
-            }
-        }
-    } else {
-        // ===================== epilogue warps =====================
-        const int quarter = warp & 3;
-        const int half = (warp - 2) >> 2;
-        const int row = quarter * 32 + lane;
-        int it = 0, tile = 0;
-        // move one item's A blocks (ring items it .. it+KB-1) from shared to tensor memory
-        auto stage_a = [&](int it0) {
-            const uint32_t col = L::A_COL0 + (uint32_t)(half * 32 * KB);
-#pragma unroll
-            for (int kb = 0; kb < KB; ++kb) {
-                const int s = (it0 + kb) % S;
-                mbar_wait(bar_b_full(s), ((it0 + kb) / S) & 1);
-                const uint32_t src = smem_b + s * L::B_STAGE_BYTES + (uint32_t)half * TC_TILE_BYTES + (uint32_t)row * 128u;
-                uint32_t r[32];
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const uint32_t addr = src + (uint32_t)((q ^ (row & 7)) << 4);
-                    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
-                                 : "=r"(r[4 * q + 0]), "=r"(r[4 * q + 1]), "=r"(r[4 * q + 2]), "=r"(r[4 * q + 3]) : "r"(addr));
-                }
-                tc_st32(tmem_base + ((uint32_t)(quarter * 32) << 16) + col + (uint32_t)(kb * 32), r);
-            }
-            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_a_full);
-        };
-        // items without work between two work items: empty results
-        auto write_empty = [&](int w_from, int w_to) {
-            for (int w = w_from; w < w_to && w < n_items; w += gridDim.x) {
-                int p, m0, n_a, n_b;
-                if (item_rows(w, p, m0, n_a, n_b)) continue;
-                if (half == 0 && m0 + row < NA) top[(size_t)p * NA + m0 + row] = top2_empty();
-            }
-        };
-        int w = next_work(blockIdx.x);
-        write_empty(blockIdx.x, w);
-        if (w < n_items) stage_a(it);
-        while (w < n_items) {
-            int p, m0, n_a, n_b;
-            item_rows(w, p, m0, n_a, n_b);
-            const int n_tiles = (n_b + TC_BN - 1) / TC_BN;
-            const int w_next = next_work(w + gridDim.x);
-            it += KB;                        // this item's A blocks
-            const int it_next_a = it + n_tiles * KB;  // ring index of the next item's first A block
-            const float ma = __uint_as_float(max_a[p]), mb = __uint_as_float(max_b[p]);
-            const float C = 1.002f * ma * mb + (use_bias ? 0.5f * mb * mb : 0.f) + 1e-30f;
-            const float *bias = norms_b + (size_t)p * NB;
-            uint32_t best = 0, second = 0, third = 0;
-            int best_chunk = -1, second_chunk = -1;
-            for (int nt = 0; nt < n_tiles; ++nt, ++tile) {
-                const int t = tile % ACC;
-                const int n0 = nt * TC_BN;
-                float add_lane0 = C, add_lane1 = C;
-                if (use_bias) {
-                    const int ca = n0 + half * 32 + lane, cb_ = ca + 64;
-                    if (ca < n_b) add_lane0 = fmaf(-0.5f, __ldg(bias + ca), C);
-                    if (cb_ < n_b) add_lane1 = fmaf(-0.5f, __ldg(bias + cb_), C);
-                }
-                mbar_wait(bar_acc_full(t), (tile / ACC) & 1);
-                tc_fence_after();
-                // the item's last MMA has completed: the A region of tensor memory is free, so the next item's A
-                // goes in first and its MMAs start while this tile is still being read and ranked
-                if (nt == n_tiles - 1 && w_next < n_items) stage_a(it_next_a);
-                uint32_t va[32], vb[32];
-                const int c0 = half, c1 = half + 2;
-                const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(t * TC_BN);
-                const bool have0 = n0 + c0 * 32 < n_b, have1 = n0 + c1 * 32 < n_b;
-                if (have0) tc_ld32(tbase + (uint32_t)(c0 * 32), va);
-                if (have1) tc_ld32(tbase + (uint32_t)(c1 * 32), vb);
-                tc_ld_wait();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar_acc_empty(t));
-
-                auto process = [&](const uint32_t (&v)[32], int col0, float add_lane) {
-                    const bool full = col0 + 32 <= n_b;
-                    uint32_t b4[4] = {0, 0, 0, 0}, s4[4] = {0, 0, 0, 0}, t4[4] = {0, 0, 0, 0};
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float add = use_bias ? __shfl_sync(0xffffffffu, add_lane, j) : C;
-                        uint32_t x = (__float_as_uint(__uint_as_float(v[j]) + add) & ~31u) | (uint32_t)(31 - j);
-                        if (!full && col0 + j >= n_b) x = 0;
-                        t4[j & 3] = max(t4[j & 3], min(x, s4[j & 3]));
-                        s4[j & 3] = max(s4[j & 3], min(x, b4[j & 3]));
-                        b4[j & 3] = max(b4[j & 3], x);
-                    }
-                    auto merge3 = [](uint32_t &b, uint32_t &s_, uint32_t &t_, uint32_t b2, uint32_t s2, uint32_t t2) {
-                        const uint32_t nt_ = max(max(t_, t2), max(min(s_, b2), min(b, s2)));
-                        const uint32_t ns = max(max(s_, s2), min(b, b2));
-                        b = max(b, b2); s_ = ns; t_ = nt_;
-                    };
-                    merge3(b4[0], s4[0], t4[0], b4[1], s4[1], t4[1]);
-                    merge3(b4[2], s4[2], t4[2], b4[3], s4[3], t4[3]);
-                    merge3(b4[0], s4[0], t4[0], b4[2], s4[2], t4[2]);
-                    const uint32_t cb = b4[0], cs = s4[0];
-                    const int chunk = col0 >> 5;
-                    const uint32_t old_best = best, old_second = second;
-                    const int old_best_chunk = best_chunk;
-                    merge3(best, second, third, cb, cs, t4[0]);
-                    if (best != old_best) best_chunk = chunk;
-                    if (second != old_second) second_chunk = (second == old_best && best != old_best) ? old_best_chunk : chunk;
-                };
-                if (have0) process(va, n0 + c0 * 32, add_lane0);
-                if (have1) process(vb, n0 + c1 * 32, add_lane1);
-            }
-            it = it_next_a;
-            // merge the two column subsets of each row through the dedicated scratch
-            if (half == 1) {
-                mrg[row * 4 + 0] = best; mrg[row * 4 + 1] = second;
-                mrg[row * 4 + 2] = (uint32_t)best_chunk; mrg[row * 4 + 3] = (uint32_t)second_chunk;
-                mrg[512 + row] = third;
-            }
-            asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_WARPS * 32) : "memory");
-            if (half == 0) {
-                const uint32_t ob = mrg[row * 4 + 0], os = mrg[row * 4 + 1];
-                const int obc = (int)mrg[row * 4 + 2], osc = (int)mrg[row * 4 + 3];
-                uint32_t nb_, ns_; int nbc, nsc;
-                if (ob > best) { nb_ = ob; nbc = obc; if (best >= os) { ns_ = best; nsc = best_chunk; } else { ns_ = os; nsc = osc; } }
-                else { nb_ = best; nbc = best_chunk; if (ob >= second) { ns_ = ob; nsc = obc; } else { ns_ = second; nsc = second_chunk; } }
-                const uint32_t ot = mrg[512 + row];
-                third = max(max(third, ot), max(min(second, ob), min(best, os)));
-                best = nb_; best_chunk = nbc; second = ns_; second_chunk = nsc;
-                if (m0 + row < NA) {
-                    Top2 out = top2_empty();
-                    if (m0 + row < n_a) {
-                        if (best_chunk >= 0) {
-                            out.best_idx = best_chunk * 32 + 31 - (int)(best & 31u);
-                            out.best = __uint_as_float(best & ~31u) - C;
-                        }
-                        if (second_chunk >= 0) {
-                            out.second_idx = second_chunk * 32 + 31 - (int)(second & 31u);
-                            out.second = __uint_as_float(second & ~31u) - C;
-                        }
-                        if (third != 0) out.third = __uint_as_float(third & ~31u) - C;
-                    }
-                    top[(size_t)p * NA + m0 + row] = out;
-                }
-            }
-            asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_WARPS * 32) : "memory");  // scratch is free again
-            write_empty(w + gridDim.x, w_next);
-            w = w_next;
-        }
-    }
-
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 1) {
-        tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
-    }
-}
-
 // ---------------------------------------------------------------- host side
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                     const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -802,30 +507,6 @@ int match_top2_tensor(const __nv_bfloat16 *a_hi, const __nv_bfloat16 *a_mid, con
     if ((rc = make_operand_map(&bh, b_hi, P, NB, D)) != MP_OK) return rc;
     if ((rc = make_operand_map(&bm, b_mid, P, NB, D)) != MP_OK) return rc;
     static const bool atm = !(getenv("MP_TC_A_SMEM") && atoi(getenv("MP_TC_A_SMEM")) == 1);  // tuning aid: 1 = A in smem
-    static const bool persist = !(getenv("MP_TC_PERSIST") && atoi(getenv("MP_TC_PERSIST")) == 0);  // tuning aid: 0 = one CTA per item
-    if (persist && atm) {
-        int dev = 0, sms = 148;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        const long long items = (long long)((NA + TC_BM - 1) / TC_BM) * P;
-        const unsigned grid = (unsigned)(items < sms ? items : sms);
-#define MP_TC_PERSIST_LAUNCH(KB)                                                                                        \
-    {                                                                                                                   \
-        auto k = match_top2_tc_persist_kernel<KB>;                                                                      \
-        MP_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcPersistSmem<KB>::TOTAL)); \
-        k<<<grid, TC_THREADS, TcPersistSmem<KB>::TOTAL, stream>>>(ah, am, bh, bm, na, NA, nb, NB, P, norms_b, use_bias,  \
-                                                                  max_a, max_b, top);                                   \
-        MP_LAUNCH_OK_S("match_top2_tc_kernel", stream);                                                                 \
-        return MP_OK;                                                                                                   \
-    }
-        switch (D / 64) {
-            case 1: MP_TC_PERSIST_LAUNCH(1);
-            case 2: MP_TC_PERSIST_LAUNCH(2);
-            case 3: MP_TC_PERSIST_LAUNCH(3);
-            default: MP_TC_PERSIST_LAUNCH(4);
-        }
-#undef MP_TC_PERSIST_LAUNCH
-    }
 #define MP_TC_LAUNCH(KB)                                                                                              \
     return atm ? launch_tc<KB, true>(ah, am, bh, bm, a_hi, a_mid, na, NA, nb, NB, P, norms_b, use_bias, max_a, max_b, top, stream) \
                : launch_tc<KB, false>(ah, am, bh, bm, a_hi, a_mid, na, NA, nb, NB, P, norms_b, use_bias, max_a, max_b, top, stream)
