@@ -364,14 +364,25 @@ match_top2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
                 const bool full = col0 + 32 <= n_b;
                 // sorted triples (b >= s >= t) in four independent accumulators for ILP
                 uint32_t b4[4] = {0, 0, 0, 0}, s4[4] = {0, 0, 0, 0}, t4[4] = {0, 0, 0, 0};
+                if (full) {  // warp-uniform: the per-element bound check only runs on a ragged last chunk
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const float add = use_bias ? __shfl_sync(0xffffffffu, add_lane, j) : C;
-                    uint32_t x = (__float_as_uint(__uint_as_float(v[j]) + add) & ~31u) | (uint32_t)(31 - j);
-                    if (!full && col0 + j >= n_b) x = 0;
-                    t4[j & 3] = max(t4[j & 3], min(x, s4[j & 3]));
-                    s4[j & 3] = max(s4[j & 3], min(x, b4[j & 3]));
-                    b4[j & 3] = max(b4[j & 3], x);
+                    for (int j = 0; j < 32; ++j) {
+                        const float add = use_bias ? __shfl_sync(0xffffffffu, add_lane, j) : C;
+                        const uint32_t x = (__float_as_uint(__uint_as_float(v[j]) + add) & ~31u) | (uint32_t)(31 - j);
+                        t4[j & 3] = max(t4[j & 3], min(x, s4[j & 3]));
+                        s4[j & 3] = max(s4[j & 3], min(x, b4[j & 3]));
+                        b4[j & 3] = max(b4[j & 3], x);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float add = use_bias ? __shfl_sync(0xffffffffu, add_lane, j) : C;
+                        uint32_t x = (__float_as_uint(__uint_as_float(v[j]) + add) & ~31u) | (uint32_t)(31 - j);
+                        if (col0 + j >= n_b) x = 0;
+                        t4[j & 3] = max(t4[j & 3], min(x, s4[j & 3]));
+                        s4[j & 3] = max(s4[j & 3], min(x, b4[j & 3]));
+                        b4[j & 3] = max(b4[j & 3], x);
+                    }
                 }
                 // k-th largest of two sorted triples: second = max(s, s', min(b, b')),
                 // third = max(t, t', min(s, b'), min(b, s'))
