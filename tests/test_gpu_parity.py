@@ -642,6 +642,33 @@ def test_pipeline_matches_stagewise_reference_chain(utils, oracle):
         np.testing.assert_allclose(m['distance'][p, :n].cpu().numpy(), wd, rtol=RTOL, atol=1e-6)
 
 
+def test_pipeline_stream_equals_call():
+    """KeypointPipeline.stream (pinned host batches, upload of batch i+1 overlapped with batch i) yields exactly
+    what KeypointPipeline.__call__ returns for each batch on its own."""
+    from multipoint_b200.models import MultiPoint
+    from multipoint_b200.pipeline import KeypointPipeline, calibrate_random_init
+    torch.manual_seed(3)
+    net = MultiPoint({'multispectral': True, 'descriptor_size': 64}).cuda().eval()
+    calibrate_random_init(net, torch.rand(4, 1, 64, 80, device="cuda"), is_optical=torch.tensor([[1], [1], [0], [0]], dtype=torch.bool, device="cuda"))
+    pipe = KeypointPipeline(net, nms=4, detection_threshold=0.015, topk=64)
+    batches = []
+    for seed in (11, 12, 13):
+        b = syn.image_pair_batch(seed, 2, 64, 80)
+        batches.append({s: {k: torch.from_numpy(v).pin_memory() for k, v in b[s].items() if k != 'valid_mask'} for s in ('optical', 'thermal')})
+    streamed = []
+    for r in pipe.stream(iter(batches), "cuda"):
+        streamed.append({'kp': r['optical']['keypoints'].cpu(), 'cnt': r['thermal']['counts'].cpu(), 'q': r['matches']['query'].cpu(),
+                         't': r['matches']['train'].cpu(), 'n': r['matches']['counts'].cpu()})
+    assert len(streamed) == 3
+    for b, got in zip(batches, streamed):
+        r = pipe({s: {k: v.cuda() for k, v in d.items()} for s, d in b.items()})
+        assert torch.equal(got['kp'], r['optical']['keypoints'].cpu()) and torch.equal(got['cnt'], r['thermal']['counts'].cpu())
+        assert torch.equal(got['n'], r['matches']['counts'].cpu())
+        for p in range(2):   # entries beyond the count are not defined
+            n = int(got['n'][p])
+            assert torch.equal(got['q'][p, :n], r['matches']['query'][p, :n].cpu()) and torch.equal(got['t'][p, :n], r['matches']['train'][p, :n].cpu())
+
+
 # ------------------------------------------------------------------ multi-GPU path, simulated in one process
 def test_sharded_adaptation_equals_fused(utils, ops):
     """Two ranks' partial accumulators summed (what the NCCL all-reduce does) then finished equal
