@@ -168,9 +168,7 @@ match_top2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
                      const __nv_bfloat16 *__restrict__ a_hi_ptr, const __nv_bfloat16 *__restrict__ a_mid_ptr,
                      const int32_t *__restrict__ na, int NA, const int32_t *__restrict__ nb, int NB,
                      const float *__restrict__ norms_b, int use_bias, const unsigned *__restrict__ max_a,
-                     const unsigned *__restrict__ max_b, Top2 *__restrict__ top, int exp_flags) {
-    // exp_flags (MP_TC_EXP, timing experiments only -- results are wrong with any bit set):
-    //   1 skip the epilogue arithmetic, 2 load B only for the first tile, 4 skip the A staging loads, 8 issue no MMAs
+                     const unsigned *__restrict__ max_b, Top2 *__restrict__ top) {
     using L = TcSmem<KB, ATM>;
     constexpr int S = L::B_STAGES;
     constexpr int ACC = L::ACC_STAGES;
@@ -241,7 +239,6 @@ match_top2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
                 for (int kb = 0; kb < KB; ++kb, ++it) {
                     const int s = it % S;
                     mbar_wait(bar_b_empty(s), ((it / S) & 1) ^ 1);
-                    if ((exp_flags & 2) && nt > 0) { mbar_arrive(bar_b_full(s)); continue; }
                     mbar_expect_tx(bar_b_full(s), L::B_STAGE_BYTES);
                     const uint32_t dst = smem_b + s * L::B_STAGE_BYTES;
                     tma_load_3d(dst, &map_b_hi, bar_b_full(s), kb * TC_BK, nt * TC_BN, p);
@@ -271,7 +268,6 @@ match_top2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
                     const uint32_t b_hi = smem_b + s * L::B_STAGE_BYTES, b_mid = b_hi + TC_TILE_BYTES;
 #pragma unroll
                     for (int k = 0; k < TC_BK / 16; ++k) {
-                        if (exp_flags & 8) break;
                         const uint32_t ko = k * 32;  // 16 bf16 = 32 B inside the 128 B swizzle row
                         const uint64_t db_hi = umma_desc_sw128(b_hi + ko), db_mid = umma_desc_sw128(b_mid + ko);
                         if (ATM) {
@@ -402,7 +398,6 @@ match_top2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
                 if (best != old_best) best_chunk = chunk;
                 if (second != old_second) second_chunk = (second == old_best && best != old_best) ? old_best_chunk : chunk;
             };
-            if (exp_flags & 1) continue;
             if (have0) process(va, n0 + c0 * 32, add_lane0);
             if (have1) process(vb, n0 + c1 * 32, add_lane1);
         }
@@ -496,9 +491,8 @@ static int launch_tc(const CUtensorMap &ah, const CUtensorMap &am, const CUtenso
     auto k = match_top2_tc_kernel<KB, ATM>;
     MP_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcSmem<KB, ATM>::TOTAL));
     dim3 grid((NA + TC_BM - 1) / TC_BM, P);
-    static const int exp_flags = getenv("MP_TC_EXP") ? atoi(getenv("MP_TC_EXP")) : 0;  // timing experiments (wrong results)
     k<<<grid, TC_THREADS, TcSmem<KB, ATM>::TOTAL, s>>>(ah, am, bh, bm, a_hi, a_mid, na, NA, nb, NB, norms_b, use_bias,
-                                                        max_a, max_b, top, exp_flags);
+                                                        max_a, max_b, top);
     MP_LAUNCH_OK_S("match_top2_tc_kernel", s);
     return MP_OK;
 }
