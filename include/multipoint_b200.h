@@ -226,6 +226,19 @@ MP_API int mp_points_correct_f32(const double *qw, const int *nq, int capq, cons
                                  int P, float threshold, uint8_t *row_any, const int *mq, const int *mt, const int *nm,
                                  int capm, uint8_t *tp, mp_stream_t stream);
 
+/* ---- row 3: the elementwise glue between the backbone's cuDNN convolutions, MultiPoint.forward,
+ * multipoint/models/MultiPoint.py:61-90 (getNonlinearity / getConvolutionBlock / generate_encoder).
+ * One pass for  ReLU -> BatchNorm2d(eval) [-> MaxPool2d(2,2)] [-> ReflectionPad2d(1) | ZeroPad2d(1)]
+ * (BatchNorm -> ReLU when bn_first): x (B,C,H,W) fp32 -> out (B,C,Ho+2*pad,Wo+2*pad), Ho = H/2 with
+ * pool.  scale[c] = weight/sqrt(running_var+eps), shift[c] = bias - running_mean*scale (folded on
+ * the host; <= 2 ulp from torch's eval BatchNorm).  conv_bias[c] (or NULL) is added to x first: the
+ * convolution is then called without its bias, which torch would add in a separate elementwise
+ * kernel.  pad in {0,1}; reflect selects the pad mode.
+ * B*C <= 65535 per call. */
+MP_API int mp_relu_bn_pad_f32(const float *x, int B, int C, int H, int W, const float *conv_bias, const float *scale,
+                              const float *shift, int bn_first, int pool, int pad, int reflect, float *out,
+                              mp_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -19,7 +19,7 @@ OBJ = os.path.join(HERE, "lib", "obj")
 LIB = os.path.join(HERE, "lib", "libmultipoint_b200.so")
 
 SOURCES = ["mp_common.cu", "detector_head.cu", "descriptor_normalize.cu", "box_nms.cu",
-           "sample_descriptors.cu", "match.cu", "match_tc.cu", "homographic.cu", "valid_mask.cu", "eval_points.cu"]
+           "sample_descriptors.cu", "match.cu", "match_tc.cu", "homographic.cu", "valid_mask.cu", "eval_points.cu", "activation_fused.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC,-fvisibility=hidden", "-I" + os.path.join(ROOT, "include"), "-I" + CSRC]
 

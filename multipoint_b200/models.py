@@ -98,6 +98,67 @@ class MultiPoint(nn.Module):
             layers.append(nn.BatchNorm2d(out_channels))
         return nn.Sequential(*layers)
 
+    # ------------------------------------------------------------------ fused inference path
+    @staticmethod
+    def _folded_bn(bn):
+        """Eval-mode BatchNorm as a per-channel affine (scale, shift); cached on the module until a parameter or
+        buffer changes (in-place updates such as load_state_dict bump the tensors' version counters)."""
+        ver = (bn.weight._version, bn.bias._version, bn.running_mean._version, bn.running_var._version,
+               bn.weight.data_ptr(), bn.running_var.data_ptr())
+        hit = getattr(bn, '_mp_folded', None)
+        if hit is None or hit[0] != ver:
+            with torch.no_grad():
+                scale = (bn.weight.float() / torch.sqrt(bn.running_var.float() + bn.eps)).contiguous()
+                shift = (bn.bias.float() - bn.running_mean.float() * scale).contiguous()
+            hit = (ver, scale, shift)
+            bn._mp_folded = hit
+        return hit[1], hit[2]
+
+    def _run(self, seq, x):
+        """``seq(x)`` for the encoder / head Sequentials.  In inference (eval mode, no autograd, fp32 CUDA input) the
+        ReLU -> BatchNorm [-> MaxPool] [-> pad] chain after every 3x3 convolution runs as one pass
+        (ops.relu_bn_pad) instead of three or four full-tensor elementwise kernels; the convolutions are the same
+        cuDNN calls.  Anything that does not match that pattern, and every other mode, goes through the modules."""
+        if (self.training or torch.is_grad_enabled() or not x.is_cuda or x.dtype != torch.float32
+                or self.config['mixed_precision'] or torch.is_autocast_enabled()):
+            return seq(x)
+        pads = (nn.ReflectionPad2d, nn.ZeroPad2d)
+        mods = list(seq)
+        i, padded = 0, False
+        while i < len(mods):
+            m = mods[i]
+            if isinstance(m, pads) and padded:      # the fused pass before already produced the padded tensor
+                padded = False
+                i += 1
+                continue
+            pair = mods[i + 1:i + 3]
+            fusable = (isinstance(m, nn.Conv2d) and m.padding_mode == 'zeros' and len(pair) == 2
+                       and {type(pair[0]), type(pair[1])} == {nn.ReLU, nn.BatchNorm2d}
+                       and not (pair[0].training or pair[1].training))
+            if not fusable:
+                x = m(x)
+                i += 1
+                continue
+            # the convolution without its bias (the fused pass adds it: torch would spend one more elementwise kernel)
+            x = nn.functional.conv2d(x, m.weight, None, m.stride, m.padding, m.dilation, m.groups)
+            bn_first = isinstance(pair[0], nn.BatchNorm2d)
+            bn = pair[0] if bn_first else pair[1]
+            j = i + 3
+            pool = (j < len(mods) and isinstance(mods[j], nn.MaxPool2d) and mods[j].kernel_size in (2, (2, 2))
+                    and mods[j].stride in (2, (2, 2)) and mods[j].padding in (0, (0, 0)) and not mods[j].ceil_mode
+                    and x.shape[-2] % 2 == 0 and x.shape[-1] % 2 == 0)
+            if pool:
+                j += 1
+            pad_next = (j < len(mods) and isinstance(mods[j], pads) and tuple(mods[j].padding) == (1, 1, 1, 1)
+                        and min(x.shape[-2:]) // (2 if pool else 1) >= 2)
+            scale, shift = self._folded_bn(bn)
+            x = ops.relu_bn_pad(x.contiguous(), scale, shift, bn_first=bn_first, pool=pool, pad=1 if pad_next else 0,
+                                reflect=isinstance(mods[j], nn.ReflectionPad2d) if pad_next else True,
+                                conv_bias=None if m.bias is None else m.bias.detach())
+            padded = pad_next
+            i = j
+        return x
+
     # ------------------------------------------------------------------ reference API
     def set_force_return_logits(self, value):
         if not isinstance(value, bool):
@@ -115,15 +176,15 @@ class MultiPoint(nn.Module):
         encoder according to data['is_optical'][:,0]."""
         image = data['image']
         if not self.config['multispectral']:
-            return self.encoder(image)
+            return self._run(self.encoder, image)
         sel = data['is_optical'][:, 0].bool()
         n_opt = int(sel.sum())
         if n_opt == image.shape[0]:
-            return self.encoder_optical(image)
+            return self._run(self.encoder_optical, image)
         if n_opt == 0:
-            return self.encoder_thermal(image)
-        xo = self.encoder_optical(image[sel])
-        xt = self.encoder_thermal(image[~sel])
+            return self._run(self.encoder_thermal, image)
+        xo = self._run(self.encoder_optical, image[sel])
+        xt = self._run(self.encoder_thermal, image[~sel])
         x = torch.empty((image.shape[0],) + tuple(xo.shape[1:]), dtype=xo.dtype, device=xo.device)
         x[sel] = xo
         x[~sel] = xt
@@ -138,13 +199,13 @@ class MultiPoint(nn.Module):
         return out
 
     def detector_head(self, x):
-        logits = self.detector_head_convolutions(x).to(torch.float)
+        logits = self._run(self.detector_head_convolutions, x).to(torch.float)
         if self.training or self.config['force_return_logits']:
             return None, logits
         return ops.detector_head(logits), None
 
     def descriptor_head(self, x, channels_last=False):
-        x = self.descriptor_head_convolutions(x).to(torch.float)
+        x = self._run(self.descriptor_head_convolutions, x).to(torch.float)
         if not self.config['normalize_descriptors']:
             return x
         if torch.is_grad_enabled() and x.requires_grad:
@@ -157,8 +218,8 @@ class MultiPoint(nn.Module):
     def backbone_outputs(self, data):
         """(logits (B,65,Hc,Wc), raw descriptor map (B,D,Hc,Wc)) -- everything cuDNN computes."""
         x = self.encode(data)
-        logits = self.detector_head_convolutions(x).to(torch.float)
-        raw = self.descriptor_head_convolutions(x).to(torch.float) if self.config['descriptor_head'] else None
+        logits = self._run(self.detector_head_convolutions, x).to(torch.float)
+        raw = self._run(self.descriptor_head_convolutions, x).to(torch.float) if self.config['descriptor_head'] else None
         return logits, raw
 
 

@@ -377,3 +377,29 @@ def points_correct(qw, t, threshold, nq=None, nt=None, mq=None, mt=None, nm=None
                                                      P, float(threshold), _ptr(row_any), _ptr(mq), _ptr(mt), _ptr(_counts(nm, P, "nm")),
                                                      capm, _ptr(tp), _stream(qw)), "mp_points_correct_f32")
     return row_any, tp
+
+
+# ----------------------------------------------------------------------------- row 3: glue between the backbone convolutions
+def relu_bn_pad(x, scale, shift, bn_first=False, pool=False, pad=1, reflect=True, conv_bias=None):
+    """[+ conv_bias] -> ReLU -> eval BatchNorm (folded scale/shift) [-> MaxPool2d(2,2)] [-> pad 1] in one pass.
+    x (B,C,H,W) fp32 -> (B,C,Ho+2*pad,Wo+2*pad)."""
+    x = _cuda(x, torch.float32, "x")
+    scale = _cuda(scale, torch.float32, "scale")
+    shift = _cuda(shift, torch.float32, "shift")
+    B, C, H, W = x.shape
+    if scale.numel() != C or shift.numel() != C:
+        raise ValueError("scale/shift must have %d entries" % C)
+    if conv_bias is not None:
+        conv_bias = _cuda(conv_bias, torch.float32, "conv_bias")
+        if conv_bias.numel() != C:
+            raise ValueError("conv_bias must have %d entries" % C)
+    Ho, Wo = (H // 2, W // 2) if pool else (H, W)
+    out = torch.empty((B, C, Ho + 2 * pad, Wo + 2 * pad), dtype=torch.float32, device=x.device)
+    step = max(1, 65535 // C)   # the kernel takes B*C <= 65535 planes per launch
+    lib = _lib.load()
+    with torch.cuda.device(x.device):
+        for b0 in range(0, B, step):
+            nb = min(step, B - b0)
+            _lib.check(lib.mp_relu_bn_pad_f32(_ptr(x[b0:b0 + nb]), nb, C, H, W, _ptr(conv_bias), _ptr(scale), _ptr(shift), int(bool(bn_first)), int(bool(pool)),
+                                              int(pad), int(bool(reflect)), _ptr(out[b0:b0 + nb]), _stream(x)), "mp_relu_bn_pad_f32")
+    return out

@@ -576,6 +576,71 @@ def test_homographic_adaptation_host_sampling_matches_reference_stream(utils):
     assert_close_but_mask_ties(out.cpu().numpy(), g["single"])
 
 
+def test_relu_bn_pad_kernel_vs_torch(ops):
+    """The fused glue between the backbone convolutions against the module sequence it replaces
+    (ReLU -> BatchNorm2d(eval) [-> MaxPool2d] [-> ReflectionPad2d | ZeroPad2d], or BatchNorm first)."""
+    torch.manual_seed(5)
+    for (B, C, H, W) in [(3, 16, 32, 40), (2, 5, 17, 23), (1, 64, 128, 160)]:
+        x = torch.randn(B, C, H, W, device="cuda") * 2
+        bn = torch.nn.BatchNorm2d(C).cuda().eval()
+        with torch.no_grad():
+            bn.weight.uniform_(-1.5, 1.5); bn.bias.normal_(); bn.running_mean.normal_(); bn.running_var.uniform_(0.2, 3.0)
+            scale = bn.weight / torch.sqrt(bn.running_var + bn.eps)
+            shift = bn.bias - bn.running_mean * scale
+            for bn_first in (False, True):
+                for pool in (False, True):
+                    if pool and (H % 2 or W % 2):
+                        continue
+                    for pad, reflect in [(0, True), (1, True), (1, False)]:
+                        cbias = torch.randn(C, device="cuda") if (pad and pool) or bn_first else None
+                        xb = x if cbias is None else x + cbias[None, :, None, None]
+                        ref = torch.relu(bn(xb)) if bn_first else bn(torch.relu(xb))
+                        if pool:
+                            ref = torch.nn.functional.max_pool2d(ref, 2, 2)
+                        if pad:
+                            ref = (torch.nn.ReflectionPad2d(1) if reflect else torch.nn.ZeroPad2d(1))(ref)
+                        got = ops.relu_bn_pad(x, scale, shift, bn_first=bn_first, pool=pool, pad=pad, reflect=reflect, conv_bias=cbias)
+                        torch.testing.assert_close(got, ref, rtol=2e-6, atol=2e-6)
+    with pytest.raises(ValueError):
+        ops.relu_bn_pad(torch.zeros(1, 2, 5, 6, device="cuda"), torch.ones(2, device="cuda"), torch.zeros(2, device="cuda"), pool=True)
+
+
+def test_multipoint_fused_inference_path_equals_module_path():
+    """MultiPoint in eval / no_grad (fused glue kernels between the cuDNN convolutions) against the same network run
+    module by module (what it does whenever autograd is on): same logits / descriptors to fp32 rounding."""
+    from multipoint_b200.models import MultiPoint
+    from multipoint_b200.pipeline import calibrate_random_init
+    for cfg in ({'multispectral': True, 'descriptor_size': 64},
+                {'multispectral': False, 'descriptor_size': 32, 'bn_first': True, 'reflection_pad': False},
+                {'multispectral': False, 'descriptor_size': 32, 'double_convolution': False}):
+        torch.manual_seed(9)
+        net = MultiPoint(dict(cfg)).cuda().eval()
+        img = torch.rand(4, 1, 64, 80, device="cuda")
+        opt = torch.tensor([[1], [0], [1], [0]], dtype=torch.bool, device="cuda")
+        calibrate_random_init(net, img, is_optical=opt)
+        data = {'image': img, 'is_optical': opt}
+        with torch.no_grad():
+            xf = net.encode(data)
+            fl, fr = net.backbone_outputs(data)
+            fused = net(data)
+        with torch.enable_grad():
+            xm = net.encode(data).detach()
+            ml, mr = net.backbone_outputs(data)
+        # encoder output: fp32 rounding apart
+        torch.testing.assert_close(xf, xm, rtol=2e-5, atol=2e-5 * float(xm.abs().max()))
+        # head outputs: the calibrated random-init network is ill-conditioned (BatchNorm subtracts a mean much larger
+        # than the spread), so judge both fp32 paths against the same network in float64
+        import copy
+        net64 = copy.deepcopy(net).double()
+        with torch.enable_grad():
+            tl, tr = net64.backbone_outputs({'image': img.double(), 'is_optical': opt})
+        for f, m, t in ((fl, ml.detach(), tl.detach()), (fr, mr.detach(), tr.detach())):
+            err_f = float((f.double() - t).abs().max())
+            err_m = float((m.double() - t).abs().max())
+            assert err_f <= 3.0 * err_m + 1e-6 * float(t.abs().max()), (err_f, err_m)
+        assert fused['prob'].shape == (4, 1, 64, 80) and fused['logits'] is None
+
+
 # ------------------------------------------------------------------ row 3: model contract
 def test_multipoint_forward_vs_reference(oracle):
     from multipoint_b200.models import MultiPoint
