@@ -93,6 +93,16 @@ def main():
         add("sample_descriptors NCHW D=%d K=2048" % D, timed(lambda: ops.sample_descriptors(kp, nchw, H, W, counts=cnt)), nb)
         del raw, nchw, nhwc
 
+    # the fused glue between the backbone convolutions at the two largest layer shapes (one encoder = 64 images)
+    for (Bg, Cg, Hg, Wg, pool) in ((64, 64, 512, 640, False), (64, 64, 512, 640, True), (64, 64, 256, 320, False), (64, 128, 128, 160, True)):
+        xg = torch.randn((Bg, Cg, Hg, Wg), generator=g, device=dev)
+        scg = torch.rand((Cg,), generator=g, device=dev) + 0.5
+        shg = torch.randn((Cg,), generator=g, device=dev)
+        cbg = torch.randn((Cg,), generator=g, device=dev)
+        og = ops.relu_bn_pad(xg, scg, shg, pool=pool, pad=1, reflect=True, conv_bias=cbg)
+        add("relu_bn_pad %dx%dx%dx%d%s + reflection pad" % (Bg, Cg, Hg, Wg, " + maxpool" if pool else ""),
+            timed(lambda: ops.relu_bn_pad(xg, scg, shg, pool=pool, pad=1, reflect=True, conv_bias=cbg), iters=10), 4 * (xg.numel() + og.numel()))
+        del xg, og
     # config 3: matching sweep
     sizes = (1024, 2048, 4096) if args.quick else (1024, 2048, 4096, 8192, 16384)
     for D in (256, 64):

@@ -21,3 +21,19 @@ timeout -k 10 900 ncu --set full --clock-control none --import-source on \
 python -c "
 import json; d=json.load(open('gpurun_out/bench_n1.json')); print({k:d[k] for k in ('value','ms_per_step')}, d['e2e']['value'], d['hot_path']['ms_per_step']); print(json.dumps(d['roofline']))
 for r in d['hot_path']['kernels']: print(r)"
+# the fused backbone glue kernel at the two full-resolution layer shapes (ncu --set full)
+cat > gpurun_out/glue_ncu.py <<'PY'
+import sys, torch
+sys.path.insert(0, '.')
+from multipoint_b200 import ops
+g = torch.Generator(device='cuda').manual_seed(0)
+x = torch.randn((64, 64, 512, 640), generator=g, device='cuda')
+sc = torch.rand(64, device='cuda') + 0.5
+sh = torch.randn(64, device='cuda')
+for pool in (False, True):
+    for _ in range(3):
+        ops.relu_bn_pad(x, sc, sh, pool=pool, pad=1, reflect=True, conv_bias=sh)
+torch.cuda.synchronize()
+PY
+timeout -k 10 600 ncu --set full --clock-control none --import-source on -k regex:"relu_bn_pad" -s 2 -c 4 -o gpurun_out/prof_glue python gpurun_out/glue_ncu.py > gpurun_out/ncu_glue.log 2>&1
+tail -2 gpurun_out/ncu_glue.log
