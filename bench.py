@@ -413,6 +413,10 @@ def main():
             tj = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")))
             traffic = {k: v["dram_bytes"] for k, v in tj["per_launch"].items()}
             traffic["sample_descriptors_kernel"] = traffic.get("sample_descriptors_nhwc_vec_kernel")
+            # the glue kernel's launches differ per layer: DRAM bytes / algorithmic bytes of the captured full-resolution
+            # launches, applied to the average algorithmic bytes per launch
+            if "relu_bn_pad_kernel_dram_over_algorithmic" in tj and glue["calls"]:
+                traffic["relu_bn_pad_kernel"] = int(tj["relu_bn_pad_kernel_dram_over_algorithmic"] * glue["bytes"] / glue["calls"])
             traffic_src = tj["source"]
         except Exception:
             traffic = {}
