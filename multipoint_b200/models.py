@@ -177,6 +177,16 @@ class MultiPoint(nn.Module):
         image = data['image']
         if not self.config['multispectral']:
             return self._run(self.encoder, image)
+        n_hint = data.get('n_optical')
+        if n_hint is not None:
+            # the caller vouches that rows [0, n) are optical and the rest thermal (KeypointPipeline builds its batch
+            # that way): no device->host read of is_optical, no gather / scatter of the rows
+            n = int(n_hint)
+            if n == image.shape[0]:
+                return self._run(self.encoder_optical, image)
+            if n == 0:
+                return self._run(self.encoder_thermal, image)
+            return torch.cat([self._run(self.encoder_optical, image[:n]), self._run(self.encoder_thermal, image[n:])])
         sel = data['is_optical'][:, 0].bool()
         n_opt = int(sel.sum())
         if n_opt == image.shape[0]:

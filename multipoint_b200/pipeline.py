@@ -12,11 +12,15 @@ from . import ops
 
 class KeypointPipeline:
     def __init__(self, net, nms=4, detection_threshold=0.015, topk=2048, iou=0.1, metric='l2', cross_check=True,
-                 match_threshold=-1.0, algo=None):
+                 match_threshold=-1.0, algo=None, trust_spectrum_keys=True):
+        """trust_spectrum_keys: data['optical'] really holds optical images and data['thermal'] thermal ones (what
+        ImagePairDataset yields), so the encoder routing of MultiPoint.py:107-122 needs no device->host read of
+        ``is_optical``.  Set it to False to route every row by its ``is_optical`` flag like the reference."""
         if topk <= 0:
             raise ValueError("KeypointPipeline needs topk > 0 (fixed-capacity keypoint buffers)")
         self.net, self.nms, self.thr, self.topk, self.iou = net, nms, detection_threshold, int(topk), iou
         self.metric, self.cross_check, self.match_threshold, self.algo = metric, cross_check, match_threshold, algo
+        self.trust_spectrum_keys = bool(trust_spectrum_keys)
 
     @torch.no_grad()
     def extract_from_backbone(self, logits, raw_desc, H, W, valid_mask=None):
@@ -59,6 +63,8 @@ class KeypointPipeline:
         both = {'image': torch.cat([o['image'], t['image']])}
         if 'is_optical' in o and 'is_optical' in t:
             both['is_optical'] = torch.cat([o['is_optical'], t['is_optical']])
+            if self.trust_spectrum_keys:
+                both['n_optical'] = B   # rows [0,B) optical, [B,2B) thermal: the encoders are picked without a host sync
         if 'valid_mask' in o and 'valid_mask' in t:
             both['valid_mask'] = torch.cat([o['valid_mask'], t['valid_mask']])
         ext = self.extract(both)

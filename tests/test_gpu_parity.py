@@ -725,6 +725,12 @@ def test_pipeline_stream_equals_call():
         streamed.append({'kp': r['optical']['keypoints'].cpu(), 'cnt': r['thermal']['counts'].cpu(), 'q': r['matches']['query'].cpu(),
                          't': r['matches']['train'].cpu(), 'n': r['matches']['counts'].cpu()})
     assert len(streamed) == 3
+    # routing by the dict keys (no host sync) == routing every row by its is_optical flag (the reference's way)
+    by_flag = KeypointPipeline(net, nms=4, detection_threshold=0.015, topk=64, trust_spectrum_keys=False)
+    dev_b = {s: {k: v.cuda() for k, v in d.items()} for s, d in batches[0].items()}
+    ra, rb = pipe(dev_b), by_flag(dev_b)
+    assert torch.equal(ra['optical']['keypoints'], rb['optical']['keypoints']) and torch.equal(ra['thermal']['counts'], rb['thermal']['counts'])
+    assert torch.equal(ra['matches']['counts'], rb['matches']['counts'])
     for b, got in zip(batches, streamed):
         r = pipe({s: {k: v.cuda() for k, v in d.items()} for s, d in b.items()})
         assert torch.equal(got['kp'], r['optical']['keypoints'].cpu()) and torch.equal(got['cnt'], r['thermal']['counts'].cpu())
