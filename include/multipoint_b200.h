@@ -239,6 +239,15 @@ MP_API int mp_relu_bn_pad_f32(const float *x, int B, int C, int H, int W, const 
                               const float *shift, int bn_first, int pool, int pad, int reflect, float *out,
                               mp_stream_t stream);
 
+/* First encoder layer, MultiPoint.py:61-72,85-92: [ReflectionPad2d(1) | ZeroPad2d(1)] -> Conv2d(1 -> C, 3x3) ->
+ * ReLU/BatchNorm2d(eval) [-> pad 1 for the next convolution] in one kernel (with one input channel the
+ * convolution is bound by writing its output).  image (B,1,H,W); weight (C,1,3,3); conv_bias (C) or NULL;
+ * scale/shift as in mp_relu_bn_pad_f32; in_reflect / out_reflect select the pad modes; out
+ * (B,C,H+2*pad,W+2*pad).  W + 2*pad <= 768. */
+MP_API int mp_conv1_relu_bn_pad_f32(const float *image, int B, int H, int W, const float *weight, const float *conv_bias,
+                                    const float *scale, const float *shift, int C, int bn_first, int in_reflect, int pad,
+                                    int out_reflect, float *out, mp_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -40,6 +40,7 @@ SIGNATURES = {
     "mp_points_min_dist2_i64": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "mp_points_correct_f32": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i, _c.c_float, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
     "mp_relu_bn_pad_f32": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "mp_conv1_relu_bn_pad_f32": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "mp_ha_aggregate_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
 }
 

@@ -157,6 +157,74 @@ relu_bn_pad_vec_kernel(const float *__restrict__ x, float *__restrict__ out, con
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// First layer of the encoders: Conv2d(1 -> C, 3x3) on the padded image, + bias, ReLU, eval BatchNorm and the
+// padding of the next convolution in one kernel.  With a single input channel the convolution is 9 MACs per
+// output value and entirely bound by writing the C-channel activation (5.4 GB per 64 images of 512x640), so
+// there is nothing for a GEMM-shaped library kernel to win: cuDNN spends ~2.2 ms on it and the glue pass that
+// follows another 1.65 ms, this kernel writes the padded activation once (~0.9 ms).
+// One CTA per (output row, image); a thread owns up to four columns T apart (coalesced stores for every
+// channel) and keeps their 3x3 input patches in registers; weights and per-channel constants in shared memory.
+constexpr int C1_THREADS = 192;
+constexpr int C1_PX = 4;
+
+__global__ void __launch_bounds__(C1_THREADS)
+conv1_relu_bn_pad_kernel(const float *__restrict__ img, float *__restrict__ out, const float *__restrict__ weight,
+                         const float *__restrict__ conv_bias, const float *__restrict__ scale,
+                         const float *__restrict__ shift, int C, int H, int W, int in_reflect, int pad, int out_reflect,
+                         int bn_first) {
+    extern __shared__ __align__(16) float c1_smem[];  // [C][12]: 9 weights, conv bias, scale, shift
+    for (int i = threadIdx.x; i < C * 12; i += C1_THREADS) {
+        const int c = i / 12, k = i - c * 12;
+        c1_smem[i] = k < 9 ? weight[c * 9 + k] : (k == 9 ? (conv_bias ? conv_bias[c] : 0.f) : (k == 10 ? scale[c] : shift[c]));
+    }
+    __syncthreads();
+    const int b = blockIdx.y, yo = blockIdx.x;
+    const int Hp = H + 2 * pad, Wp = W + 2 * pad;
+    const float *src = img + (size_t)b * H * W;
+    int ys = yo - pad;
+    bool zero_out_row = false;
+    if (ys < 0) { if (out_reflect) ys = -ys; else zero_out_row = true; }
+    else if (ys >= H) { if (out_reflect) ys = 2 * H - 2 - ys; else zero_out_row = true; }
+    float patch[C1_PX][9];
+    bool live[C1_PX], zero_px[C1_PX];
+#pragma unroll
+    for (int j = 0; j < C1_PX; ++j) {
+        const int xo = threadIdx.x + j * C1_THREADS;
+        live[j] = xo < Wp;
+        int xs = xo - pad;
+        zero_px[j] = zero_out_row;
+        if (xs < 0) { if (out_reflect) xs = -xs; else zero_px[j] = true; }
+        else if (xs >= W) { if (out_reflect) xs = 2 * W - 2 - xs; else zero_px[j] = true; }
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+            int iy = ys + k / 3 - 1, ix = xs + k % 3 - 1;
+            bool inside = true;  // the input's own padding (ReflectionPad2d(1) / ZeroPad2d(1) in front of the convolution)
+            if (iy < 0) { if (in_reflect) iy = -iy; else inside = false; }
+            else if (iy >= H) { if (in_reflect) iy = 2 * H - 2 - iy; else inside = false; }
+            if (ix < 0) { if (in_reflect) ix = -ix; else inside = false; }
+            else if (ix >= W) { if (in_reflect) ix = 2 * W - 2 - ix; else inside = false; }
+            patch[j][k] = (live[j] && !zero_px[j] && inside) ? __ldg(src + (size_t)iy * W + ix) : 0.f;
+        }
+    }
+    float *dst = out + ((size_t)b * C * Hp + yo) * Wp;
+    for (int c = 0; c < C; ++c) {
+        const float4 w0 = *reinterpret_cast<const float4 *>(c1_smem + c * 12);
+        const float4 w1 = *reinterpret_cast<const float4 *>(c1_smem + c * 12 + 4);
+        const float4 w2 = *reinterpret_cast<const float4 *>(c1_smem + c * 12 + 8);  // w[8], conv bias, scale, shift
+#pragma unroll
+        for (int j = 0; j < C1_PX; ++j) {
+            float acc = patch[j][0] * w0.x;
+            acc = fmaf(patch[j][1], w0.y, acc); acc = fmaf(patch[j][2], w0.z, acc); acc = fmaf(patch[j][3], w0.w, acc);
+            acc = fmaf(patch[j][4], w1.x, acc); acc = fmaf(patch[j][5], w1.y, acc); acc = fmaf(patch[j][6], w1.z, acc);
+            acc = fmaf(patch[j][7], w1.w, acc); acc = fmaf(patch[j][8], w2.x, acc);
+            float v = af_apply(acc, w2.y, w2.z, w2.w, bn_first);
+            if (zero_px[j]) v = 0.f;
+            if (live[j]) dst[(size_t)c * Hp * Wp + threadIdx.x + j * C1_THREADS] = v;
+        }
+    }
+}
+
 }  // namespace mp
 
 extern "C" int mp_relu_bn_pad_f32(const float *x, int B, int C, int H, int W, const float *conv_bias, const float *scale,
@@ -192,5 +260,24 @@ extern "C" int mp_relu_bn_pad_f32(const float *x, int B, int C, int H, int W, co
     else
         mp::relu_bn_pad_kernel<false><<<grid, mp::AF_THREADS, 0, (cudaStream_t)stream>>>(x, out, conv_bias, scale, shift, C, H, W, pad, reflect, bn_first);
     MP_LAUNCH_OK_S("relu_bn_pad_kernel", (cudaStream_t)stream);
+    return MP_OK;
+}
+
+extern "C" int mp_conv1_relu_bn_pad_f32(const float *image, int B, int H, int W, const float *weight, const float *conv_bias,
+                                        const float *scale, const float *shift, int C, int bn_first, int in_reflect, int pad,
+                                        int out_reflect, float *out, mp_stream_t stream) {
+    mp::prof_entry((cudaStream_t)stream);
+    MP_CHECK_ARG(B >= 0 && C > 0 && H >= 2 && W >= 2, "mp_conv1_relu_bn_pad_f32: bad shape B=%d C=%d H=%d W=%d", B, C, H, W);
+    MP_CHECK_ARG(pad == 0 || pad == 1, "mp_conv1_relu_bn_pad_f32: pad must be 0 or 1");
+    MP_CHECK_ARG(C <= 1024, "mp_conv1_relu_bn_pad_f32: at most 1024 output channels");
+    MP_CHECK_ARG(W + 2 * pad <= mp::C1_THREADS * mp::C1_PX, "mp_conv1_relu_bn_pad_f32: image wider than %d", mp::C1_THREADS * mp::C1_PX - 2);
+    if (B == 0) return MP_OK;
+    MP_CHECK_ARG(image && weight && scale && shift && out, "mp_conv1_relu_bn_pad_f32: null pointer");
+    MP_CHECK_ARG(B <= 65535, "mp_conv1_relu_bn_pad_f32: at most 65535 images per call");
+    dim3 grid((unsigned)(H + 2 * pad), (unsigned)B);
+    const size_t smem = (size_t)C * 12 * sizeof(float);
+    mp::conv1_relu_bn_pad_kernel<<<grid, mp::C1_THREADS, smem, (cudaStream_t)stream>>>(image, out, weight, conv_bias, scale, shift, C, H, W,
+                                                                                      in_reflect, pad, out_reflect, bn_first);
+    MP_LAUNCH_OK_S("conv1_relu_bn_pad_kernel", (cudaStream_t)stream);
     return MP_OK;
 }

@@ -125,6 +125,22 @@ class MultiPoint(nn.Module):
         pads = (nn.ReflectionPad2d, nn.ZeroPad2d)
         mods = list(seq)
         i, padded = 0, False
+        # first encoder layer: pad -> Conv2d(1 -> C, 3x3) -> ReLU/BatchNorm [-> pad] on a one-channel image is one kernel
+        if (len(mods) >= 4 and isinstance(mods[0], pads) and tuple(mods[0].padding) == (1, 1, 1, 1) and x.shape[1] == 1
+                and isinstance(mods[1], nn.Conv2d) and mods[1].in_channels == 1 and mods[1].kernel_size == (3, 3)
+                and mods[1].stride == (1, 1) and mods[1].padding == (0, 0) and mods[1].dilation == (1, 1) and mods[1].groups == 1
+                and {type(mods[2]), type(mods[3])} == {nn.ReLU, nn.BatchNorm2d} and not (mods[2].training or mods[3].training)
+                and min(x.shape[-2:]) >= 2 and x.shape[-1] + 2 <= 768
+                and not (len(mods) > 4 and isinstance(mods[4], nn.MaxPool2d))):
+            bn_first = isinstance(mods[2], nn.BatchNorm2d)
+            scale, shift = self._folded_bn(mods[2] if bn_first else mods[3])
+            pad_next = len(mods) > 4 and isinstance(mods[4], pads) and tuple(mods[4].padding) == (1, 1, 1, 1)
+            conv = mods[1]
+            x = ops.conv1_relu_bn_pad(x.contiguous(), conv.weight.detach(), None if conv.bias is None else conv.bias.detach(), scale, shift,
+                                      bn_first=bn_first, in_reflect=isinstance(mods[0], nn.ReflectionPad2d), pad=1 if pad_next else 0,
+                                      out_reflect=isinstance(mods[4], nn.ReflectionPad2d) if pad_next else True)
+            padded = pad_next
+            i = 4
         while i < len(mods):
             m = mods[i]
             if isinstance(m, pads) and padded:      # the fused pass before already produced the padded tensor

@@ -403,3 +403,24 @@ def relu_bn_pad(x, scale, shift, bn_first=False, pool=False, pad=1, reflect=True
             _lib.check(lib.mp_relu_bn_pad_f32(_ptr(x[b0:b0 + nb]), nb, C, H, W, _ptr(conv_bias), _ptr(scale), _ptr(shift), int(bool(bn_first)), int(bool(pool)),
                                               int(pad), int(bool(reflect)), _ptr(out[b0:b0 + nb]), _stream(x)), "mp_relu_bn_pad_f32")
     return out
+
+
+def conv1_relu_bn_pad(image, weight, conv_bias, scale, shift, bn_first=False, in_reflect=True, pad=1, out_reflect=True):
+    """[pad 1] -> Conv2d(1 -> C, 3x3) -> +bias -> ReLU/BatchNorm(eval) [-> pad 1] for the encoders' first layer.
+    image (B,1,H,W) fp32 -> (B,C,H+2*pad,W+2*pad)."""
+    image = _cuda(image, torch.float32, "image")
+    weight = _cuda(weight, torch.float32, "weight")
+    scale = _cuda(scale, torch.float32, "scale")
+    shift = _cuda(shift, torch.float32, "shift")
+    B, cin, H, W = image.shape
+    C = weight.shape[0]
+    if cin != 1 or tuple(weight.shape[1:]) != (1, 3, 3):
+        raise ValueError("conv1_relu_bn_pad needs a (B,1,H,W) image and (C,1,3,3) weights")
+    if conv_bias is not None:
+        conv_bias = _cuda(conv_bias, torch.float32, "conv_bias")
+    out = torch.empty((B, C, H + 2 * pad, W + 2 * pad), dtype=torch.float32, device=image.device)
+    with torch.cuda.device(image.device):
+        _lib.check(_lib.load().mp_conv1_relu_bn_pad_f32(_ptr(image), B, H, W, _ptr(weight), _ptr(conv_bias), _ptr(scale), _ptr(shift), C,
+                                                        int(bool(bn_first)), int(bool(in_reflect)), int(pad), int(bool(out_reflect)),
+                                                        _ptr(out), _stream(image)), "mp_conv1_relu_bn_pad_f32")
+    return out

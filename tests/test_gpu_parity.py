@@ -605,6 +605,29 @@ def test_relu_bn_pad_kernel_vs_torch(ops):
         ops.relu_bn_pad(torch.zeros(1, 2, 5, 6, device="cuda"), torch.ones(2, device="cuda"), torch.zeros(2, device="cuda"), pool=True)
 
 
+def test_conv1_relu_bn_pad_kernel_vs_torch(ops):
+    """The encoders' first layer as one kernel against pad -> cuDNN conv -> ReLU/BatchNorm -> pad."""
+    torch.manual_seed(6)
+    for (B, C, H, W) in [(2, 64, 64, 80), (3, 7, 17, 23), (1, 64, 128, 640)]:
+        img = torch.rand(B, 1, H, W, device="cuda")
+        conv = torch.nn.Conv2d(1, C, 3).cuda()
+        bn = torch.nn.BatchNorm2d(C).cuda().eval()
+        with torch.no_grad():
+            bn.weight.uniform_(-1.5, 1.5); bn.bias.normal_(); bn.running_mean.normal_(std=0.1); bn.running_var.uniform_(0.2, 3.0)
+            scale = bn.weight / torch.sqrt(bn.running_var + bn.eps)
+            shift = bn.bias - bn.running_mean * scale
+            for bn_first in (False, True):
+                for in_reflect in (True, False):
+                    for pad, out_reflect in [(0, True), (1, True), (1, False)]:
+                        y = conv((torch.nn.ReflectionPad2d(1) if in_reflect else torch.nn.ZeroPad2d(1))(img))
+                        ref = torch.relu(bn(y)) if bn_first else bn(torch.relu(y))
+                        if pad:
+                            ref = (torch.nn.ReflectionPad2d(1) if out_reflect else torch.nn.ZeroPad2d(1))(ref)
+                        got = ops.conv1_relu_bn_pad(img, conv.weight, conv.bias, scale, shift, bn_first=bn_first, in_reflect=in_reflect,
+                                                    pad=pad, out_reflect=out_reflect)
+                        torch.testing.assert_close(got, ref, rtol=1e-5, atol=1e-5)
+
+
 def test_multipoint_fused_inference_path_equals_module_path():
     """MultiPoint in eval / no_grad (fused glue kernels between the cuDNN convolutions) against the same network run
     module by module (what it does whenever autograd is on): same logits / descriptors to fp32 rounding."""
