@@ -405,6 +405,8 @@ def main():
     }
     if glue["calls"]:   # launches of different sizes (one per layer): average algorithmic bytes per launch
         algorithmic["relu_bn_pad_kernel"] = ("hbm", glue["bytes"] / glue["calls"])
+    # first encoder layer, one launch per encoder (P images each): image read + padded 64-channel activation written
+    algorithmic["conv1_relu_bn_pad_kernel"] = ("hbm", P * 4 * (H * W + 64 * (H + 2) * (W + 2)))
     # DRAM bytes per launch from the committed ncu --set full capture of this same workload (bench.py --only-hot);
     # only meaningful at the default sizes the capture was taken at
     traffic = {}

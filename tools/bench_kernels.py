@@ -103,6 +103,11 @@ def main():
         add("relu_bn_pad %dx%dx%dx%d%s + reflection pad" % (Bg, Cg, Hg, Wg, " + maxpool" if pool else ""),
             timed(lambda: ops.relu_bn_pad(xg, scg, shg, pool=pool, pad=1, reflect=True, conv_bias=cbg), iters=10), 4 * (xg.numel() + og.numel()))
         del xg, og
+    imgc = torch.rand((64, 1, H, W), generator=g, device=dev)
+    wc = torch.randn((64, 1, 3, 3), generator=g, device=dev) * 0.3
+    sc64, sh64 = torch.rand((64,), generator=g, device=dev) + 0.5, torch.randn((64,), generator=g, device=dev)
+    add("conv1_relu_bn_pad 64 images 1->64 channels 512x640 + reflection pads",
+        timed(lambda: ops.conv1_relu_bn_pad(imgc, wc, sh64, sc64, sh64), iters=10), 64 * 4 * (H * W + 64 * (H + 2) * (W + 2)))
     # config 3: matching sweep
     sizes = (1024, 2048, 4096) if args.quick else (1024, 2048, 4096, 8192, 16384)
     for D in (256, 64):

@@ -33,7 +33,11 @@ sh = torch.randn(64, device='cuda')
 for pool in (False, True):
     for _ in range(3):
         ops.relu_bn_pad(x, sc, sh, pool=pool, pad=1, reflect=True, conv_bias=sh)
+img = torch.rand((64, 1, 512, 640), generator=g, device='cuda')
+w = torch.randn((64, 1, 3, 3), generator=g, device='cuda')
+for _ in range(2):
+    ops.conv1_relu_bn_pad(img, w, sh, sc, sh)
 torch.cuda.synchronize()
 PY
-timeout -k 10 600 ncu --set full --clock-control none --import-source on -k regex:"relu_bn_pad" -s 2 -c 4 -o gpurun_out/prof_glue python gpurun_out/glue_ncu.py > gpurun_out/ncu_glue.log 2>&1
+timeout -k 10 600 ncu --set full --clock-control none --import-source on -k regex:"relu_bn_pad" -s 2 -c 6 -o gpurun_out/prof_glue python gpurun_out/glue_ncu.py > gpurun_out/ncu_glue.log 2>&1
 tail -2 gpurun_out/ncu_glue.log
