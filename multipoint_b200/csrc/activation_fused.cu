@@ -208,6 +208,7 @@ conv1_relu_bn_pad_kernel(const float *__restrict__ img, float *__restrict__ out,
         }
     }
     float *dst = out + ((size_t)b * C * Hp + yo) * Wp;
+#pragma unroll 4
     for (int c = 0; c < C; ++c) {
         const float4 w0 = *reinterpret_cast<const float4 *>(c1_smem + c * 12);
         const float4 w1 = *reinterpret_cast<const float4 *>(c1_smem + c * 12 + 4);
