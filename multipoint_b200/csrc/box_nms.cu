@@ -13,14 +13,20 @@
 // soon as one higher-priority neighbour is kept, and kept once all of them are decided not-kept.
 // Decisions are only taken on settled facts, so any evaluation order reaches the same result.
 //
-// Kernels (HBM-bound: 4 B read + 4 B written per pixel, plus 8 B per survivor):
-//  1. nms_tile_kernel    one CTA per TH x TW tile with an E-pixel apron staged in shared memory;
-//                        iterates to the local fixed point, writes the dense result once.  Pixels
-//                        whose dependency chain leaves the apron (<0.1 % at E=8) are written as
-//                        -score and queued on a per-image worklist.
-//  2. nms_fixup_kernel   one CTA per image; resolves the worklist against the dense map in L2.
+// Kernels (algorithmic traffic: 4 B read + 4 B written per pixel, plus 8 B per survivor):
+//  dense path (no top-k, footprints that reach beyond 3 px, images the sparse path hands back)
+//   1. nms_tile_fast_kernel / nms_tile_kernel   one CTA per TH x TW tile with an E-pixel apron staged in
+//                        shared memory; iterates to the local fixed point over candidate lists, writes the
+//                        dense result once.  Pixels whose dependency chain leaves the apron (<0.1 % at E=8)
+//                        are written as -score and queued on a per-image worklist.
+//   2. nms_fixup_kernel  one CTA per image; resolves the worklist against the dense map in L2.
 //                        Exits immediately when the list is empty.
-//  3. nms_select_kernel  one CTA per image; optional top-k by radix select on (score desc, index
+//  sparse top-k path (keep_top_k > 0, the shipped configuration; see the comment above nms_candidates_kernel)
+//   1'. nms_candidates_kernel  streams the heatmap once: zero-fills the dense map, lists the candidates and
+//                        histograms their scores.
+//   2'. nms_sparse_kernel  one CTA per image settles only the candidates that can reach the top k.
+//  both
+//   3. nms_select_kernel one CTA per image; optional top-k by radix select on (score desc, index
 //                        asc), then ordered (row-major) compaction of the survivors through a
 //                        bitmap into int64 (y,x) keypoints.
 #include <math.h>

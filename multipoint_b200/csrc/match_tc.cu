@@ -4,19 +4,21 @@
 //
 //   S = A . B^T  with fp32 descriptors split into bf16 planes a = a_hi + a_mid (+ 2^-18 |a|):
 //   S ~= A_hi.B_hi^T + A_hi.B_mid^T + A_mid.B_hi^T      (three tcgen05.mma passes, fp32 accumulate)
-//   |S~ - S| <= 4e-5 |a||b|  (match_internal.cuh); rows whose top-2 margin is inside that bound are
-//   re-ranked exactly in fp64 by match_recheck_kernel, so the argmax that leaves this file plus
-//   the recheck equals the fp64 argmax with ties to the lowest index.
+//   |S~ - S| <= 4e-5 |a||b|  (match_internal.cuh); rows whose top-3 margins are inside that bound are
+//   re-ranked exactly in fp64 (match.cu: pair / row / 8-row recheck kernels), so the argmax that leaves this
+//   file plus the recheck equals the fp64 argmax with ties to the lowest index.
 //
-// One CTA owns 128 rows of A for one image pair:
-//   - A_hi / A_mid for the whole K = D (<= 256) stay resident in shared memory (TMA, 128B swizzle)
-//   - B_hi / B_mid stream through a 3-4 stage TMA ring in (128 rows x 64 k) blocks
-//   - one elected thread issues tcgen05.mma (M=128, N=128, K=16, kind::f16) into one of four
-//     128-column TMEM accumulators; tcgen05.commit releases the smem stage / publishes the tile
-//   - four epilogue warps read the accumulator with tcgen05.ld (one row per thread) and keep a
-//     running (best, second, indices) per row while the next tile's MMAs run
+// One CTA (10 warps) owns 128 rows of A for one image pair:
+//   - warp 0: TMA producer.  A_hi / A_mid for the whole K = D (<= 256) arrive as the first D/64 items of a
+//     six-stage ring of 32 KB blocks (128 rows x 64 k, hi + mid, 128B swizzle), B_hi / B_mid follow tile by tile
+//   - warps 2-9: copy A from the ring into tensor memory (tcgen05.st, one row per thread), then act as the
+//     epilogue: tcgen05.ld of the finished accumulator (two warps per TMEM lane quarter, alternate 32-column
+//     chunks), packed-key arg-top-3 per row while the next tile's MMAs run
+//   - warp 1: one elect.sync thread issues tcgen05.mma (M=128, N=128, K=16, kind::f16, A from TMEM, B from
+//     shared memory) into one of two 128-column TMEM accumulators; tcgen05.commit releases the ring stage /
+//     publishes the tile
 // The only global traffic is the bf16 operands (B re-read once per 128-row block, from L2) and
-// 16 B of result per row.
+// 20 B of result per row.
 #include <cuda.h>
 #include <stdlib.h>
 
