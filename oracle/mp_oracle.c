@@ -758,3 +758,89 @@ MPO_API void mpo_points_correct(const double *qw, int Nq, const int64_t *t, int 
         tp[k] = sqrtf(dy * dy + dx * dx) <= thr;
     }
 }
+
+/* ------------------------------------------------------------------------ */
+/* Row 3 glue: what sits between the backbone's convolutions,                 */
+/* multipoint/models/MultiPoint.py:61-90 (getNonlinearity, getConvolutionBlock,*/
+/* generate_encoder): nn.ReLU -> nn.BatchNorm2d (eval: (x-mean)/sqrt(var+eps)  */
+/* *weight+bias) [-> nn.MaxPool2d(2,2)] [-> nn.ReflectionPad2d(1) |            */
+/* nn.ZeroPad2d(1)], or BatchNorm first with bn_first.  conv_bias (may be NULL)*/
+/* is the preceding convolution's bias.  x (B,C,H,W) -> out (B,C,Ho+2p,Wo+2p). */
+/* ------------------------------------------------------------------------ */
+static float mpo_act(float x, float cb, float mean, float var, float eps, float w, float b, int bn_first)
+{
+    x = x + cb;
+    if (bn_first) {
+        float y = (x - mean) / sqrtf(var + eps) * w + b;
+        return y > 0.f ? y : 0.f;
+    }
+    x = x > 0.f ? x : 0.f;
+    return (x - mean) / sqrtf(var + eps) * w + b;
+}
+
+static int mpo_glue_reflect(int i, int n, int reflect, int *outside)
+{
+    *outside = 0;
+    if (i < 0) { *outside = 1; return reflect ? -i : 0; }
+    if (i >= n) { *outside = 1; return reflect ? 2 * n - 2 - i : 0; }
+    return i;
+}
+
+MPO_API void mpo_relu_bn_pad(const float *x, int B, int C, int H, int W, const float *conv_bias, const float *mean,
+                             const float *var, float eps, const float *weight, const float *bias, int bn_first, int pool,
+                             int pad, int reflect, float *out)
+{
+    const int Ho = pool ? H / 2 : H, Wo = pool ? W / 2 : W, Hp = Ho + 2 * pad, Wp = Wo + 2 * pad;
+    for (int p = 0; p < B * C; ++p) {
+        const int c = p % C;
+        const float cb = conv_bias ? conv_bias[c] : 0.f;
+        for (int yo = 0; yo < Hp; ++yo)
+            for (int xo = 0; xo < Wp; ++xo) {
+                int oy, ox;
+                const int ys = mpo_glue_reflect(yo - pad, Ho, reflect, &oy), xs = mpo_glue_reflect(xo - pad, Wo, reflect, &ox);
+                float v;
+                if ((oy || ox) && !reflect) {
+                    v = 0.f;
+                } else if (pool) {
+                    v = -INFINITY;
+                    for (int dy = 0; dy < 2; ++dy)
+                        for (int dx = 0; dx < 2; ++dx) {
+                            const float t = mpo_act(x[((size_t)p * H + 2 * ys + dy) * W + 2 * xs + dx], cb, mean[c], var[c], eps,
+                                                    weight[c], bias[c], bn_first);
+                            if (t > v) v = t;
+                        }
+                } else {
+                    v = mpo_act(x[((size_t)p * H + ys) * W + xs], cb, mean[c], var[c], eps, weight[c], bias[c], bn_first);
+                }
+                out[((size_t)p * Hp + yo) * Wp + xo] = v;
+            }
+    }
+}
+
+/* First encoder layer: [pad 1] -> Conv2d(1 -> C, 3x3, cross-correlation like torch) -> the chain above [-> pad 1]. */
+MPO_API void mpo_conv1_relu_bn_pad(const float *img, int B, int H, int W, const float *w9, const float *conv_bias, int C,
+                                   const float *mean, const float *var, float eps, const float *weight, const float *bias,
+                                   int bn_first, int in_reflect, int pad, int out_reflect, float *out)
+{
+    const int Hp = H + 2 * pad, Wp = W + 2 * pad;
+    for (int b = 0; b < B; ++b)
+        for (int c = 0; c < C; ++c)
+            for (int yo = 0; yo < Hp; ++yo)
+                for (int xo = 0; xo < Wp; ++xo) {
+                    int oy, ox;
+                    const int ys = mpo_glue_reflect(yo - pad, H, out_reflect, &oy), xs = mpo_glue_reflect(xo - pad, W, out_reflect, &ox);
+                    float v = 0.f;
+                    if (!((oy || ox) && !out_reflect)) {
+                        float acc = 0.f;
+                        for (int k = 0; k < 9; ++k) {
+                            int iy_out, ix_out;
+                            const int iy = mpo_glue_reflect(ys + k / 3 - 1, H, in_reflect, &iy_out);
+                            const int ix = mpo_glue_reflect(xs + k % 3 - 1, W, in_reflect, &ix_out);
+                            const float t = ((iy_out || ix_out) && !in_reflect) ? 0.f : img[((size_t)b * H + iy) * W + ix];
+                            acc += t * w9[c * 9 + k];
+                        }
+                        v = mpo_act(acc, conv_bias ? conv_bias[c] : 0.f, mean[c], var[c], eps, weight[c], bias[c], bn_first);
+                    }
+                    out[(((size_t)b * C + c) * Hp + yo) * Wp + xo] = v;
+                }
+}

@@ -316,3 +316,31 @@ def points_correct(qw, t, thr, mq=None, mt=None):
     lib().mpo_points_correct(qw.ctypes.data_as(_f64p), len(qw), t.ctypes.data_as(_i64p), len(t), ctypes.c_float(thr),
                              row_any.ctypes.data_as(_u8p), mq.ctypes.data_as(i32), mt.ctypes.data_as(i32), len(mq), tp.ctypes.data_as(_u8p))
     return row_any, tp
+
+
+# --- row 3 glue: ReLU / BatchNorm(eval) / MaxPool / pad between the backbone's convolutions (MultiPoint.py:61-90) ---
+def relu_bn_pad(x, mean, var, eps, weight, bias, conv_bias=None, bn_first=False, pool=False, pad=1, reflect=True):
+    x = _f32(x)
+    B, C, H, W = x.shape
+    Ho, Wo = (H // 2, W // 2) if pool else (H, W)
+    out = np.empty((B, C, Ho + 2 * pad, Wo + 2 * pad), np.float32)
+    cb = None if conv_bias is None else _f32(conv_bias)
+    mean, var, weight, bias = _f32(mean), _f32(var), _f32(weight), _f32(bias)
+    lib().mpo_relu_bn_pad(_p(x, _f32p), B, C, H, W, None if cb is None else _p(cb, _f32p), _p(mean, _f32p), _p(var, _f32p),
+                          ctypes.c_float(eps), _p(weight, _f32p), _p(bias, _f32p), int(bn_first), int(pool), int(pad), int(reflect),
+                          _p(out, _f32p))
+    return out
+
+
+def conv1_relu_bn_pad(img, w, conv_bias, mean, var, eps, weight, bias, bn_first=False, in_reflect=True, pad=1, out_reflect=True):
+    img = _f32(img)
+    B, _, H, W = img.shape
+    w = _f32(w)
+    C = w.shape[0]
+    out = np.empty((B, C, H + 2 * pad, W + 2 * pad), np.float32)
+    cb = None if conv_bias is None else _f32(conv_bias)
+    mean, var, weight, bias = _f32(mean), _f32(var), _f32(weight), _f32(bias)
+    lib().mpo_conv1_relu_bn_pad(_p(img, _f32p), B, H, W, _p(w, _f32p), None if cb is None else _p(cb, _f32p), C, _p(mean, _f32p),
+                                _p(var, _f32p), ctypes.c_float(eps), _p(weight, _f32p), _p(bias, _f32p), int(bn_first), int(in_reflect),
+                                int(pad), int(out_reflect), _p(out, _f32p))
+    return out

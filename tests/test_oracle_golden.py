@@ -321,3 +321,38 @@ def test_evaluation_point_geometry_matches_reference(oracle):
         np.testing.assert_array_equal(np.flatnonzero(row_any), g["pt%d_correct_rows" % i])
         np.testing.assert_array_equal(tp.astype(bool), g["pt%d_correct_diag" % i])
     assert (oracle.points_min_dist2(np.array([[3, 3]]), np.zeros((0, 2)), 10, 10) == np.iinfo(np.int64).max).all()
+
+
+def test_backbone_glue_matches_torch_modules(oracle):
+    """Row 3 glue (MultiPoint.py:61-90): the oracle's ReLU / BatchNorm(eval) / MaxPool / pad chain and the
+    one-input-channel first layer against the torch modules the reference builds them from."""
+    import torch
+    torch.manual_seed(4)
+    x = torch.randn(2, 5, 12, 14) * 2
+    bn = torch.nn.BatchNorm2d(5).eval()
+    conv = torch.nn.Conv2d(1, 5, 3)
+    img = torch.rand(2, 1, 11, 9)
+    with torch.no_grad():
+        bn.weight.uniform_(-1.5, 1.5); bn.bias.normal_(); bn.running_mean.normal_(); bn.running_var.uniform_(0.2, 3.0)
+        args = (bn.running_mean.numpy(), bn.running_var.numpy(), bn.eps, bn.weight.numpy(), bn.bias.numpy())
+        cb = torch.randn(5)
+        for bn_first in (False, True):
+            for pool in (False, True):
+                for pad, reflect in [(0, True), (1, True), (1, False)]:
+                    xb = x + cb[None, :, None, None]
+                    ref = torch.relu(bn(xb)) if bn_first else bn(torch.relu(xb))
+                    if pool:
+                        ref = torch.nn.functional.max_pool2d(ref, 2, 2)
+                    if pad:
+                        ref = (torch.nn.ReflectionPad2d(1) if reflect else torch.nn.ZeroPad2d(1))(ref)
+                    got = oracle.relu_bn_pad(x.numpy(), *args, conv_bias=cb.numpy(), bn_first=bn_first, pool=pool, pad=pad, reflect=reflect)
+                    np.testing.assert_allclose(got, ref.numpy(), rtol=2e-6, atol=2e-6)
+            for in_reflect in (True, False):
+                for pad, out_reflect in [(0, True), (1, True), (1, False)]:
+                    y = conv((torch.nn.ReflectionPad2d(1) if in_reflect else torch.nn.ZeroPad2d(1))(img))
+                    ref = torch.relu(bn(y)) if bn_first else bn(torch.relu(y))
+                    if pad:
+                        ref = (torch.nn.ReflectionPad2d(1) if out_reflect else torch.nn.ZeroPad2d(1))(ref)
+                    got = oracle.conv1_relu_bn_pad(img.numpy(), conv.weight.numpy(), conv.bias.numpy(), *args, bn_first=bn_first,
+                                                   in_reflect=in_reflect, pad=pad, out_reflect=out_reflect)
+                    np.testing.assert_allclose(got, ref.numpy(), rtol=1e-5, atol=1e-5)
