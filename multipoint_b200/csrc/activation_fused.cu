@@ -208,20 +208,31 @@ conv1_relu_bn_pad_kernel(const float *__restrict__ img, float *__restrict__ out,
         }
     }
     float *dst = out + ((size_t)b * C * Hp + yo) * Wp;
+    // the four columns as two packed pairs: fma.rn.f32x2 does two of the 9-tap MACs per instruction (the kernel is
+    // bound by instruction issue, not by the 5.4 GB it writes); per-lane results are the same IEEE fmas
+    float2 p2[C1_PX / 2][9];
+#pragma unroll
+    for (int h = 0; h < C1_PX / 2; ++h)
+#pragma unroll
+        for (int k = 0; k < 9; ++k) p2[h][k] = make_float2(patch[2 * h][k], patch[2 * h + 1][k]);
 #pragma unroll 4
     for (int c = 0; c < C; ++c) {
         const float4 w0 = *reinterpret_cast<const float4 *>(c1_smem + c * 12);
         const float4 w1 = *reinterpret_cast<const float4 *>(c1_smem + c * 12 + 4);
         const float4 w2 = *reinterpret_cast<const float4 *>(c1_smem + c * 12 + 8);  // w[8], conv bias, scale, shift
+        const float wk[9] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w2.x};
 #pragma unroll
-        for (int j = 0; j < C1_PX; ++j) {
-            float acc = patch[j][0] * w0.x;
-            acc = fmaf(patch[j][1], w0.y, acc); acc = fmaf(patch[j][2], w0.z, acc); acc = fmaf(patch[j][3], w0.w, acc);
-            acc = fmaf(patch[j][4], w1.x, acc); acc = fmaf(patch[j][5], w1.y, acc); acc = fmaf(patch[j][6], w1.z, acc);
-            acc = fmaf(patch[j][7], w1.w, acc); acc = fmaf(patch[j][8], w2.x, acc);
-            float v = af_apply(acc, w2.y, w2.z, w2.w, bn_first);
-            if (zero_px[j]) v = 0.f;
-            if (live[j]) dst[(size_t)c * Hp * Wp + threadIdx.x + j * C1_THREADS] = v;
+        for (int h = 0; h < C1_PX / 2; ++h) {
+            float2 acc = make_float2(p2[h][0].x * wk[0], p2[h][0].y * wk[0]);
+#pragma unroll
+            for (int k = 1; k < 9; ++k) acc = __ffma2_rn(p2[h][k], make_float2(wk[k], wk[k]), acc);
+            float v0 = af_apply(acc.x, w2.y, w2.z, w2.w, bn_first);
+            float v1 = af_apply(acc.y, w2.y, w2.z, w2.w, bn_first);
+            if (zero_px[2 * h]) v0 = 0.f;
+            if (zero_px[2 * h + 1]) v1 = 0.f;
+            float *d = dst + (size_t)c * Hp * Wp + threadIdx.x;
+            if (live[2 * h]) d[(2 * h) * C1_THREADS] = v0;
+            if (live[2 * h + 1]) d[(2 * h + 1) * C1_THREADS] = v1;
         }
     }
 }
