@@ -40,6 +40,14 @@ def _worker(rank, world, port, q):
     want_H, want_m = utils.sample_adaptation_homographies((32, 40), cfg)
     np.testing.assert_array_equal(Hs, want_H)
     np.testing.assert_array_equal(masks, want_m)
+    # 2b. without masks only the 3x3 matrices travel (each rank rasters its own share of the masks on its GPU)
+    def sample_no_masks():
+        np.random.seed(7)
+        return utils.sample_adaptation_homographies((32, 40), cfg, with_masks=False)
+
+    Hs2, none = parallel.broadcast_homographies(sample_no_masks)
+    assert none is None
+    np.testing.assert_array_equal(Hs2, want_H)
     # 3. the two accumulators of sharded adaptation: per-rank partial sums all-reduce to the total
     rng = np.random.default_rng(3)
     contrib = rng.random((4, 2, 8, 8)).astype(np.float32)       # one term per sampled homography
