@@ -23,6 +23,8 @@ _CHANNELS = {0: ([1, 64, 64, 128, 128], None), 1: ([1, 32, 64, 96, 128], 'desc')
 
 
 class MultiPoint(nn.Module):
+    # tests set this to walk the fused path on the CPU with ops.relu_bn_pad / ops.conv1_relu_bn_pad replaced by the oracle
+    _glue_on_any_device = False
     default_config = {
         'multispectral': True,
         'descriptor_head': True,
@@ -119,7 +121,7 @@ class MultiPoint(nn.Module):
         ReLU -> BatchNorm [-> MaxPool] [-> pad] chain after every 3x3 convolution runs as one pass
         (ops.relu_bn_pad) instead of three or four full-tensor elementwise kernels; the convolutions are the same
         cuDNN calls.  Anything that does not match that pattern, and every other mode, goes through the modules."""
-        if (self.training or torch.is_grad_enabled() or not x.is_cuda or x.dtype != torch.float32
+        if (self.training or torch.is_grad_enabled() or not (x.is_cuda or self._glue_on_any_device) or x.dtype != torch.float32
                 or self.config['mixed_precision'] or torch.is_autocast_enabled()):
             return seq(x)
         pads = (nn.ReflectionPad2d, nn.ZeroPad2d)

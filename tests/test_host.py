@@ -174,3 +174,53 @@ def test_synthetic_inputs_are_reproducible():
     np.testing.assert_allclose(np.linalg.norm(d2, axis=1), 1.0, atol=1e-6)
     batch = syn.image_pair_batch(2, 3, 32, 40)
     assert batch['optical']['image'].shape == (3, 1, 32, 40) and batch['thermal']['is_optical'].sum() == 0
+
+
+def test_fused_glue_walker_on_cpu_with_oracle_kernels(monkeypatch):
+    """models.MultiPoint._run replaces ReLU / BatchNorm / MaxPool / pad (and the first layer) by fused kernels in
+    inference.  The CUDA kernels are checked on the GPU; here the *walker* -- which modules it fuses, which pad mode
+    and pooling it passes on, that nothing is applied twice or skipped -- runs on the CPU for every block layout,
+    with the two kernels replaced by the oracle's restatements, against the plain module-by-module forward."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import oracle
+    from multipoint_b200 import models, ops
+
+    def unfold(scale, shift):   # the walker passes the folded affine; the oracle takes BatchNorm parameters
+        C = scale.numel()
+        return dict(mean=np.zeros(C, np.float32), var=np.ones(C, np.float32), eps=0.0, weight=scale.numpy(), bias=shift.numpy())
+
+    def fake_glue(x, scale, shift, bn_first=False, pool=False, pad=1, reflect=True, conv_bias=None):
+        return torch.from_numpy(oracle.relu_bn_pad(x.numpy(), conv_bias=None if conv_bias is None else conv_bias.numpy(), bn_first=bn_first,
+                                                   pool=pool, pad=pad, reflect=reflect, **unfold(scale, shift)))
+
+    def fake_conv1(image, weight, conv_bias, scale, shift, bn_first=False, in_reflect=True, pad=1, out_reflect=True):
+        return torch.from_numpy(oracle.conv1_relu_bn_pad(image.numpy(), weight.numpy(), None if conv_bias is None else conv_bias.numpy(),
+                                                         bn_first=bn_first, in_reflect=in_reflect, pad=pad, out_reflect=out_reflect,
+                                                         **unfold(scale, shift)))
+
+    monkeypatch.setattr(ops, "relu_bn_pad", fake_glue)
+    monkeypatch.setattr(ops, "conv1_relu_bn_pad", fake_conv1)
+    monkeypatch.setattr(models.MultiPoint, "_glue_on_any_device", True)
+    for cfg in ({'multispectral': True, 'descriptor_size': 32},
+                {'multispectral': False, 'descriptor_size': 16, 'bn_first': True},
+                {'multispectral': False, 'descriptor_size': 16, 'reflection_pad': False},
+                {'multispectral': False, 'descriptor_size': 16, 'double_convolution': False},
+                {'multispectral': False, 'descriptor_size': 16, 'final_batchnorm': False, 'channel_version': 1}):
+        torch.manual_seed(2)
+        net = models.MultiPoint(dict(cfg)).eval()
+        with torch.no_grad():
+            for m in net.modules():          # non-trivial BatchNorm statistics
+                if isinstance(m, torch.nn.BatchNorm2d):
+                    m.running_mean.normal_(std=0.2); m.running_var.uniform_(0.5, 2.0); m.weight.uniform_(0.5, 1.5); m.bias.normal_(std=0.2)
+            img = torch.rand(2, 1, 32, 40)
+            data = {'image': img, 'is_optical': torch.tensor([[1], [0]], dtype=torch.bool)}
+            x_fused = net.encode(data)
+            fl, fr = net.backbone_outputs(data)
+        with torch.enable_grad():            # autograd on -> the module path
+            x_mod = net.encode(data).detach()
+            ml, mr = net.backbone_outputs(data)
+        np.testing.assert_allclose(x_fused.numpy(), x_mod.numpy(), rtol=1e-4, atol=1e-5, err_msg=str(cfg))
+        np.testing.assert_allclose(fl.numpy(), ml.detach().numpy(), rtol=1e-3, atol=1e-4, err_msg=str(cfg))
+        np.testing.assert_allclose(fr.numpy(), mr.detach().numpy(), rtol=1e-3, atol=1e-4, err_msg=str(cfg))
