@@ -22,6 +22,11 @@ from .utils import dict_update
 _CHANNELS = {0: ([1, 64, 64, 128, 128], None), 1: ([1, 32, 64, 96, 128], 'desc'), 2: ([1, 8, 16, 32, 64], 'desc')}
 
 
+def _drop_folded_when_training(bn, _inputs):
+    if bn.training:
+        bn.__dict__.pop('_mp_folded', None)
+
+
 class MultiPoint(nn.Module):
     # tests set this to walk the fused path on the CPU with ops.relu_bn_pad / ops.conv1_relu_bn_pad replaced by the oracle
     _glue_on_any_device = False
@@ -73,10 +78,18 @@ class MultiPoint(nn.Module):
             print('MultiPoint number of trainable parameter: ' + str(sum(p.numel() for p in self.parameters())))
 
     # ------------------------------------------------------------------ construction helpers
+    @staticmethod
+    def _batchnorm(N):
+        """BatchNorm2d whose cached eval-mode affine (``_folded_bn``) is dropped by every training-mode forward: that
+        forward rewrites running_mean / running_var without bumping the tensors' version counters."""
+        bn = nn.BatchNorm2d(N)
+        bn.register_forward_pre_hook(_drop_folded_when_training)
+        return bn
+
     def getNonlinearity(self, N):
         if self.config['bn_first']:
-            return nn.BatchNorm2d(N), nn.ReLU(True)
-        return nn.ReLU(True), nn.BatchNorm2d(N)
+            return self._batchnorm(N), nn.ReLU(True)
+        return nn.ReLU(True), self._batchnorm(N)
 
     def getConvolutionBlock(self, N_in, N_out):
         block = [self.pad_method(1), nn.Conv2d(N_in, N_out, 3), *self.getNonlinearity(N_out)]
@@ -97,14 +110,16 @@ class MultiPoint(nn.Module):
         layers = [self.pad_method(1), nn.Conv2d(self.n_channels[4], self.head_channels, 3),
                   *self.getNonlinearity(self.head_channels), nn.Conv2d(self.head_channels, out_channels, 1)]
         if self.config['final_batchnorm']:
-            layers.append(nn.BatchNorm2d(out_channels))
+            layers.append(self._batchnorm(out_channels))
         return nn.Sequential(*layers)
 
     # ------------------------------------------------------------------ fused inference path
     @staticmethod
     def _folded_bn(bn):
         """Eval-mode BatchNorm as a per-channel affine (scale, shift); cached on the module until a parameter or
-        buffer changes (in-place updates such as load_state_dict bump the tensors' version counters)."""
+        buffer changes: in-place updates such as load_state_dict bump the tensors' version counters, and a
+        training-mode forward (which updates the running statistics without bumping them) drops the cache through
+        the module's forward-pre hook (``_batchnorm``)."""
         ver = (bn.weight._version, bn.bias._version, bn.running_mean._version, bn.running_var._version,
                bn.weight.data_ptr(), bn.running_var.data_ptr())
         hit = getattr(bn, '_mp_folded', None)

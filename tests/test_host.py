@@ -224,3 +224,35 @@ def test_fused_glue_walker_on_cpu_with_oracle_kernels(monkeypatch):
         np.testing.assert_allclose(x_fused.numpy(), x_mod.numpy(), rtol=1e-4, atol=1e-5, err_msg=str(cfg))
         np.testing.assert_allclose(fl.numpy(), ml.detach().numpy(), rtol=1e-3, atol=1e-4, err_msg=str(cfg))
         np.testing.assert_allclose(fr.numpy(), mr.detach().numpy(), rtol=1e-3, atol=1e-4, err_msg=str(cfg))
+
+
+def test_folded_batchnorm_cache_follows_training_mode_updates():
+    """a training-mode forward rewrites running_mean / running_var without bumping the tensors' version
+    counters, so an affine folded during an earlier eval forward must not survive it."""
+    import torch
+    from multipoint_b200 import models
+    from multipoint_b200.pipeline import calibrate_random_init
+
+    torch.manual_seed(0)
+    net = models.MultiPoint({'multispectral': False, 'descriptor_size': 16}).eval()
+    bns = [m for m in net.modules() if isinstance(m, torch.nn.BatchNorm2d)]
+    before = [tuple(t.clone() for t in models.MultiPoint._folded_bn(m)) for m in bns]   # what an eval forward caches
+    assert all('_mp_folded' in m.__dict__ for m in bns)
+    calibrate_random_init(net, torch.rand(2, 1, 32, 40))       # train-mode forward with momentum 1
+    assert not net.training
+    changed = 0
+    for m, (s0, b0) in zip(bns, before):
+        scale, shift = models.MultiPoint._folded_bn(m)
+        want = m.weight.detach() / torch.sqrt(m.running_var + m.eps)
+        torch.testing.assert_close(scale, want, rtol=1e-6, atol=0)
+        torch.testing.assert_close(shift, m.bias.detach() - m.running_mean * want, rtol=1e-5, atol=1e-7)
+        changed += int(not torch.equal(scale, s0))
+    assert changed == len(bns)
+    # a BatchNorm put into training mode on its own (not through the parent) is covered as well
+    bn = bns[0]
+    models.MultiPoint._folded_bn(bn)
+    bn.train()
+    bn(torch.randn(2, bn.num_features, 4, 4) * 3 + 1)
+    bn.eval()
+    scale, _ = models.MultiPoint._folded_bn(bn)
+    torch.testing.assert_close(scale, bn.weight.detach() / torch.sqrt(bn.running_var + bn.eps), rtol=1e-6, atol=0)
