@@ -825,6 +825,7 @@ MatchLayout::MatchLayout(int P, int N1, int N2, int D) {
     mid1 = take(sizeof(__nv_bfloat16) * r1 * D);
     hi2 = take(sizeof(__nv_bfloat16) * r2 * D);
     mid2 = take(sizeof(__nv_bfloat16) * r2 * D);
+    colpart = take(match_colpart_bytes(P, N1, N2));
     total = off;
 }
 
@@ -860,9 +861,10 @@ static int run_nearest(const float *d1, const int32_t *n1, int N1, const float *
     MP_LAUNCH_OK_S("match_prep_vec_kernel", s);
 
     if (tensor) {
-        int rc = match_top2_tensor(hi1, mid1, n1, N1, hi2, mid2, n2, N2, P, D, norms2, use_bias, max1, max2, top12, s);
-        if (rc != MP_OK) return rc;
-        rc = match_top2_tensor(hi2, mid2, n2, N2, hi1, mid1, n1, N1, P, D, norms1, use_bias, max2, max1, top21, s);
+        // one GEMM per pair: rows of set 1 against set 2 (top12) and, from the same accumulators, the columns' view
+        // = rows of set 2 against set 1 (top21)
+        int rc = match_top2_tensor(hi1, mid1, n1, N1, hi2, mid2, n2, N2, P, D, norms1, norms2, use_bias, max1, max2, top12, top21,
+                                   ws + L.colpart, s);
         if (rc != MP_OK) return rc;
     } else {
         dim3 g1((N1 + ST_ROWS - 1) / ST_ROWS, P), g2((N2 + ST_ROWS - 1) / ST_ROWS, P);

@@ -45,14 +45,17 @@ constexpr float MATCH_PACK_REL = 3.8147e-6f;  // 2^-18
 constexpr float MATCH_EPS_SIMT = 4e-5f;
 
 struct MatchLayout {
-    size_t scalars, row_part_key, row_part_idx, norms1, norms2, top12, top21, idx12, idx21, flagged1, flagged2, pairs1, pairs2, train_tmp, dist_tmp, hi1, mid1, hi2, mid2, total;
+    size_t scalars, row_part_key, row_part_idx, norms1, norms2, top12, top21, idx12, idx21, flagged1, flagged2, pairs1, pairs2, train_tmp, dist_tmp, hi1, mid1, hi2, mid2, colpart, total;
     MatchLayout(int P, int N1, int N2, int D);
 };
 
-// match_tc.cu: rows of A (hi/mid bf16 planes, (P,NA,D)) against rows of B; writes top[(P,NA)].
+// match_tc.cu: rows of A (hi/mid bf16 planes, (P,NA,D)) against rows of B; writes top[(P,NA)] and, when top_cols is
+// given, the column side top_cols[(P,NB)] (rows of B against rows of A) from the same GEMM.  colpart: workspace of
+// match_colpart_bytes(P, NA, NB) for the per-chunk column records.
+size_t match_colpart_bytes(int P, int NA, int NB);
 int match_top2_tensor(const __nv_bfloat16 *a_hi, const __nv_bfloat16 *a_mid, const int32_t *na, int NA,
                       const __nv_bfloat16 *b_hi, const __nv_bfloat16 *b_mid, const int32_t *nb, int NB, int P, int D,
-                      const float *norms_b, int use_bias, const unsigned *max_a, const unsigned *max_b, Top2 *top,
-                      cudaStream_t stream);
+                      const float *norms_a, const float *norms_b, int use_bias, const unsigned *max_a, const unsigned *max_b,
+                      Top2 *top, Top2 *top_cols, void *colpart, cudaStream_t stream);
 
 }  // namespace mp

@@ -17,8 +17,13 @@
 //   - warp 1: one elect.sync thread issues tcgen05.mma (M=128, N=128, K=16, kind::f16, A from TMEM, B from
 //     shared memory) into one of two 128-column TMEM accumulators; tcgen05.commit releases the ring stage /
 //     publishes the tile
-// The only global traffic is the bf16 operands (B re-read once per 128-row block, from L2) and
-// 20 B of result per row.
+// Both directions come out of the one GEMM (matching.py:53-60: argmin over axis 1 and axis 0 of the same
+// distance matrix): a thread owns one row of the accumulator, so the row side is an in-thread running arg-top-3;
+// for the column side the 32 rows a warp holds of one column are reduced with two warp-collective reductions
+// (redux.sync -> CREDUX): the packed maximum, and the gap to the runner-up.  Each (32-row chunk, column) leaves
+// 8 bytes; match_colmerge_kernel folds the chunks of a column into the same Top2 record the row side writes.
+// The only global traffic is the bf16 operands (B re-read once per 128-row block, from L2), 20 B of result
+// per row and 8 B per (32-row chunk, column).
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -158,19 +163,22 @@ struct TcSmem {
     static constexpr uint32_t A_BYTES = ATM ? 0u : 2u * KB * TC_TILE_BYTES;
     static constexpr uint32_t B_STAGE_BYTES = 2u * TC_TILE_BYTES;
     static constexpr uint32_t B_OFF = A_BYTES;
-    static constexpr uint32_t BAR_OFF = B_OFF + B_STAGES * B_STAGE_BYTES;
+    static constexpr uint32_t BAR_OFF = B_OFF + B_STAGES * B_STAGE_BYTES;  // multiple of 1024
     static constexpr int NUM_BARS = 1 + 2 * B_STAGES + 2 * ACC_STAGES;
-    static constexpr uint32_t TOTAL = BAR_OFF + NUM_BARS * 8 + 16 + 1024;  // + tmem ptr + alignment slack
+    static constexpr uint32_t BIAS_OFF = (BAR_OFF + NUM_BARS * 8 + 16 + 15) & ~15u;  // after the barriers and the tmem pointer
+    static constexpr uint32_t BIAS_BYTES = TC_EPI_WARPS * 64 * 4;          // per epilogue warp: its 2 x 32 column terms of a tile
+    static constexpr uint32_t TOTAL = BIAS_OFF + BIAS_BYTES + 1024;        // + alignment slack
 };
 
-template <int KB, bool ATM>
+template <int KB, bool ATM, bool COLS>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 match_top2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_mid,
                      const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_mid,
                      const __nv_bfloat16 *__restrict__ a_hi_ptr, const __nv_bfloat16 *__restrict__ a_mid_ptr,
                      const int32_t *__restrict__ na, int NA, const int32_t *__restrict__ nb, int NB,
-                     const float *__restrict__ norms_b, int use_bias, const unsigned *__restrict__ max_a,
-                     const unsigned *__restrict__ max_b, Top2 *__restrict__ top) {
+                     const float *__restrict__ norms_a, const float *__restrict__ norms_b, int use_bias,
+                     const unsigned *__restrict__ max_a, const unsigned *__restrict__ max_b, Top2 *__restrict__ top,
+                     uint2 *__restrict__ colpart, int RC, int NBP) {
     using L = TcSmem<KB, ATM>;
     constexpr int S = L::B_STAGES;
     constexpr int ACC = L::ACC_STAGES;
@@ -330,6 +338,14 @@ match_top2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
         const float ma = __uint_as_float(max_a[p]), mb = __uint_as_float(max_b[p]);
         const float C = 1.002f * ma * mb + (use_bias ? 0.5f * mb * mb : 0.f) + 1e-30f;
         const float *bias = norms_b + (size_t)p * NB;
+        // column side (COLS): key of (row i, column j) as seen from column j is a.b - |a_i|^2/2 (L2) or a.b (NN),
+        // shifted by CC > 0; the row's own term is a per-thread constant.  Rows beyond n_a never win (mask 0).
+        const float CC = 1.002f * ma * mb + (use_bias ? 0.5f * ma * ma : 0.f) + 1e-30f;
+        const bool row_ok = m0 + row < n_a;
+        const float add_row = (COLS && use_bias && row_ok) ? fmaf(-0.5f, __ldg(norms_a + (size_t)p * NA + m0 + row), CC) : CC;
+        const uint32_t cmask = row_ok ? ~31u : 0u, ccode = row_ok ? (uint32_t)(31 - lane) : 0u;
+        uint2 *cdst = COLS ? colpart + ((size_t)p * RC + (m0 >> 5) + quarter) * NBP + lane : nullptr;
+        float *sbias = reinterpret_cast<float *>(smem_raw + (base + L::BIAS_OFF - smem_u32(smem_raw))) + (warp - 2) * 64;
         uint32_t best = 0, second = 0, third = 0;  // packed keys; 0 = nothing yet
         int best_chunk = -1, second_chunk = -1;  // global chunk index (32 columns each)
         for (int nt = 0; nt < n_tiles; ++nt) {
@@ -355,33 +371,48 @@ match_top2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
             if (have1) tc_ld32(tbase + (uint32_t)(c1 * 32), vb);
             tc_ld_wait();
             tc_fence_before();
-            __syncwarp();
+            __syncwarp();   // also: every lane is done reading the previous tile's column terms
             if (lane == 0) mbar_arrive(bar_acc_empty(t));
+            if (use_bias) {
+                // the 2 x 32 column terms of this tile, one per lane, become warp-visible through shared memory:
+                // four columns per broadcast LDS.128 instead of one SHFL per element
+                sbias[lane] = add_lane0;
+                sbias[32 + lane] = add_lane1;
+                __syncwarp();
+            }
 
-            auto process = [&](const uint32_t (&v)[32], int col0, float add_lane) {
+            auto process = [&](const uint32_t (&v)[32], int col0, const float *sb) {
                 const bool full = col0 + 32 <= n_b;
                 // sorted triples (b >= s >= t) in four independent accumulators for ILP
                 uint32_t b4[4] = {0, 0, 0, 0}, s4[4] = {0, 0, 0, 0}, t4[4] = {0, 0, 0, 0};
-                if (full) {  // warp-uniform: the per-element bound check only runs on a ragged last chunk
+                uint32_t keep_m = 0, keep_g = 0;   // lane j keeps column j's (maximum, gap to the runner-up - 1)
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float add = use_bias ? __shfl_sync(0xffffffffu, add_lane, j) : C;
-                        const uint32_t x = (__float_as_uint(__uint_as_float(v[j]) + add) & ~31u) | (uint32_t)(31 - j);
-                        t4[j & 3] = max(t4[j & 3], min(x, s4[j & 3]));
-                        s4[j & 3] = max(s4[j & 3], min(x, b4[j & 3]));
-                        b4[j & 3] = max(b4[j & 3], x);
+                for (int j4 = 0; j4 < 32; j4 += 4) {
+                    float add4[4] = {C, C, C, C};
+                    if (use_bias) {
+                        const float4 q = *reinterpret_cast<const float4 *>(sb + j4);
+                        add4[0] = q.x; add4[1] = q.y; add4[2] = q.z; add4[3] = q.w;
                     }
-                } else {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float add = use_bias ? __shfl_sync(0xffffffffu, add_lane, j) : C;
-                        uint32_t x = (__float_as_uint(__uint_as_float(v[j]) + add) & ~31u) | (uint32_t)(31 - j);
-                        if (col0 + j >= n_b) x = 0;
+                    for (int jj = 0; jj < 4; ++jj) {
+                        const int j = j4 + jj;
+                        const float val = __uint_as_float(v[j]);
+                        const float fr = val + add4[jj];
+                        uint32_t x = (__float_as_uint(fr) & ~31u) | (uint32_t)(31 - j);
+                        if (!full && col0 + j >= n_b) x = 0;   // warp-uniform: only a ragged last chunk pays for the bound check
                         t4[j & 3] = max(t4[j & 3], min(x, s4[j & 3]));
                         s4[j & 3] = max(s4[j & 3], min(x, b4[j & 3]));
                         b4[j & 3] = max(b4[j & 3], x);
+                        if (COLS) {
+                            const float fc = use_bias ? val + add_row : fr;   // NN: CC == C, one add serves both sides
+                            const uint32_t xc = (__float_as_uint(fc) & cmask) | ccode;
+                            const uint32_t m = __reduce_max_sync(0xffffffffu, xc);
+                            const uint32_t g = __reduce_min_sync(0xffffffffu, m - xc - 1u);   // the winner wraps to 0xffffffff
+                            if (lane == j) { keep_m = m; keep_g = g; }
+                        }
                     }
                 }
+                if (COLS) cdst[col0] = make_uint2(keep_m, keep_g);   // 256 B per warp, coalesced; columns >= n_b are padding
                 // k-th largest of two sorted triples: second = max(s, s', min(b, b')),
                 // third = max(t, t', min(s, b'), min(b, s'))
                 auto merge3 = [](uint32_t &b, uint32_t &s_, uint32_t &t_, uint32_t b2, uint32_t s2, uint32_t t2) {
@@ -400,8 +431,8 @@ match_top2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
                 if (best != old_best) best_chunk = chunk;
                 if (second != old_second) second_chunk = (second == old_best && best != old_best) ? old_best_chunk : chunk;
             };
-            if (have0) process(va, n0 + c0 * 32, add_lane0);
-            if (have1) process(vb, n0 + c1 * 32, add_lane1);
+            if (have0) process(va, n0 + c0 * 32, sbias);
+            if (have1) process(vb, n0 + c1 * 32, sbias + 32);
         }
         // merge the two column subsets of each row (operand smem is free: every MMA has completed)
         uint32_t *mrg = reinterpret_cast<uint32_t *>(smem_raw + (base - smem_u32(smem_raw)));
@@ -485,24 +516,72 @@ static int make_operand_map(CUtensorMap *map, const __nv_bfloat16 *ptr, int P, i
     return MP_OK;
 }
 
-template <int KB, bool ATM>
+// ---------------------------------------------------------------- column side: fold the 32-row chunks
+// One thread per column j of pair p: the chunk records (maximum m, gap g) give the chunk's two best packed keys
+// m and m - g - 1 (low 5 bits = 31 - row inside the chunk).  The chunk's third key is unknown but not larger than
+// its second, so the second is entered twice: a near-tie whose best and second share a chunk is then classified
+// for the full exact rescan (conservative), every other case is exact.
+__global__ void __launch_bounds__(256)
+match_colmerge_kernel(const uint2 *__restrict__ colpart, int RC, int NBP, const int32_t *__restrict__ na, int NA,
+                      const int32_t *__restrict__ nb, int NB, int use_bias, const unsigned *__restrict__ max_a,
+                      const unsigned *__restrict__ max_b, Top2 *__restrict__ top_cols) {
+    const int p = blockIdx.y, j = blockIdx.x * 256 + threadIdx.x;
+    if (j >= NB) return;
+    const int n_a = na ? min(na[p], NA) : NA, n_b = nb ? min(nb[p], NB) : NB;
+    Top2 out = top2_empty();
+    if (j < n_b && n_a > 0) {
+        const float ma = __uint_as_float(max_a[p]), mb = __uint_as_float(max_b[p]);
+        const float CC = 1.002f * ma * mb + (use_bias ? 0.5f * ma * ma : 0.f) + 1e-30f;
+        const uint2 *src = colpart + (size_t)p * RC * NBP + j;
+        const int chunks = (n_a + 31) >> 5;
+        uint32_t b = 0, s = 0, t = 0;
+        int bc = -1, sc = -1;
+        auto insert = [&](uint32_t x, int c, bool indexed) {
+            if (x > b) { t = s; s = b; sc = bc; b = x; bc = c; }
+            else if (x > s) { t = s; s = x; sc = indexed ? c : -2; }
+            else if (x > t) t = x;
+        };
+        uint2 nx = __ldg(src);
+        for (int c = 0; c < chunks; ++c) {
+            const uint2 cur = nx;
+            if (c + 1 < chunks) nx = __ldg(src + (size_t)(c + 1) * NBP);
+            if (cur.x == 0) continue;
+            const uint32_t k2 = cur.x - cur.y - 1u;
+            insert(cur.x, c, true);
+            if (k2 != 0) { insert(k2, c, true); insert(k2, c, false); }
+        }
+        // equal packed keys cannot occur inside a chunk (distinct row codes); across chunks the strict '>' keeps the
+        // earlier chunk = the lower row index, and such ties are inside the recheck margin anyway
+        if (bc >= 0) { out.best_idx = bc * 32 + 31 - (int)(b & 31u); out.best = __uint_as_float(b & ~31u) - CC; }
+        if (sc >= 0) { out.second_idx = sc * 32 + 31 - (int)(s & 31u); out.second = __uint_as_float(s & ~31u) - CC; }
+        if (t != 0) out.third = __uint_as_float(t & ~31u) - CC;
+    }
+    top_cols[(size_t)p * NB + j] = out;
+}
+
+template <int KB, bool ATM, bool COLS>
 static int launch_tc(const CUtensorMap &ah, const CUtensorMap &am, const CUtensorMap &bh, const CUtensorMap &bm,
                      const __nv_bfloat16 *a_hi, const __nv_bfloat16 *a_mid, const int32_t *na, int NA,
-                     const int32_t *nb, int NB, int P, const float *norms_b, int use_bias, const unsigned *max_a,
-                     const unsigned *max_b, Top2 *top, cudaStream_t s) {
-    auto k = match_top2_tc_kernel<KB, ATM>;
+                     const int32_t *nb, int NB, int P, const float *norms_a, const float *norms_b, int use_bias,
+                     const unsigned *max_a, const unsigned *max_b, Top2 *top, uint2 *colpart, int RC, int NBP, cudaStream_t s) {
+    auto k = match_top2_tc_kernel<KB, ATM, COLS>;
     MP_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcSmem<KB, ATM>::TOTAL));
     dim3 grid((NA + TC_BM - 1) / TC_BM, P);
-    k<<<grid, TC_THREADS, TcSmem<KB, ATM>::TOTAL, s>>>(ah, am, bh, bm, a_hi, a_mid, na, NA, nb, NB, norms_b, use_bias,
-                                                        max_a, max_b, top);
+    k<<<grid, TC_THREADS, TcSmem<KB, ATM>::TOTAL, s>>>(ah, am, bh, bm, a_hi, a_mid, na, NA, nb, NB, norms_a, norms_b, use_bias,
+                                                        max_a, max_b, top, colpart, RC, NBP);
     MP_LAUNCH_OK_S("match_top2_tc_kernel", s);
     return MP_OK;
 }
 
+size_t match_colpart_bytes(int P, int NA, int NB) {
+    const size_t rc = 4 * (size_t)((NA + TC_BM - 1) / TC_BM), nbp = (size_t)((NB + TC_BN - 1) / TC_BN) * TC_BN;
+    return sizeof(uint2) * (size_t)P * rc * nbp;
+}
+
 int match_top2_tensor(const __nv_bfloat16 *a_hi, const __nv_bfloat16 *a_mid, const int32_t *na, int NA,
                       const __nv_bfloat16 *b_hi, const __nv_bfloat16 *b_mid, const int32_t *nb, int NB, int P, int D,
-                      const float *norms_b, int use_bias, const unsigned *max_a, const unsigned *max_b, Top2 *top,
-                      cudaStream_t stream) {
+                      const float *norms_a, const float *norms_b, int use_bias, const unsigned *max_a, const unsigned *max_b,
+                      Top2 *top, Top2 *top_cols, void *colpart, cudaStream_t stream) {
     if (D % 64 != 0 || D > 256 || D <= 0) {
         set_error("match_top2_tensor: D=%d must be a multiple of 64 and <= 256", D);
         return MP_ERR_UNSUPPORTED;
@@ -513,10 +592,19 @@ int match_top2_tensor(const __nv_bfloat16 *a_hi, const __nv_bfloat16 *a_mid, con
     if ((rc = make_operand_map(&am, a_mid, P, NA, D)) != MP_OK) return rc;
     if ((rc = make_operand_map(&bh, b_hi, P, NB, D)) != MP_OK) return rc;
     if ((rc = make_operand_map(&bm, b_mid, P, NB, D)) != MP_OK) return rc;
-    static const bool atm = !(getenv("MP_TC_A_SMEM") && atoi(getenv("MP_TC_A_SMEM")) == 1);  // tuning aid: 1 = A in smem
-#define MP_TC_LAUNCH(KB)                                                                                              \
-    return atm ? launch_tc<KB, true>(ah, am, bh, bm, a_hi, a_mid, na, NA, nb, NB, P, norms_b, use_bias, max_a, max_b, top, stream) \
-               : launch_tc<KB, false>(ah, am, bh, bm, a_hi, a_mid, na, NA, nb, NB, P, norms_b, use_bias, max_a, max_b, top, stream)
+    const int RC = 4 * ((NA + TC_BM - 1) / TC_BM), NBP = (NB + TC_BN - 1) / TC_BN * TC_BN;
+    uint2 *cp = (uint2 *)colpart;
+    const bool cols = top_cols != nullptr;
+    if (cols && cp == nullptr) {
+        set_error("match_top2_tensor: the column side needs its chunk buffer");
+        return MP_ERR_WORKSPACE;
+    }
+#define MP_TC_LAUNCH(KB)                                                                                                         \
+    rc = cols ? launch_tc<KB, true, true>(ah, am, bh, bm, a_hi, a_mid, na, NA, nb, NB, P, norms_a, norms_b, use_bias, max_a,     \
+                                          max_b, top, cp, RC, NBP, stream)                                                       \
+              : launch_tc<KB, true, false>(ah, am, bh, bm, a_hi, a_mid, na, NA, nb, NB, P, norms_a, norms_b, use_bias, max_a,    \
+                                           max_b, top, cp, RC, NBP, stream);                                                     \
+    break
     switch (D / 64) {
         case 1: MP_TC_LAUNCH(1);
         case 2: MP_TC_LAUNCH(2);
@@ -524,6 +612,11 @@ int match_top2_tensor(const __nv_bfloat16 *a_hi, const __nv_bfloat16 *a_mid, con
         default: MP_TC_LAUNCH(4);
     }
 #undef MP_TC_LAUNCH
+    if (rc != MP_OK || !cols) return rc;
+    dim3 grid((NB + 255) / 256, P);
+    match_colmerge_kernel<<<grid, 256, 0, stream>>>(cp, RC, NBP, na, NA, nb, NB, use_bias, max_a, max_b, top_cols);
+    MP_LAUNCH_OK_S("match_colmerge_kernel", stream);
+    return MP_OK;
 }
 
 }  // namespace mp
