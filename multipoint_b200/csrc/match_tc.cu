@@ -127,6 +127,33 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 // tcgen05.ld is asynchronous: the registers are valid only after this wait
 __device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// warp-collective minimum (SASS: CREDUX.MIN into a uniform register); volatile keeps the batches in source order
+__device__ __forceinline__ uint32_t warp_min_u32(uint32_t x) {
+    uint32_t r;
+    asm volatile("redux.sync.min.u32 %0, %1, 0xffffffff;" : "=r"(r) : "r"(x));
+    return r;
+}
+// (a & b) | c and its complement in one LOP3
+__device__ __forceinline__ uint32_t and_or(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+__device__ __forceinline__ uint32_t not_and_or(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0x15;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
 
 // UMMA shared-memory descriptor, K-major operand, 128-byte swizzle (cute::UMMA::SmemDescriptor):
 //   [0,14) start address >> 4   [16,30) leading byte offset >> 4 (=1, unused for swizzled K-major)
@@ -166,17 +193,19 @@ struct TcSmem {
     static constexpr uint32_t BAR_OFF = B_OFF + B_STAGES * B_STAGE_BYTES;  // multiple of 1024
     static constexpr int NUM_BARS = 1 + 2 * B_STAGES + 2 * ACC_STAGES;
     static constexpr uint32_t BIAS_OFF = (BAR_OFF + NUM_BARS * 8 + 16 + 15) & ~15u;  // after the barriers and the tmem pointer
-    static constexpr uint32_t BIAS_BYTES = TC_EPI_WARPS * 64 * 4;          // per epilogue warp: its 2 x 32 column terms of a tile
+    // per epilogue warp: the 2 x 32 column terms of a tile, double-buffered over tiles (512 B), and the (32 x 8 B)
+    // column records of a chunk, double-buffered over chunks (512 B)
+    static constexpr uint32_t BIAS_BYTES = TC_EPI_WARPS * 1024;
     static constexpr uint32_t TOTAL = BIAS_OFF + BIAS_BYTES + 1024;        // + alignment slack
 };
 
-template <int KB, bool ATM, bool COLS>
+template <int KB, bool ATM, bool COLS, bool BIAS>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 match_top2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_mid,
                      const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_mid,
                      const __nv_bfloat16 *__restrict__ a_hi_ptr, const __nv_bfloat16 *__restrict__ a_mid_ptr,
                      const int32_t *__restrict__ na, int NA, const int32_t *__restrict__ nb, int NB,
-                     const float *__restrict__ norms_a, const float *__restrict__ norms_b, int use_bias,
+                     const float *__restrict__ norms_a, const float *__restrict__ norms_b,
                      const unsigned *__restrict__ max_a, const unsigned *__restrict__ max_b, Top2 *__restrict__ top,
                      uint2 *__restrict__ colpart, int RC, int NBP) {
     using L = TcSmem<KB, ATM>;
@@ -336,103 +365,125 @@ match_top2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
             if (lane == 0) mbar_arrive(bar_a_full);
         }
         const float ma = __uint_as_float(max_a[p]), mb = __uint_as_float(max_b[p]);
-        const float C = 1.002f * ma * mb + (use_bias ? 0.5f * mb * mb : 0.f) + 1e-30f;
+        // row side: key of column j for this row = a.b + C (NN) or a.b - |b_j|^2/2 + C (L2); C > |smallest key| keeps it
+        // positive.  Columns beyond n_b get the term 0: their operand rows are zero, so their keys are < 32 = "nothing".
+        const float C = 1.002f * ma * mb + (BIAS ? 0.5f * mb * mb : 0.f) + 1e-30f;
         const float *bias = norms_b + (size_t)p * NB;
-        // column side (COLS): key of (row i, column j) as seen from column j is a.b - |a_i|^2/2 (L2) or a.b (NN),
-        // shifted by CC > 0; the row's own term is a per-thread constant.  Rows beyond n_a never win (mask 0).
-        const float CC = 1.002f * ma * mb + (use_bias ? 0.5f * ma * ma : 0.f) + 1e-30f;
+        // column side (COLS): key of this row as seen from column j = a.b + CC (NN) or a.b - |a_i|^2/2 + CC (L2): the row's
+        // own term is a per-thread constant.  Keys are complemented (smaller = closer) so that the winner and the gap to
+        // the runner-up both come out of a warp-collective minimum.  Rows beyond n_a carry the key ~0 and never win.
+        const float CC = 1.002f * ma * mb + (BIAS ? 0.5f * ma * ma : 0.f) + 1e-30f;
         const bool row_ok = m0 + row < n_a;
-        const float add_row = (COLS && use_bias && row_ok) ? fmaf(-0.5f, __ldg(norms_a + (size_t)p * NA + m0 + row), CC) : CC;
+        const float add_row = (COLS && BIAS && row_ok) ? fmaf(-0.5f, __ldg(norms_a + (size_t)p * NA + m0 + row), CC) : CC;
         const uint32_t cmask = row_ok ? ~31u : 0u, ccode = row_ok ? (uint32_t)(31 - lane) : 0u;
         uint2 *cdst = COLS ? colpart + ((size_t)p * RC + (m0 >> 5) + quarter) * NBP + lane : nullptr;
-        float *sbias = reinterpret_cast<float *>(smem_raw + (base + L::BIAS_OFF - smem_u32(smem_raw))) + (warp - 2) * 64;
-        uint32_t best = 0, second = 0, third = 0;  // packed keys; 0 = nothing yet
-        int best_chunk = -1, second_chunk = -1;  // global chunk index (32 columns each)
-        for (int nt = 0; nt < n_tiles; ++nt) {
-            const int t = nt % ACC;
-            const int n0 = nt * TC_BN;
-            // per-column additive term C (NN) or C - |b|^2/2 (L2), fetched before the wait so the load
-            // latency hides behind the MMAs of this tile (it showed up as 17 % of the stall samples)
-            float add_lane0 = C, add_lane1 = C;
-            if (use_bias) {
-                const int ca = n0 + half * 32 + lane, cb_ = ca + 64;
-                if (ca < n_b) add_lane0 = fmaf(-0.5f, __ldg(bias + ca), C);
-                if (cb_ < n_b) add_lane1 = fmaf(-0.5f, __ldg(bias + cb_), C);
-            }
-            mbar_wait(bar_acc_full(t), (nt / ACC) & 1);
-            tc_fence_after();
-            // both of this warp's chunks are pulled out of tensor memory first, then the accumulator
-            // stage is handed back to the MMA warp before any of the arg-top-3 arithmetic runs
-            uint32_t va[32], vb[32];
-            const int c0 = half, c1 = half + 2;
-            const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(t * TC_BN);
-            const bool have0 = n0 + c0 * 32 < n_b, have1 = n0 + c1 * 32 < n_b;
-            if (have0) tc_ld32(tbase + (uint32_t)(c0 * 32), va);
-            if (have1) tc_ld32(tbase + (uint32_t)(c1 * 32), vb);
-            tc_ld_wait();
-            tc_fence_before();
-            __syncwarp();   // also: every lane is done reading the previous tile's column terms
-            if (lane == 0) mbar_arrive(bar_acc_empty(t));
-            if (use_bias) {
-                // the 2 x 32 column terms of this tile, one per lane, become warp-visible through shared memory:
-                // four columns per broadcast LDS.128 instead of one SHFL per element
-                sbias[lane] = add_lane0;
-                sbias[32 + lane] = add_lane1;
-                __syncwarp();
-            }
+        uint8_t *wsm = smem_raw + (base + L::BIAS_OFF - smem_u32(smem_raw)) + (warp - 2) * 1024;
+        float *sbias = reinterpret_cast<float *>(wsm);            // [2 tiles][64]
+        uint4 *srec = reinterpret_cast<uint4 *>(wsm + 512);       // [2 chunks][16] = (m, g) of two columns each
+        const uint32_t keymask = ~31u + (uint32_t)(n_tiles >> 30);   // ~31 in a register: one LOP3 per key, code as immediate
 
-            auto process = [&](const uint32_t (&v)[32], int col0, const float *sb) {
-                const bool full = col0 + 32 <= n_b;
-                // sorted triples (b >= s >= t) in four independent accumulators for ILP
-                uint32_t b4[4] = {0, 0, 0, 0}, s4[4] = {0, 0, 0, 0}, t4[4] = {0, 0, 0, 0};
-                uint32_t keep_m = 0, keep_g = 0;   // lane j keeps column j's (maximum, gap to the runner-up - 1)
+        uint32_t best = 0, second = 0, third = 0;  // packed keys; < 32 = nothing yet
+        int best_chunk = -1, second_chunk = -1;    // global chunk index (32 columns each)
+        const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16);
+
+        // one 32-column chunk of this thread's accumulator row
+        auto process = [&](const uint32_t (&v)[32], int col0, const float *sb, uint4 *rec) {
+            // sorted triples (b >= s >= t) in two independent accumulators
+            uint32_t b2[2] = {0, 0}, s2[2] = {0, 0}, t2[2] = {0, 0};
 #pragma unroll
-                for (int j4 = 0; j4 < 32; j4 += 4) {
-                    float add4[4] = {C, C, C, C};
-                    if (use_bias) {
-                        const float4 q = *reinterpret_cast<const float4 *>(sb + j4);
-                        add4[0] = q.x; add4[1] = q.y; add4[2] = q.z; add4[3] = q.w;
-                    }
+            for (int j8 = 0; j8 < 32; j8 += 8) {
+                uint32_t nx[8];
+#pragma unroll
+                for (int j4 = j8; j4 < j8 + 8; j4 += 4) {
+                    const float4 q = *reinterpret_cast<const float4 *>(sb + j4);   // broadcast LDS.128
+                    const float add4[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
                     for (int jj = 0; jj < 4; ++jj) {
                         const int j = j4 + jj;
                         const float val = __uint_as_float(v[j]);
                         const float fr = val + add4[jj];
-                        uint32_t x = (__float_as_uint(fr) & ~31u) | (uint32_t)(31 - j);
-                        if (!full && col0 + j >= n_b) x = 0;   // warp-uniform: only a ragged last chunk pays for the bound check
-                        t4[j & 3] = max(t4[j & 3], min(x, s4[j & 3]));
-                        s4[j & 3] = max(s4[j & 3], min(x, b4[j & 3]));
-                        b4[j & 3] = max(b4[j & 3], x);
+                        const uint32_t x = and_or(__float_as_uint(fr), keymask, (uint32_t)(31 - j));
+                        t2[j & 1] = max(t2[j & 1], min(x, s2[j & 1]));
+                        s2[j & 1] = max(s2[j & 1], min(x, b2[j & 1]));
+                        b2[j & 1] = max(b2[j & 1], x);
                         if (COLS) {
-                            const float fc = use_bias ? val + add_row : fr;   // NN: CC == C, one add serves both sides
-                            const uint32_t xc = (__float_as_uint(fc) & cmask) | ccode;
-                            const uint32_t m = __reduce_max_sync(0xffffffffu, xc);
-                            const uint32_t g = __reduce_min_sync(0xffffffffu, m - xc - 1u);   // the winner wraps to 0xffffffff
-                            if (lane == j) { keep_m = m; keep_g = g; }
+                            const float fc = BIAS ? val + add_row : fr;   // NN: CC == C, one add serves both sides
+                            nx[j - j8] = not_and_or(__float_as_uint(fc), cmask, ccode);
                         }
                     }
                 }
-                if (COLS) cdst[col0] = make_uint2(keep_m, keep_g);   // 256 B per warp, coalesced; columns >= n_b are padding
-                // k-th largest of two sorted triples: second = max(s, s', min(b, b')),
-                // third = max(t, t', min(s, b'), min(b, s'))
-                auto merge3 = [](uint32_t &b, uint32_t &s_, uint32_t &t_, uint32_t b2, uint32_t s2, uint32_t t2) {
-                    const uint32_t nt = max(max(t_, t2), max(min(s_, b2), min(b, s2)));
-                    const uint32_t ns = max(max(s_, s2), min(b, b2));
-                    b = max(b, b2); s_ = ns; t_ = nt;
-                };
-                merge3(b4[0], s4[0], t4[0], b4[1], s4[1], t4[1]);
-                merge3(b4[2], s4[2], t4[2], b4[3], s4[3], t4[3]);
-                merge3(b4[0], s4[0], t4[0], b4[2], s4[2], t4[2]);
-                const uint32_t cb = b4[0], cs = s4[0];
-                const int chunk = col0 >> 5;
-                const uint32_t old_best = best, old_second = second;
-                const int old_best_chunk = best_chunk;
-                merge3(best, second, third, cb, cs, t4[0]);
-                if (best != old_best) best_chunk = chunk;
-                if (second != old_second) second_chunk = (second == old_best && best != old_best) ? old_best_chunk : chunk;
+                if (COLS) {
+                    // eight columns per batch: the eight winners first, then the eight gaps, so that the collectives'
+                    // latencies overlap instead of forming one dependent chain per column
+                    uint32_t m[8], g[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) m[k] = warp_min_u32(nx[k]);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) g[k] = warp_min_u32(nx[k] - m[k] - 1u);   // the winner wraps to 0xffffffff
+                    if (lane == 0) {
+#pragma unroll
+                        for (int k = 0; k < 8; k += 2) rec[(j8 + k) >> 1] = make_uint4(m[k], g[k], m[k + 1], g[k + 1]);
+                    }
+                }
+            }
+            if (COLS) {
+                __syncwarp();
+                cdst[col0] = reinterpret_cast<const uint2 *>(rec)[lane];   // 256 B per warp, coalesced; columns >= n_b are padding
+            }
+            // k-th largest of two sorted triples: second = max(s, s', min(b, b')),
+            // third = max(t, t', min(s, b'), min(b, s'))
+            auto merge3 = [](uint32_t &b, uint32_t &s_, uint32_t &t_, uint32_t bb, uint32_t ss, uint32_t tt) {
+                const uint32_t nt = max(max(t_, tt), max(min(s_, bb), min(b, ss)));
+                const uint32_t ns = max(max(s_, ss), min(b, bb));
+                b = max(b, bb); s_ = ns; t_ = nt;
             };
-            if (have0) process(va, n0 + c0 * 32, sbias);
-            if (have1) process(vb, n0 + c1 * 32, sbias + 32);
+            merge3(b2[0], s2[0], t2[0], b2[1], s2[1], t2[1]);
+            const int chunk = col0 >> 5;
+            const uint32_t old_best = best, old_second = second;
+            const int old_best_chunk = best_chunk;
+            merge3(best, second, third, b2[0], s2[0], t2[0]);
+            if (best != old_best) best_chunk = chunk;
+            if (second != old_second) second_chunk = (second == old_best && best != old_best) ? old_best_chunk : chunk;
+        };
+        // the 2 x 32 column terms of tile nt, one per lane, become warp-visible through shared memory
+        auto stage_terms = [&](int nt) {
+            const int ca = nt * TC_BN + half * 32 + lane, cb_ = ca + 64;
+            float a0 = 0.f, a1 = 0.f;
+            if (ca < n_b) a0 = BIAS ? fmaf(-0.5f, __ldg(bias + ca), C) : C;
+            if (cb_ < n_b) a1 = BIAS ? fmaf(-0.5f, __ldg(bias + cb_), C) : C;
+            float *dst = sbias + (nt & 1) * 64;
+            dst[lane] = a0;
+            dst[32 + lane] = a1;
+        };
+        // Software pipeline over the 2 * n_tiles chunks of this warp: the tcgen05.ld of chunk s+1 is in flight while chunk s
+        // is processed (tcgen05.wait::ld waits for every outstanding load, so it is issued right after the wait for chunk s).
+        uint32_t va[32], vb[32];
+        stage_terms(0);
+        mbar_wait(bar_acc_full(0), 0);
+        tc_fence_after();
+        tc_ld32(tlane + (uint32_t)(half * 32), va);
+        for (int nt = 0; nt < n_tiles; ++nt) {
+            const int t = nt % ACC;
+            const int n0 = nt * TC_BN;
+            const uint32_t tacc = tlane + (uint32_t)(t * TC_BN);
+            // ---- chunk 0 of the tile is in va (loading); start chunk 1 behind it
+            tc_ld_wait();
+            tc_ld32(tacc + (uint32_t)((half + 2) * 32), vb);
+            __syncwarp();   // the tile's column terms are visible; the previous chunk's records have been read
+            process(va, n0 + half * 32, sbias + (nt & 1) * 64, srec);
+            // ---- chunk 1: wait, hand the accumulator stage back, start the next tile's chunk 0
+            tc_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_acc_empty(t));
+            if (nt + 1 < n_tiles) {
+                stage_terms(nt + 1);
+                const int t1 = (nt + 1) % ACC;
+                mbar_wait(bar_acc_full(t1), ((nt + 1) / ACC) & 1);
+                tc_fence_after();
+                tc_ld32(tlane + (uint32_t)(t1 * TC_BN + half * 32), va);
+            }
+            process(vb, n0 + (half + 2) * 32, sbias + (nt & 1) * 64 + 32, srec + 16);
         }
         // merge the two column subsets of each row (operand smem is free: every MMA has completed)
         uint32_t *mrg = reinterpret_cast<uint32_t *>(smem_raw + (base - smem_u32(smem_raw)));
@@ -456,15 +507,15 @@ match_top2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
         if (half == 0 && m0 + row < NA) {
             Top2 out = top2_empty();
             if (m0 + row < n_a) {
-                if (best_chunk >= 0) {
+                if (best >= 32u) {
                     out.best_idx = best_chunk * 32 + 31 - (int)(best & 31u);
                     out.best = __uint_as_float(best & ~31u) - C;
                 }
-                if (second_chunk >= 0) {
+                if (second >= 32u) {
                     out.second_idx = second_chunk * 32 + 31 - (int)(second & 31u);
                     out.second = __uint_as_float(second & ~31u) - C;
                 }
-                if (third != 0) out.third = __uint_as_float(third & ~31u) - C;
+                if (third >= 32u) out.third = __uint_as_float(third & ~31u) - C;
             }
             top[(size_t)p * NA + m0 + row] = out;
         }
@@ -517,7 +568,7 @@ static int make_operand_map(CUtensorMap *map, const __nv_bfloat16 *ptr, int P, i
 }
 
 // ---------------------------------------------------------------- column side: fold the 32-row chunks
-// One thread per column j of pair p: the chunk records (maximum m, gap g) give the chunk's two best packed keys
+// One thread per column j of pair p: the chunk records (~maximum, gap g) give the chunk's two best packed keys
 // m and m - g - 1 (low 5 bits = 31 - row inside the chunk).  The chunk's third key is unknown but not larger than
 // its second, so the second is entered twice: a near-tie whose best and second share a chunk is then classified
 // for the full exact rescan (conservative), every other case is exact.
@@ -545,10 +596,11 @@ match_colmerge_kernel(const uint2 *__restrict__ colpart, int RC, int NBP, const 
         for (int c = 0; c < chunks; ++c) {
             const uint2 cur = nx;
             if (c + 1 < chunks) nx = __ldg(src + (size_t)(c + 1) * NBP);
-            if (cur.x == 0) continue;
-            const uint32_t k2 = cur.x - cur.y - 1u;
-            insert(cur.x, c, true);
-            if (k2 != 0) { insert(k2, c, true); insert(k2, c, false); }
+            const uint32_t k1 = ~cur.x;   // the kernel reduces complemented keys
+            if (k1 < 32u) continue;
+            const uint32_t k2 = k1 - cur.y - 1u;
+            insert(k1, c, true);
+            if (k2 >= 32u) { insert(k2, c, true); insert(k2, c, false); }
         }
         // equal packed keys cannot occur inside a chunk (distinct row codes); across chunks the strict '>' keeps the
         // earlier chunk = the lower row index, and such ties are inside the recheck margin anyway
@@ -559,15 +611,15 @@ match_colmerge_kernel(const uint2 *__restrict__ colpart, int RC, int NBP, const 
     top_cols[(size_t)p * NB + j] = out;
 }
 
-template <int KB, bool ATM, bool COLS>
+template <int KB, bool ATM, bool COLS, bool BIAS>
 static int launch_tc(const CUtensorMap &ah, const CUtensorMap &am, const CUtensorMap &bh, const CUtensorMap &bm,
                      const __nv_bfloat16 *a_hi, const __nv_bfloat16 *a_mid, const int32_t *na, int NA,
-                     const int32_t *nb, int NB, int P, const float *norms_a, const float *norms_b, int use_bias,
+                     const int32_t *nb, int NB, int P, const float *norms_a, const float *norms_b,
                      const unsigned *max_a, const unsigned *max_b, Top2 *top, uint2 *colpart, int RC, int NBP, cudaStream_t s) {
-    auto k = match_top2_tc_kernel<KB, ATM, COLS>;
+    auto k = match_top2_tc_kernel<KB, ATM, COLS, BIAS>;
     MP_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcSmem<KB, ATM>::TOTAL));
     dim3 grid((NA + TC_BM - 1) / TC_BM, P);
-    k<<<grid, TC_THREADS, TcSmem<KB, ATM>::TOTAL, s>>>(ah, am, bh, bm, a_hi, a_mid, na, NA, nb, NB, norms_a, norms_b, use_bias,
+    k<<<grid, TC_THREADS, TcSmem<KB, ATM>::TOTAL, s>>>(ah, am, bh, bm, a_hi, a_mid, na, NA, nb, NB, norms_a, norms_b,
                                                         max_a, max_b, top, colpart, RC, NBP);
     MP_LAUNCH_OK_S("match_top2_tc_kernel", s);
     return MP_OK;
@@ -599,11 +651,10 @@ int match_top2_tensor(const __nv_bfloat16 *a_hi, const __nv_bfloat16 *a_mid, con
         set_error("match_top2_tensor: the column side needs its chunk buffer");
         return MP_ERR_WORKSPACE;
     }
-#define MP_TC_LAUNCH(KB)                                                                                                         \
-    rc = cols ? launch_tc<KB, true, true>(ah, am, bh, bm, a_hi, a_mid, na, NA, nb, NB, P, norms_a, norms_b, use_bias, max_a,     \
-                                          max_b, top, cp, RC, NBP, stream)                                                       \
-              : launch_tc<KB, true, false>(ah, am, bh, bm, a_hi, a_mid, na, NA, nb, NB, P, norms_a, norms_b, use_bias, max_a,    \
-                                           max_b, top, cp, RC, NBP, stream);                                                     \
+#define MP_TC_ARGS ah, am, bh, bm, a_hi, a_mid, na, NA, nb, NB, P, norms_a, norms_b, max_a, max_b, top, cp, RC, NBP, stream
+#define MP_TC_LAUNCH(KB)                                                                             \
+    rc = cols ? (use_bias ? launch_tc<KB, true, true, true>(MP_TC_ARGS) : launch_tc<KB, true, true, false>(MP_TC_ARGS))     \
+              : (use_bias ? launch_tc<KB, true, false, true>(MP_TC_ARGS) : launch_tc<KB, true, false, false>(MP_TC_ARGS));  \
     break
     switch (D / 64) {
         case 1: MP_TC_LAUNCH(1);
@@ -611,6 +662,7 @@ int match_top2_tensor(const __nv_bfloat16 *a_hi, const __nv_bfloat16 *a_mid, con
         case 3: MP_TC_LAUNCH(3);
         default: MP_TC_LAUNCH(4);
     }
+#undef MP_TC_ARGS
 #undef MP_TC_LAUNCH
     if (rc != MP_OK || !cols) return rc;
     dim3 grid((NB + 255) / 256, P);
