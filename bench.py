@@ -18,9 +18,16 @@ tcgen05 matcher.
             and matches, through the public pipeline API
   hot_path  the same without the cuDNN backbone (backbone outputs resident in HBM): the part this
             repo implements; per-stage times and the roofline of its dominant kernel
+  roofline  the dominant kernel of the path this repo implements: the tcgen05 matcher, algorithmic
+            flop = 2*N1*N2*D once per pair (the three bf16 passes it executes are reported beside it)
+  config3_matching_sweep   BASELINE config 3: 1k-16k keypoints x 256-d (and 64-d) per pair, whole matcher chain
+  config4_adaptation       BASELINE config 4: export_keypoints' homographic adaptation, 100 homographies per image;
+            at N > 1 also one batch with the homography samples sharded over the ranks and the two accumulators
+            summed by one NCCL all-reduce (the only data-path collective of the whole path)
   cpu_baseline  (N=1) the reference's CPU chain for ONE pair on the host cores: torch CPU backbone +
             oracle/reference_port.py (torch softmax / torchvision nms / grid_sample / cv2.BFMatcher)
-Reference arm: that same CPU chain, one pair per step, all host threads, rank 0 only.
+Reference arm: that same CPU chain, one pair per step (value is per pair, so it compares with the 64-pair step's
+pairs/s), all host threads, rank 0 only.
 """
 import argparse
 import json
@@ -47,6 +54,7 @@ def parse_args():
     ap.add_argument("--desc", type=int, default=256, help="descriptor size (256 = class default, 64 = shipped params.yaml)")
     ap.add_argument("--topk", type=int, default=2048)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra-configs", action="store_true", help="skip the config 3 / config 4 sections")
     ap.add_argument("--only-value", action="store_true", help="time only the resident step (used under ncu)")
     ap.add_argument("--only-hot", action="store_true",
                     help="run only the post-backbone hot path on synthetic backbone outputs (used under ncu)")
@@ -64,7 +72,10 @@ def workload_config(args, extra=None):
                        "bfmatcher crossCheck" % (args.pairs, args.desc, args.topk),
            "pairs_per_gpu": args.pairs, "descriptor_size": args.desc, "topk": args.topk, "nms": 4,
            "detection_threshold": 0.015, "weights": "random init (seed 0), final BatchNorms calibrated",
-           "l2_policy": "inputs larger than L2 (168 MB of images, 1.5 GB of backbone outputs per step)"}
+           "l2_policy": "inputs larger than L2 (168 MB of images, 1.5 GB of backbone outputs per step)",
+           "precision": "fp32 throughout: cudnn.allow_tf32=False and matmul.allow_tf32=False (the reference's CPU arithmetic). "
+                        "Stock PyTorch leaves cudnn.allow_tf32=True, i.e. the reference on any Ampere-or-later GPU would run its "
+                        "convolutions in TF32: that configuration is reported as backbone_tf32_context, not as the headline"}
     if extra:
         cfg.update(extra)
     return cfg
@@ -182,6 +193,155 @@ def run_reference(args):
             "gpu_launches": 0}
     print(json.dumps(line))
     return 0
+
+
+# --------------------------------------------------------------------------------------------- BASELINE configs 3 and 4
+def matching_sweep(dev, hbm_peak, tf_peak):
+    """BASELINE config 3: dense mutual-NN matching, 1k-16k keypoints x 256-d (and 64-d, the shipped size) for one
+    pair: the whole chain behind get_matches('bfmatcher', crossCheck=True) on device-resident descriptors
+    (prep, one tcgen05 GEMM with both directions, flag, fp64 recheck, mutual test, compaction)."""
+    import torch
+    from multipoint_b200 import _lib, ops
+    rows = []
+    for D in (256, 64):
+        for N in (1024, 2048, 4096, 8192, 16384):
+            g = torch.Generator(device=dev).manual_seed(N + D)
+            a = torch.nn.functional.normalize(torch.randn((1, N, D), generator=g, device=dev), dim=2)
+            perm = torch.randperm(N, generator=g, device=dev)
+            b = torch.nn.functional.normalize(a[:, perm] + 0.05 * torch.randn((1, N, D), generator=g, device=dev), dim=2)
+            fn = lambda: ops.match(a, b, metric='l2', algo='tensor', kind='mutual', cross_check=True)  # noqa: E731
+            iters = 10 if N <= 4096 else 5
+            for _ in range(3):
+                out = fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / iters
+            _lib.profile_begin()
+            for _ in range(iters):
+                fn()
+            torch.cuda.synchronize()
+            prof = _lib.profile_end()
+            tc = prof.get("match_top2_tc_kernel", {"total_ms": 0.0})["total_ms"] / iters
+            fl = 2.0 * N * N * D
+            rows.append({"N": N, "D": D, "ms": round(ms, 4), "matches": int(out[3].sum()), "gemm_launches": int(prof.get("match_top2_tc_kernel", {"launches": 0})["launches"] / iters),
+                         "gemm_us": round(tc * 1e3, 1), "algorithmic_TFLOPs": round(fl / ms / 1e9, 1),
+                         "gemm_algorithmic_TFLOPs": round(fl / tc / 1e9, 1) if tc else None,
+                         "gemm_frac_of_bf16_peak": round(fl / tc / 1e9 / tf_peak, 4) if tc else None,
+                         "gemm_executed_frac": round(3 * fl / tc / 1e9 / tf_peak, 4) if tc else None})
+            del a, b
+    return {"workload": "config 3: get_matches('bfmatcher', crossCheck=True) for one pair, N x N x D, descriptors resident in HBM",
+            "flop": "2*N*N*D once per pair (algorithmic); the GEMM executes 3 bf16 passes of it", "rows": rows}
+
+
+def adaptation_bench(net, dev, rank, world, hbm_peak, n_pairs=2, num=100, steps=2):
+    """BASELINE config 4: what export_keypoints does per batch -- homographic_adaptation_multispectral with ``num``
+    homographies (99 sampled + identity) on ``n_pairs`` 512x640 pairs, then box NMS and keypoints.  Returns
+    images/s for the whole call (backbone included) and the library's kernels with their HBM fractions."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from multipoint_b200 import _lib, parallel, utils
+    from multipoint_b200 import synthetic as syn
+    cfg = {'num': num, 'aggregation': 'prod', 'erosion_radius': 5, 'mask_border': True, 'min_count': 5, 'filter_size': 0}
+    batch = syn.image_pair_batch(7000 + rank, n_pairs, H, W)
+    data = {s: {k: torch.from_numpy(v).to(dev) for k, v in batch[s].items() if k != 'valid_mask'} for s in ('optical', 'thermal')}
+
+    def call(shard=None, Hs=None):
+        with torch.no_grad():
+            prob = utils.homographic_adaptation_multispectral(data, net, cfg, homographies=Hs, shard=shard)
+            nms = utils.box_nms(prob, 4, 0.015, keep_top_k=0)
+            return prob, nms
+
+    np.random.seed(1234)
+    call()
+    torch.cuda.synchronize()
+    _lib.profile_begin()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        prob, nms = call()
+    e1.record()
+    torch.cuda.synchronize()
+    prof = _lib.profile_end()
+    ms = e0.elapsed_time(e1) / steps
+    n = num - 1
+    HW = H * W
+    algorithmic = {   # bytes per launch (DESIGN.md section 4): warped plane read + written; heatmaps + mask read, accumulators once
+        "warp_kernel": n * n_pairs * 2 * HW * 4,
+        "ha_aggregate_kernel": n * (2 * n_pairs * HW * 4 + HW) + 2 * n_pairs * HW * 4,
+        "valid_mask_kernel": n * HW,
+    }
+    rows = []
+    for name in ("warp_kernel", "ha_aggregate_kernel", "valid_mask_kernel", "detector_head_kernel", "nms_tile_fast_kernel"):
+        if name in prof:
+            rec = prof[name]
+            avg_ms = rec["total_ms"] / max(rec["launches"], 1)
+            row = {"kernel": name, "launches_per_batch": rec["launches"] / steps, "avg_us": round(avg_ms * 1e3, 1)}
+            if name in algorithmic:
+                row.update(algorithmic_bytes_per_launch=algorithmic[name], achieved_GBps=round(algorithmic[name] / avg_ms / 1e6, 1),
+                           frac_of_hbm=round(algorithmic[name] / avg_ms / 1e6 / hbm_peak, 4))
+            rows.append(row)
+    lib_ms = sum(v["total_ms"] for k, v in prof.items() if k in ("warp_kernel", "ha_aggregate_kernel", "valid_mask_kernel")) / steps
+    res = {"workload": "config 4: homographic_adaptation_multispectral(num=%d, prod) + box_nms(topk=0) on %d synthetic 512x640 pairs "
+                       "per GPU (the export_keypoints batch)" % (num, n_pairs),
+           "ms_per_batch": round(ms, 2), "pairs_per_s": round(n_pairs * world * 1000.0 / ms, 3),
+           "images_through_backbone_per_s": round(2 * n_pairs * num * world * 1000.0 / ms, 1),
+           "adaptation_kernels_ms_per_batch": round(lib_ms, 3), "kernels": rows,
+           "keypoints_per_pair": int((nms > 0.015).sum()) // n_pairs}
+    if world > 1:
+        # the one data-path collective: homography samples sharded over the ranks (same images on every rank),
+        # partial (prob, count) accumulators summed by one NCCL all-reduce each, then the fused finish
+        data0 = [{k: v.clone() for k, v in data[s].items()} for s in ('optical', 'thermal')]
+        for d in data0:
+            for v in d.values():
+                dist.broadcast(v, 0)
+        shared = {'optical': data0[0], 'thermal': data0[1]}
+        ar = {"ms": 0.0, "bytes": 0, "calls": 0}
+
+        def timed_all_reduce(t):
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            a1.record()
+            ar.setdefault("events", []).append((a0, a1))
+            ar["bytes"] += t.numel() * t.element_size()
+            ar["calls"] += 1
+            return t
+
+        def call_sharded():
+            hw = (H, W)
+            Hs, _ = parallel.broadcast_homographies(lambda: utils.sample_adaptation_homographies(hw, utils._check_ha_config(cfg), with_masks=False), device=dev)
+            with torch.no_grad():
+                return utils.homographic_adaptation_multispectral(shared, net, cfg, homographies=Hs, shard=(rank, world, timed_all_reduce))
+
+        np.random.seed(4321)
+        call_sharded()
+        ar.update(ms=0.0, bytes=0, calls=0, events=[])
+        dist.barrier(); torch.cuda.synchronize()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        out_sh = call_sharded()
+        s1.record()
+        torch.cuda.synchronize(); dist.barrier()
+        ms_sh = torch.tensor([s0.elapsed_time(s1), sum(a.elapsed_time(b) for a, b in ar["events"])], dtype=torch.float64, device=dev)
+        dist.all_reduce(ms_sh, op=dist.ReduceOp.MAX)
+        # the same batch unsharded on this rank: the sharded result must agree to fp32 summation order
+        np.random.seed(4321)
+        Hs_ref, _ = utils.sample_adaptation_homographies((H, W), utils._check_ha_config(cfg), with_masks=False)
+        with torch.no_grad():
+            ref = utils.homographic_adaptation_multispectral(shared, net, cfg, homographies=Hs_ref)
+        diff = (out_sh - ref).abs().max().reshape(1).double()
+        dist.all_reduce(diff, op=dist.ReduceOp.MAX)
+        res["sharded"] = {"what": "one batch, %d homography samples split round-robin over %d ranks; NCCL all-reduce(SUM) of prob and count" % (n, world),
+                          "ms_per_batch": round(float(ms_sh[0]), 2), "pairs_per_s": round(n_pairs * 1000.0 / float(ms_sh[0]), 3),
+                          "all_reduce_ms": round(float(ms_sh[1]), 3), "all_reduce_calls": ar["calls"], "all_reduce_bytes": ar["bytes"],
+                          "max_abs_diff_vs_unsharded": float(diff[0])}
+    return res
 
 
 def main():
@@ -412,7 +572,8 @@ def main():
     traffic = {}
     if (P, Kp, Dd, H, W) == (64, 2048, 256, 512, 640):
         try:
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")))
+            tpath = os.path.join(ROOT, "profiles", "r2_ncu_traffic.json")
+            tj = json.load(open(tpath if os.path.exists(tpath) else os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")))
             traffic = {k: v["dram_bytes"] for k, v in tj["per_launch"].items()}
             traffic["sample_descriptors_kernel"] = traffic.get("sample_descriptors_nhwc_vec_kernel")
             # the glue kernel's launches differ per layer: DRAM bytes / algorithmic bytes of the captured full-resolution
@@ -440,11 +601,16 @@ def main():
         if traffic.get(name):
             row["traffic"] = traffic[name]
         kernel_rows.append(row)
-    dom = next((r for r in kernel_rows if "bound" in r), None)   # the largest share of the hot path among the kernels with a roofline
+    # the roofline object is the dominant kernel of the path SURVEY section 8 scopes (the post-backbone chain); the backbone
+    # glue kernels (relu_bn_pad / conv1_relu_bn_pad, outside section 8) keep their rows in hot_path.kernels
+    section8 = ("match_top2_tc_kernel", "detector_head_kernel", "nms_tile_fast_kernel", "nms_candidates_kernel", "normalize_desc_kernel",
+                "sample_descriptors_kernel", "match_prep_vec_kernel")
+    dom = next((r for r in kernel_rows if "bound" in r and r["kernel"] in section8), None)
     if dom is not None and dom["bound"] == "tensor":
         roofline = {"kernel": dom["kernel"], "bound": "tensor", "achieved": dom["achieved_TFLOPs"], "peak": tf_peak, "unit": "TFLOP/s",
                     "frac": dom["frac"], "traffic": dom.get("traffic"), "avg_launch_us": dom["avg_us"], "launches_per_step": dom["launches_per_step"],
                     "algorithmic_flop_per_launch": dom["algorithmic_flop_per_launch"],
+                    "algorithmic_flop": "2*N1*N2*D per pair, counted once (both directions come out of the one GEMM) x %d pairs per launch" % P,
                     "executed": {"TFLOP/s": dom["executed_TFLOPs"], "frac": dom["executed_frac"],
                                  "note": "3 bf16 MMA passes (hi*hi, hi*mid, mid*hi) per algorithmic fp32 product"},
                     "peak_source": peak_src + " bf16_tflops (burst)"}
@@ -478,6 +644,12 @@ def main():
     line["backbone_tf32_context"] = {"value": P * world * 1000.0 / ms_tf32, "unit": "pairs/s", "ms_per_step": ms_tf32,
                                      "note": "cudnn.allow_tf32=True for the backbone only; reported for context, headline stays fp32"}
 
+    if not args.no_extra_configs:
+        if rank == 0:
+            line["config3_matching_sweep"] = matching_sweep(dev, hbm_peak, tf_peak)
+        barrier()
+        line["config4_adaptation"] = adaptation_bench(net, dev, rank, world, hbm_peak)
+
     if world == 1 and rank == 0 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         net_cpu = build_net(args.desc, "cpu")
@@ -490,6 +662,24 @@ def main():
                                           "oracle/reference_port.py (torch softmax, torchvision batched_nms, grid_sample, cv2.BFMatcher)",
                                 "seconds_per_pair": sec, "backbone_seconds": sum(s[1] for s in secs) / len(secs),
                                 "matches": secs[0][2], "keypoints": secs[0][3]}
+        # box_nms is effectively serial on the CPU (torchvision's greedy scan): SURVEY 8d asks for it at 1 thread too
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import reference_port as rp
+        with torch.no_grad():
+            lo, _ = net_cpu.backbone_outputs({'image': torch.from_numpy(pair['optical']['image']),
+                                              'is_optical': torch.from_numpy(pair['optical']['is_optical'])})
+            prob_cpu = rp.detector_head(lo)
+        nms_sec = {}
+        for nthr in (1, threads):
+            torch.set_num_threads(nthr)
+            t0 = time.perf_counter()
+            kept = rp.box_nms(prob_cpu, 4, 0.015, keep_top_k=args.topk)
+            nms_sec[nthr] = time.perf_counter() - t0
+        torch.set_num_threads(threads)
+        line["cpu_baseline"]["box_nms_threads_1"] = {"seconds_per_image": round(nms_sec[1], 4), "candidates": int((prob_cpu > 0.015).sum()),
+                                                     "kept": int((kept > 0).sum())}
+        line["cpu_baseline"]["box_nms_threads_all"] = {"seconds_per_image": round(nms_sec[threads], 4), "threads": threads}
+        line["cpu_baseline"]["seconds_per_pair_with_1_thread_nms"] = round(sec - 2 * (nms_sec[threads] - nms_sec[1]), 4)
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

@@ -39,10 +39,29 @@ __device__ __forceinline__ void top2_update(Top2 &t, float key, int idx) {
 //          accumulation in the tensor core over <= 48 MMAs adds <= ~1e-5  -> 4e-5 with margin
 //  simt  : fp32 FMA chain over D <= 4096 terms                              -> 4e-5 as well
 constexpr float MATCH_EPS_TENSOR = 4e-5f;
-// the tensor epilogue packs the column index into the 5 low mantissa bits of (key + C), C <= 1.002|a||b| + |b|^2/2:
-// an extra absolute error of 2^-18 * 2C, added to the bound by the flag kernel
-constexpr float MATCH_PACK_REL = 3.8147e-6f;  // 2^-18
+// the tensor epilogue orders keys by the mantissa of f = key + C, C = 3 * 2^E < 6.1 * bound (KeyScale below): the add
+// rounds to ulp(f) / 2 <= 2^-23 * 2^(E+1) < 2^-21 * bound per key.  The flag kernel adds pack_rel * 2 * bound.
+constexpr float MATCH_PACK_REL = 4.76837e-7f;  // 2^-21
 constexpr float MATCH_EPS_SIMT = 4e-5f;
+
+// Packed 32-bit keys of the tensor epilogue.  With C = 3 * 2^E and 2^E > bound >= |v|, f = v + C lies in the single
+// binade [2^(E+1), 2^(E+2)), so bits(f) * 32 + code keeps the whole mantissa above a 5-bit code and compares like f.
+struct KeyScale {
+    float C;           // 3 * 2^E
+    uint32_t expbits;  // exponent field of that binade, in place
+};
+__device__ __forceinline__ KeyScale key_scale(float bound) {
+    const float b = fmaxf(1.01f * bound, 1e-30f);
+    const uint32_t e = (__float_as_uint(b) >> 23) + 1u;   // 2^(e-127) > b
+    KeyScale k;
+    k.C = 3.f * __uint_as_float(e << 23);
+    k.expbits = (e + 1u) << 23;
+    return k;
+}
+// the value v a key stands for (low 5 bits = code)
+__device__ __forceinline__ float key_value(const KeyScale &k, uint32_t key) {
+    return __uint_as_float(k.expbits | ((key >> 5) & 0x7fffffu)) - k.C;
+}
 
 struct MatchLayout {
     size_t scalars, row_part_key, row_part_idx, norms1, norms2, top12, top21, idx12, idx21, flagged1, flagged2, pairs1, pairs2, train_tmp, dist_tmp, hi1, mid1, hi2, mid2, colpart, total;

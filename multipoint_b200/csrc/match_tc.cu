@@ -143,15 +143,15 @@ __device__ __forceinline__ uint32_t warp_min_u32(uint32_t x) {
     asm volatile("redux.sync.min.u32 %0, %1, 0xffffffff;" : "=r"(r) : "r"(x));
     return r;
 }
-// (a & b) | c and its complement in one LOP3
-__device__ __forceinline__ uint32_t and_or(uint32_t a, uint32_t b, uint32_t c) {
+// d = a * b + c on the integer multiply-add pipe (keeps the key arithmetic off the ALU pipe that the min/max chain saturates)
+__device__ __forceinline__ uint32_t mad_u32(uint32_t a, uint32_t b, uint32_t c) {
     uint32_t r;
-    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
     return r;
 }
-__device__ __forceinline__ uint32_t not_and_or(uint32_t a, uint32_t b, uint32_t c) {
+__device__ __forceinline__ uint32_t warp_max_u32(uint32_t x) {
     uint32_t r;
-    asm("lop3.b32 %0, %1, %2, %3, 0x15;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    asm volatile("redux.sync.max.u32 %0, %1, 0xffffffff;" : "=r"(r) : "r"(x));
     return r;
 }
 
@@ -365,22 +365,26 @@ match_top2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
             if (lane == 0) mbar_arrive(bar_a_full);
         }
         const float ma = __uint_as_float(max_a[p]), mb = __uint_as_float(max_b[p]);
-        // row side: key of column j for this row = a.b + C (NN) or a.b - |b_j|^2/2 + C (L2); C > |smallest key| keeps it
-        // positive.  Columns beyond n_b get the term 0: their operand rows are zero, so their keys are < 32 = "nothing".
-        const float C = 1.002f * ma * mb + (BIAS ? 0.5f * mb * mb : 0.f) + 1e-30f;
+        // Packed keys (match_internal.cuh: KeyScale).  Row side: f = a.b [- |b_j|^2/2] + C with C = 3 * 2^E and
+        // 2^E > |a.b - ...|, so every f lies in the one binade [2^(E+1), 2^(E+2)): its 23 mantissa bits order the keys
+        // and bits(f) * 32 + (31 - j) -- one integer multiply-add -- is the key with the column inside the chunk in the
+        // low 5 bits.  Columns beyond n_b get the term 0: their operand rows are zero, f = 0, key < 32 = "nothing".
+        const KeyScale kr = key_scale(1.002f * ma * mb + (BIAS ? 0.5f * mb * mb : 0.f));
         const float *bias = norms_b + (size_t)p * NB;
-        // column side (COLS): key of this row as seen from column j = a.b + CC (NN) or a.b - |a_i|^2/2 + CC (L2): the row's
-        // own term is a per-thread constant.  Keys are complemented (smaller = closer) so that the winner and the gap to
-        // the runner-up both come out of a warp-collective minimum.  Rows beyond n_a carry the key ~0 and never win.
-        const float CC = 1.002f * ma * mb + (BIAS ? 0.5f * ma * ma : 0.f) + 1e-30f;
+        // Column side (COLS): f = a.b [- |a_i|^2/2] + CC, the row's own term being a per-thread constant; the key is
+        // complemented (smaller = closer) so that the winner and the gap to the runner-up both come out of
+        // warp-collective reductions.  Rows beyond n_a carry the key ~0 and never win.
+        const KeyScale kc = key_scale(1.002f * ma * mb + (BIAS ? 0.5f * ma * ma : 0.f));
         const bool row_ok = m0 + row < n_a;
-        const float add_row = (COLS && BIAS && row_ok) ? fmaf(-0.5f, __ldg(norms_a + (size_t)p * NA + m0 + row), CC) : CC;
-        const uint32_t cmask = row_ok ? ~31u : 0u, ccode = row_ok ? (uint32_t)(31 - lane) : 0u;
+        const float add_row = (COLS && BIAS && row_ok) ? fmaf(-0.5f, __ldg(norms_a + (size_t)p * NA + m0 + row), kc.C) : kc.C;
+        const uint32_t opaque0 = (uint32_t)(n_tiles >> 30);           // 0, but not to the compiler: keeps the multipliers in registers
+        const uint32_t mul_r = 32u + opaque0;
+        const uint32_t mul_c = row_ok ? 0u - 32u : opaque0;            // ~(32 f + code) = -32 f + ~code
+        const uint32_t code_c = row_ok ? ~(uint32_t)(31 - lane) : ~0u;
         uint2 *cdst = COLS ? colpart + ((size_t)p * RC + (m0 >> 5) + quarter) * NBP + lane : nullptr;
         uint8_t *wsm = smem_raw + (base + L::BIAS_OFF - smem_u32(smem_raw)) + (warp - 2) * 1024;
         float *sbias = reinterpret_cast<float *>(wsm);            // [2 tiles][64]
         uint4 *srec = reinterpret_cast<uint4 *>(wsm + 512);       // [2 chunks][16] = (m, g) of two columns each
-        const uint32_t keymask = ~31u + (uint32_t)(n_tiles >> 30);   // ~31 in a register: one LOP3 per key, code as immediate
 
         uint32_t best = 0, second = 0, third = 0;  // packed keys; < 32 = nothing yet
         int best_chunk = -1, second_chunk = -1;    // global chunk index (32 columns each)
@@ -388,8 +392,7 @@ match_top2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
 
         // one 32-column chunk of this thread's accumulator row
         auto process = [&](const uint32_t (&v)[32], int col0, const float *sb, uint4 *rec) {
-            // sorted triples (b >= s >= t) in two independent accumulators
-            uint32_t b2[2] = {0, 0}, s2[2] = {0, 0}, t2[2] = {0, 0};
+            const uint32_t old_best = best, old_second = second;
 #pragma unroll
             for (int j8 = 0; j8 < 32; j8 += 8) {
                 uint32_t nx[8];
@@ -402,24 +405,26 @@ match_top2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
                         const int j = j4 + jj;
                         const float val = __uint_as_float(v[j]);
                         const float fr = val + add4[jj];
-                        const uint32_t x = and_or(__float_as_uint(fr), keymask, (uint32_t)(31 - j));
-                        t2[j & 1] = max(t2[j & 1], min(x, s2[j & 1]));
-                        s2[j & 1] = max(s2[j & 1], min(x, b2[j & 1]));
-                        b2[j & 1] = max(b2[j & 1], x);
+                        const uint32_t x = mad_u32(__float_as_uint(fr), mul_r, (uint32_t)(31 - j));
+                        // running sorted triple: the chain through (best, second, third) is one min/max deep per element
+                        third = max(third, min(x, second));
+                        second = max(second, min(x, best));
+                        best = max(best, x);
                         if (COLS) {
-                            const float fc = BIAS ? val + add_row : fr;   // NN: CC == C, one add serves both sides
-                            nx[j - j8] = not_and_or(__float_as_uint(fc), cmask, ccode);
+                            const float fc = BIAS ? val + add_row : fr;   // NN: same constant, one add serves both sides
+                            nx[j - j8] = mad_u32(__float_as_uint(fc), mul_c, code_c);
                         }
                     }
                 }
                 if (COLS) {
                     // eight columns per batch: the eight winners first, then the eight gaps, so that the collectives'
-                    // latencies overlap instead of forming one dependent chain per column
+                    // latencies overlap instead of forming one dependent chain per column.  m - nx is 0 for the winner
+                    // and 2^32 - gap for everybody else: its maximum is the runner-up.
                     uint32_t m[8], g[8];
 #pragma unroll
                     for (int k = 0; k < 8; ++k) m[k] = warp_min_u32(nx[k]);
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) g[k] = warp_min_u32(nx[k] - m[k] - 1u);   // the winner wraps to 0xffffffff
+                    for (int k = 0; k < 8; ++k) g[k] = warp_max_u32(m[k] - nx[k]);
                     if (lane == 0) {
 #pragma unroll
                         for (int k = 0; k < 8; k += 2) rec[(j8 + k) >> 1] = make_uint4(m[k], g[k], m[k + 1], g[k + 1]);
@@ -430,35 +435,27 @@ match_top2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
                 __syncwarp();
                 cdst[col0] = reinterpret_cast<const uint2 *>(rec)[lane];   // 256 B per warp, coalesced; columns >= n_b are padding
             }
-            // k-th largest of two sorted triples: second = max(s, s', min(b, b')),
-            // third = max(t, t', min(s, b'), min(b, s'))
-            auto merge3 = [](uint32_t &b, uint32_t &s_, uint32_t &t_, uint32_t bb, uint32_t ss, uint32_t tt) {
-                const uint32_t nt = max(max(t_, tt), max(min(s_, bb), min(b, ss)));
-                const uint32_t ns = max(max(s_, ss), min(b, bb));
-                b = max(b, bb); s_ = ns; t_ = nt;
-            };
-            merge3(b2[0], s2[0], t2[0], b2[1], s2[1], t2[1]);
+            // which chunk the new best / second came from (keys of different chunks can be equal only in their low bits'
+            // meaning, never in value order: a changed key is a key of this chunk)
             const int chunk = col0 >> 5;
-            const uint32_t old_best = best, old_second = second;
-            const int old_best_chunk = best_chunk;
-            merge3(best, second, third, b2[0], s2[0], t2[0]);
+            if (second != old_second) second_chunk = (second == old_best && best != old_best) ? best_chunk : chunk;
             if (best != old_best) best_chunk = chunk;
-            if (second != old_second) second_chunk = (second == old_best && best != old_best) ? old_best_chunk : chunk;
         };
-        // the 2 x 32 column terms of tile nt, one per lane, become warp-visible through shared memory
-        auto stage_terms = [&](int nt) {
+        auto fetch_terms = [&](int nt, float &a0, float &a1) {
             const int ca = nt * TC_BN + half * 32 + lane, cb_ = ca + 64;
-            float a0 = 0.f, a1 = 0.f;
-            if (ca < n_b) a0 = BIAS ? fmaf(-0.5f, __ldg(bias + ca), C) : C;
-            if (cb_ < n_b) a1 = BIAS ? fmaf(-0.5f, __ldg(bias + cb_), C) : C;
-            float *dst = sbias + (nt & 1) * 64;
-            dst[lane] = a0;
-            dst[32 + lane] = a1;
+            a0 = 0.f; a1 = 0.f;
+            if (ca < n_b) a0 = BIAS ? fmaf(-0.5f, __ldg(bias + ca), kr.C) : kr.C;
+            if (cb_ < n_b) a1 = BIAS ? fmaf(-0.5f, __ldg(bias + cb_), kr.C) : kr.C;
         };
         // Software pipeline over the 2 * n_tiles chunks of this warp: the tcgen05.ld of chunk s+1 is in flight while chunk s
         // is processed (tcgen05.wait::ld waits for every outstanding load, so it is issued right after the wait for chunk s).
+        // The 2 x 32 column terms of a tile, one per lane, are fetched a whole tile ahead and become warp-visible through
+        // shared memory (double-buffered over tiles).
         uint32_t va[32], vb[32];
-        stage_terms(0);
+        float a0n, a1n;
+        fetch_terms(0, a0n, a1n);
+        sbias[lane] = a0n; sbias[32 + lane] = a1n;
+        if (n_tiles > 1) fetch_terms(1, a0n, a1n);
         mbar_wait(bar_acc_full(0), 0);
         tc_fence_after();
         tc_ld32(tlane + (uint32_t)(half * 32), va);
@@ -477,7 +474,9 @@ match_top2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_acc_empty(t));
             if (nt + 1 < n_tiles) {
-                stage_terms(nt + 1);
+                float *dst = sbias + ((nt + 1) & 1) * 64;      // last read two tiles ago
+                dst[lane] = a0n; dst[32 + lane] = a1n;
+                if (nt + 2 < n_tiles) fetch_terms(nt + 2, a0n, a1n);
                 const int t1 = (nt + 1) % ACC;
                 mbar_wait(bar_acc_full(t1), ((nt + 1) / ACC) & 1);
                 tc_fence_after();
@@ -509,13 +508,13 @@ match_top2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
             if (m0 + row < n_a) {
                 if (best >= 32u) {
                     out.best_idx = best_chunk * 32 + 31 - (int)(best & 31u);
-                    out.best = __uint_as_float(best & ~31u) - C;
+                    out.best = key_value(kr, best);
                 }
                 if (second >= 32u) {
                     out.second_idx = second_chunk * 32 + 31 - (int)(second & 31u);
-                    out.second = __uint_as_float(second & ~31u) - C;
+                    out.second = key_value(kr, second);
                 }
-                if (third >= 32u) out.third = __uint_as_float(third & ~31u) - C;
+                if (third >= 32u) out.third = key_value(kr, third);
             }
             top[(size_t)p * NA + m0 + row] = out;
         }
@@ -569,7 +568,7 @@ static int make_operand_map(CUtensorMap *map, const __nv_bfloat16 *ptr, int P, i
 
 // ---------------------------------------------------------------- column side: fold the 32-row chunks
 // One thread per column j of pair p: the chunk records (~maximum, gap g) give the chunk's two best packed keys
-// m and m - g - 1 (low 5 bits = 31 - row inside the chunk).  The chunk's third key is unknown but not larger than
+// (low 5 bits = 31 - row inside the chunk).  The chunk's third key is unknown but not larger than
 // its second, so the second is entered twice: a near-tie whose best and second share a chunk is then classified
 // for the full exact rescan (conservative), every other case is exact.
 __global__ void __launch_bounds__(256)
@@ -582,7 +581,7 @@ match_colmerge_kernel(const uint2 *__restrict__ colpart, int RC, int NBP, const 
     Top2 out = top2_empty();
     if (j < n_b && n_a > 0) {
         const float ma = __uint_as_float(max_a[p]), mb = __uint_as_float(max_b[p]);
-        const float CC = 1.002f * ma * mb + (use_bias ? 0.5f * ma * ma : 0.f) + 1e-30f;
+        const KeyScale kc = key_scale(1.002f * ma * mb + (use_bias ? 0.5f * ma * ma : 0.f));
         const uint2 *src = colpart + (size_t)p * RC * NBP + j;
         const int chunks = (n_a + 31) >> 5;
         uint32_t b = 0, s = 0, t = 0;
@@ -592,21 +591,27 @@ match_colmerge_kernel(const uint2 *__restrict__ colpart, int RC, int NBP, const 
             else if (x > s) { t = s; s = x; sc = indexed ? c : -2; }
             else if (x > t) t = x;
         };
-        uint2 nx = __ldg(src);
-        for (int c = 0; c < chunks; ++c) {
-            const uint2 cur = nx;
-            if (c + 1 < chunks) nx = __ldg(src + (size_t)(c + 1) * NBP);
-            const uint32_t k1 = ~cur.x;   // the kernel reduces complemented keys
-            if (k1 < 32u) continue;
-            const uint32_t k2 = k1 - cur.y - 1u;
-            insert(k1, c, true);
-            if (k2 >= 32u) { insert(k2, c, true); insert(k2, c, false); }
+        // eight chunk records in flight per thread: the loop is a chain of dependent L2 round trips otherwise
+        for (int c0 = 0; c0 < chunks; c0 += 8) {
+            uint2 cur[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                cur[u] = c0 + u < chunks ? __ldg(src + (size_t)(c0 + u) * NBP) : make_uint2(~0u, 0u);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const uint32_t k1 = ~cur[u].x;   // the kernel reduces complemented keys
+                if (k1 < 32u) continue;
+                // cur.y = 2^32 - (runner-up - winner) of the complemented keys, 0 = no runner-up
+                const uint32_t k2 = cur[u].y == 0u ? 0u : ~(cur[u].x - cur[u].y);
+                insert(k1, c0 + u, true);
+                if (k2 >= 32u) { insert(k2, c0 + u, true); insert(k2, c0 + u, false); }
+            }
         }
         // equal packed keys cannot occur inside a chunk (distinct row codes); across chunks the strict '>' keeps the
         // earlier chunk = the lower row index, and such ties are inside the recheck margin anyway
-        if (bc >= 0) { out.best_idx = bc * 32 + 31 - (int)(b & 31u); out.best = __uint_as_float(b & ~31u) - CC; }
-        if (sc >= 0) { out.second_idx = sc * 32 + 31 - (int)(s & 31u); out.second = __uint_as_float(s & ~31u) - CC; }
-        if (t != 0) out.third = __uint_as_float(t & ~31u) - CC;
+        if (bc >= 0) { out.best_idx = bc * 32 + 31 - (int)(b & 31u); out.best = key_value(kc, b); }
+        if (sc >= 0) { out.second_idx = sc * 32 + 31 - (int)(s & 31u); out.second = key_value(kc, s); }
+        if (t >= 32u) out.third = key_value(kc, t);
     }
     top_cols[(size_t)p * NB + j] = out;
 }
