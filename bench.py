@@ -322,6 +322,7 @@ def adaptation_bench(net, dev, rank, world, hbm_peak, n_pairs=2, num=100, steps=
         np.random.seed(4321)
         call_sharded()
         ar.update(ms=0.0, bytes=0, calls=0, events=[])
+        np.random.seed(4321)           # rank 0 draws the samples: the same stream as the unsharded check below
         dist.barrier(); torch.cuda.synchronize()
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s0.record()
@@ -337,7 +338,22 @@ def adaptation_bench(net, dev, rank, world, hbm_peak, n_pairs=2, num=100, steps=
             ref = utils.homographic_adaptation_multispectral(shared, net, cfg, homographies=Hs_ref)
         diff = (out_sh - ref).abs().max().reshape(1).double()
         dist.all_reduce(diff, op=dist.ReduceOp.MAX)
+        # the collective on its own, ranks aligned by a barrier: two all-reduces of (B,H,W) fp32
+        buf = torch.zeros_like(out_sh[:, 0])
+        dist.all_reduce(buf)
+        dist.barrier(); torch.cuda.synchronize()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(10):
+            dist.all_reduce(buf)
+        c1.record()
+        torch.cuda.synchronize()
+        iso = torch.tensor([c0.elapsed_time(c1) / 10 * 2], dtype=torch.float64, device=dev)
+        dist.all_reduce(iso, op=dist.ReduceOp.MAX)
         res["sharded"] = {"what": "one batch, %d homography samples split round-robin over %d ranks; NCCL all-reduce(SUM) of prob and count" % (n, world),
+                          "all_reduce_ms_isolated": round(float(iso[0]), 4),
+                          "all_reduce_note": "all_reduce_ms is measured inside the batch and includes waiting for the slowest rank; "
+                                             "all_reduce_ms_isolated is the same two collectives with the ranks aligned",
                           "ms_per_batch": round(float(ms_sh[0]), 2), "pairs_per_s": round(n_pairs * 1000.0 / float(ms_sh[0]), 3),
                           "all_reduce_ms": round(float(ms_sh[1]), 3), "all_reduce_calls": ar["calls"], "all_reduce_bytes": ar["bytes"],
                           "max_abs_diff_vs_unsharded": float(diff[0])}

@@ -26,8 +26,9 @@ __device__ __forceinline__ void src_coord(const float *A, float xs, float ys, in
     const float Y = __fadd_rn(__fadd_rn(__fmul_rn(A[3], xs), __fmul_rn(A[4], ys)), A[5]);
     const float Z = __fadd_rn(__fadd_rn(__fmul_rn(A[6], xs), __fmul_rn(A[7], ys)), A[8]);
     const float sc = fabsf(Z) > 1e-8f ? __fdiv_rn(1.0f, Z) : 1.0f;
-    ix = __fmul_rn(__fdiv_rn(__fadd_rn(__fmul_rn(X, sc), 1.f), 2.f), (float)(Ws - 1));
-    iy = __fmul_rn(__fdiv_rn(__fadd_rn(__fmul_rn(Y, sc), 1.f), 2.f), (float)(Hs - 1));
+    // (.. + 1) / 2 as a multiplication by 0.5: the same bits as the division for every finite input
+    ix = __fmul_rn(__fmul_rn(__fadd_rn(__fmul_rn(X, sc), 1.f), 0.5f), (float)(Ws - 1));
+    iy = __fmul_rn(__fmul_rn(__fadd_rn(__fmul_rn(Y, sc), 1.f), 0.5f), (float)(Hs - 1));
 }
 
 // ATen reflect_coordinates(in, 0, 2*(size-1)) + clip_coordinates
@@ -35,6 +36,7 @@ __device__ __forceinline__ float reflect_coord(float in, int size) {
     if (size <= 1) return 0.f;
     const float span = (float)(size - 1);
     in = fabsf(in);
+    if (in <= span) return in;   // inside: zero flips (and in == span reflects onto itself); skips fmodf on the common path
     const float extra = fmodf(in, span);
     const int flips = (int)floorf(__fdiv_rn(in, span));
     float r = (flips % 2 == 0) ? extra : __fsub_rn(span, extra);
@@ -67,11 +69,28 @@ template <typename F>
 __device__ __forceinline__ float bilinear_apply(const Bilinear &q, int Ws, F value) {
     float v = 0.f;
     if (!q.any) return v;
+    if (q.vx0 && q.vx1 && q.vy0 && q.vy1) {   // interior: the four taps are issued together, same summation order
+        const int o = q.y0 * Ws + q.x0;
+        const float a = value(o), b = value(o + 1), c = value(o + Ws), d = value(o + Ws + 1);
+        v = __fadd_rn(v, __fmul_rn(a, q.nw));
+        v = __fadd_rn(v, __fmul_rn(b, q.ne));
+        v = __fadd_rn(v, __fmul_rn(c, q.sw));
+        return __fadd_rn(v, __fmul_rn(d, q.se));
+    }
     if (q.vy0 && q.vx0) v = __fadd_rn(v, __fmul_rn(value(q.y0 * Ws + q.x0), q.nw));
     if (q.vy0 && q.vx1) v = __fadd_rn(v, __fmul_rn(value(q.y0 * Ws + q.x0 + 1), q.ne));
     if (q.vy1 && q.vx0) v = __fadd_rn(v, __fmul_rn(value((q.y0 + 1) * Ws + q.x0), q.sw));
     if (q.vy1 && q.vx1) v = __fadd_rn(v, __fmul_rn(value((q.y0 + 1) * Ws + q.x0 + 1), q.se));
     return v;
+}
+
+// A CTA owns a 32 x 8 block of destination pixels; each of its 8 warps an 8 x 4 patch of it (not a 32 x 1 row): the
+// sampled homographies rotate by up to 90 degrees, and the source footprint of a compact patch stays within a few
+// rows whatever the angle, where a 32-pixel row can map onto 32 different source rows = 32 L1 wavefronts per gather.
+__device__ __forceinline__ void patch_pixel(int &x, int &y) {
+    const int t = threadIdx.y * 32 + threadIdx.x, w = t >> 5, l = t & 31;
+    x = blockIdx.x * 32 + (w & 3) * 8 + (l & 7);
+    y = blockIdx.y * 8 + (w >> 2) * 4 + (l >> 3);
 }
 
 // grid (ceil(W/32), ceil(H/8), n_mats); each thread one destination pixel, all N planes
@@ -83,7 +102,8 @@ warp_kernel(const float *__restrict__ src, int N, int H, int W, const float *__r
     const int m = blockIdx.z;
     if (threadIdx.y == 0 && threadIdx.x < 9) As[threadIdx.x] = A[9 * m + threadIdx.x];
     __syncthreads();
-    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+    int x, y;
+    patch_pixel(x, y);
     if (x >= W || y >= H) return;
     float ix, iy;
     src_coord(As, xs[x], ys[y], W, H, ix, iy);
@@ -115,7 +135,8 @@ ha_aggregate_kernel(const float *__restrict__ prob0, const float *__restrict__ p
     for (int i = threadIdx.y * 32 + threadIdx.x; i < n * 9; i += 256) As[i] = Ainv[i];
     __syncthreads();
     const int b = blockIdx.z;
-    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+    int x, y;
+    patch_pixel(x, y);
     if (x >= W || y >= H) return;
     const size_t HW = (size_t)H * W;
     const size_t o = (size_t)b * HW + (size_t)y * W + x;
@@ -123,6 +144,7 @@ ha_aggregate_kernel(const float *__restrict__ prob0, const float *__restrict__ p
     if (flags & MP_HA_INIT) { prob = prob0[o]; count = 1.0f; }
     else { prob = prob_acc[o]; count = count_acc[o]; }
     const float xv = xs[x], yv = ys[y];
+#pragma unroll 4
     for (int i = 0; i < n; ++i) {
         float ix, iy;
         src_coord(As + 9 * i, xv, yv, W, H, ix, iy);

@@ -559,29 +559,43 @@ def _adaptation_core(images, is_optical, net, config, second, homographies, mask
     tables = ops.linspace_tables(H, W, dev)
     n = len(mine)
     empty = torch.zeros((0, B, H, W), device=dev)
-    if n:
-        Hm = torch.from_numpy(np.asarray(homographies, np.float64)[mine].astype(np.float32))
-        A_warp = normalized_warp_matrix(Hm, (H, W), (H, W)).to(dev)
-        A_unwarp = normalized_warp_matrix(torch.inverse(Hm), (H, W), (H, W)).to(dev)  # torch.inverse(homography) :112,:180
-        if masks is None:   # built on the device, this rank's share only
-            mk = compute_valid_masks((H, W), np.asarray(homographies, np.float64)[mine], config['erosion_radius'],
-                                     config['mask_border'], dev)
-        elif torch.is_tensor(masks):
-            mk = masks.to(dev, torch.uint8)[mine].contiguous()
-        else:
-            mk = torch.from_numpy(np.ascontiguousarray(np.asarray(masks)[mine])).to(dev, torch.uint8)
-        warped = ops.warp(images[:, 0], A_warp, 'bilinear', 'reflection', tables).reshape(n * B, 1, H, W)  # :86 / :171
-        pw_a = run(warped, is_optical).reshape(n, B, H, W).contiguous()
+    if n == 0:
+        return ops.ha_aggregate(prob0, empty, None if second is None else empty, torch.zeros((0, H, W), dtype=torch.uint8, device=dev),
+                                torch.zeros((0, 3, 3), device=dev), agg, config['min_count'], init=(rank == 0), finish=fused, tables=tables)
+    H_mine = np.asarray(homographies, np.float64)[mine]
+    Hm = torch.from_numpy(H_mine.astype(np.float32))
+    A_warp = normalized_warp_matrix(Hm, (H, W), (H, W)).to(dev)
+    A_unwarp = normalized_warp_matrix(torch.inverse(Hm), (H, W), (H, W)).to(dev)  # torch.inverse(homography) :112,:180
+    if masks is None:   # built on the device, this rank's share only
+        mk = compute_valid_masks((H, W), H_mine, config['erosion_radius'], config['mask_border'], dev)
+    elif torch.is_tensor(masks):
+        mk = masks.to(dev, torch.uint8)[mine].contiguous()
+    else:
+        mk = torch.from_numpy(np.ascontiguousarray(np.asarray(masks)[mine])).to(dev, torch.uint8)
+    # The samples go through warp -> net -> aggregate in chunks, so the warped images and their heatmaps take
+    # O(chunk * B) memory instead of O(num * B); the accumulators carry on from chunk to chunk in the reference's
+    # summation order (MP_HA_INIT on the first chunk, MP_HA_FINISH on the last), so the result does not depend on it.
+    chunk = max(1, int(config.get('sample_chunk', 0)) or max(1, 64 // max(B, 1)))
+    prob_acc = count_acc = out = None
+    for c0 in range(0, n, chunk):
+        c1 = min(n, c0 + chunk)
+        nc = c1 - c0
+        warped = ops.warp(images[:, 0], A_warp[c0:c1], 'bilinear', 'reflection', tables).reshape(nc * B, 1, H, W)  # :86 / :171
+        pw_a = run(warped, is_optical).reshape(nc, B, H, W).contiguous()
         pw_b = None
         if second is not None:
-            warped_b = ops.warp(img_b[:, 0], A_warp, 'bilinear', 'reflection', tables).reshape(n * B, 1, H, W)
-            pw_b = run(warped_b, opt_b).reshape(n, B, H, W).contiguous()
-    else:
-        A_unwarp = torch.zeros((0, 3, 3), device=dev)
-        mk = torch.zeros((0, H, W), dtype=torch.uint8, device=dev)
-        pw_a, pw_b = empty, (None if second is None else empty)
-    return ops.ha_aggregate(prob0, pw_a, pw_b, mk, A_unwarp, agg, config['min_count'], init=(rank == 0), finish=fused,
-                            tables=tables)
+            warped = ops.warp(img_b[:, 0], A_warp[c0:c1], 'bilinear', 'reflection', tables).reshape(nc * B, 1, H, W)
+            pw_b = run(warped, opt_b).reshape(nc, B, H, W).contiguous()
+        del warped
+        first, last = c0 == 0, c1 == n
+        res = ops.ha_aggregate(prob0 if first else None, pw_a, pw_b, mk[c0:c1], A_unwarp[c0:c1], agg, config['min_count'],
+                               init=(rank == 0 and first), finish=(fused and last), prob_acc=prob_acc, count_acc=count_acc,
+                               tables=tables)
+        if fused and last:
+            out = res
+        else:
+            prob_acc, count_acc = res
+    return out if fused else (prob_acc, count_acc)
 
 
 def adaptation_finish(prob_sum, count_sum, aggregation, min_count):
