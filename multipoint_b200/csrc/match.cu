@@ -595,7 +595,10 @@ match_decide_kernel(const float *__restrict__ d1, const int32_t *__restrict__ n1
             if (kind == MP_MATCH_MUTUAL) {
                 if (threshold >= 0.f && !(dist < threshold)) j = -1;
             } else {
-                // knnMatch(k=2) + Lowe ratio (matching.py:21-28); needs a second neighbour
+                // knnMatch(k=2) + Lowe ratio (matching.py:21-28); needs a second neighbour.  The nearest index is
+                // exact (fp64 recheck); the SECOND neighbour is the runner-up of the approximate top-3, i.e. exact only up
+                // to the key error bound (~5e-5 |a||b|): when the second and third keys are closer than that, dist2 can be
+                // the third neighbour's distance, which differs from the second's by no more than the same bound
                 const Top2 t = top12[g];
                 int j2 = (t.best_idx == j) ? t.second_idx : t.best_idx;
                 if (j2 < 0) {

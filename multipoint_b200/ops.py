@@ -37,7 +37,9 @@ def _ws(nbytes, device):
 
 
 def detector_head(logits, valid_mask=None):
-    """(B,65,Hc,Wc) fp32 logits -> (B,1,8Hc,8Wc) heatmap; optional (B,1,H,W) bool/uint8 mask."""
+    """(B,65,Hc,Wc) fp32 logits -> (B,1,8Hc,8Wc) heatmap; optional (B,1,H,W) valid mask.  The mask is a BINARY mask
+    (the reference multiplies prob by a bool valid_mask): any non-zero entry, of any dtype, keeps the pixel -- the same
+    rule extract_keypoints applies."""
     logits = _cuda(logits, torch.float32, "logits")
     if logits.dim() != 4 or logits.shape[1] != 65:
         raise ValueError("logits must be (B,65,Hc,Wc), got %s" % (tuple(logits.shape),))
@@ -47,7 +49,7 @@ def detector_head(logits, valid_mask=None):
     if valid_mask is not None:
         if not valid_mask.is_cuda:
             raise RuntimeError("valid_mask must be a CUDA tensor")
-        mask = valid_mask.to(torch.uint8).contiguous() if valid_mask.dtype != torch.uint8 else valid_mask.contiguous()
+        mask = (valid_mask != 0).to(torch.uint8).contiguous()   # 0/1 bytes whatever the dtype (a 0/255 byte mask must not scale by 255)
         if mask.numel() != prob.numel():
             raise ValueError("valid_mask must have %d elements" % prob.numel())
     with torch.cuda.device(logits.device):

@@ -45,7 +45,6 @@ def main(argv=None):
     names = data['name']
     done = dict(np.load(args.output_file)) if (args.skip_processed and os.path.exists(args.output_file)) else {}
     bs = pred['batchsize']
-    np.random.seed(args.seed)
     results = {}
     batches = list(range(0, len(names), bs))
     with torch.no_grad():
@@ -56,6 +55,9 @@ def main(argv=None):
             shard = None
             if world > 1 and not args.shard_homographies and bi % world != rank:
                 continue                                             # batches are independent units
+            # the homography stream of a batch depends only on (seed, batch index): the labels are the same for any
+            # world size, sharding mode and -skip state (the reference draws from an unseeded global stream)
+            np.random.seed((args.seed * 1000003 + bi) % (2 ** 32))
             batch = {s: {k: v[start:start + bs].to(device) for k, v in data[s].items()} for s in ('optical', 'thermal')}
             Hs = masks = None
             if world > 1 and args.shard_homographies:

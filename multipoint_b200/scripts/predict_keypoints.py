@@ -43,7 +43,7 @@ def main(argv=None):
             prob = out['prob'] * data[s]['valid_mask'] if args.mask else out['prob']
             if pred['nms'] > 0:
                 # one fused call: dense NMS map + ordered keypoints (the torch.nonzero idiom :181-183)
-                cap = pred['topk'] if pred['topk'] > 0 else prob.shape[-1] * prob.shape[-2] // 4
+                cap = pred['topk'] if pred['topk'] > 0 else None    # None = H*W: never truncates, whatever the box size
                 dense, kp, sc, cnt = utils.box_nms_keypoints(prob, pred['nms'], pred['detection_threshold'],
                                                              keep_top_k=pred['topk'], kp_cap=cap)
             else:

@@ -189,7 +189,9 @@ def match_descriptors(desc_1, desc_2, method='bfmatcher', knn_matches=False, **k
                 raise ValueError('BFMatcher.knnMatch(k=2) is not available with crossCheck=True '
                                  '(OpenCV asserts K == 1 && update == 0)')
             if desc_2.shape[0] < 2:
-                return tuple(torch.zeros((0,), dtype=dt, device=desc_1.device) for dt in (torch.int32, torch.int32, torch.float32))
+                # knnMatch(k=2) returns 1-element lists here and the reference's ``for m, n in all_matches``
+                # (matching.py:24) raises exactly this
+                raise ValueError('not enough values to unpack (expected 2, got %d)' % desc_2.shape[0])
             q, t, d, c = ops.match(desc_1, desc_2, metric='l2', kind='ratio', ratio=0.9)
         else:
             q, t, d, c = ops.match(desc_1, desc_2, metric='l2', kind='mutual', cross_check=cross)
@@ -518,7 +520,7 @@ def _net_prob(net, images, extra, chunk_imgs):
     return torch.cat(outs) if len(outs) > 1 else outs[0]
 
 
-def _adaptation_core(images, is_optical, net, config, second, homographies, masks, rank, world, fused):
+def _adaptation_core(images, is_optical, net, config, second, homographies, masks, rank, world, fused, normalized=None):
     """Identity pass + this rank's share of the sampled homographies.
     fused=True  -> the finished heatmap (B,H,W) in one aggregate launch (single process).
     fused=False -> partial accumulators (prob_sum, count_sum); rank 0's include the identity pass."""
@@ -563,9 +565,13 @@ def _adaptation_core(images, is_optical, net, config, second, homographies, mask
         return ops.ha_aggregate(prob0, empty, None if second is None else empty, torch.zeros((0, H, W), dtype=torch.uint8, device=dev),
                                 torch.zeros((0, 3, 3), device=dev), agg, config['min_count'], init=(rank == 0), finish=fused, tables=tables)
     H_mine = np.asarray(homographies, np.float64)[mine]
-    Hm = torch.from_numpy(H_mine.astype(np.float32))
-    A_warp = normalized_warp_matrix(Hm, (H, W), (H, W)).to(dev)
-    A_unwarp = normalized_warp_matrix(torch.inverse(Hm), (H, W), (H, W)).to(dev)  # torch.inverse(homography) :112,:180
+    if normalized is not None:   # (A_warp, A_unwarp) given: the per-pixel arithmetic on its own (parity tests)
+        A_warp = torch.as_tensor(np.asarray(normalized[0], np.float32)[mine]).to(dev)
+        A_unwarp = torch.as_tensor(np.asarray(normalized[1], np.float32)[mine]).to(dev)
+    else:
+        Hm = torch.from_numpy(H_mine.astype(np.float32))
+        A_warp = normalized_warp_matrix(Hm, (H, W), (H, W)).to(dev)
+        A_unwarp = normalized_warp_matrix(torch.inverse(Hm), (H, W), (H, W)).to(dev)  # torch.inverse(homography) :112,:180
     if masks is None:   # built on the device, this rank's share only
         mk = compute_valid_masks((H, W), H_mine, config['erosion_radius'], config['mask_border'], dev)
     elif torch.is_tensor(masks):
@@ -609,40 +615,44 @@ def adaptation_finish(prob_sum, count_sum, aggregation, min_count):
                             aggregation, min_count, init=False, finish=True, prob_acc=prob_sum, count_acc=count_sum)
 
 
-def _adaptation(images, is_optical, net, config, second=None, homographies=None, masks=None, shard=None):
+def _adaptation(images, is_optical, net, config, second=None, homographies=None, masks=None, shard=None, normalized=None):
     """Shared body of the two adaptation entry points.  ``shard=(rank, world, all_reduce)`` splits
     the sampled homographies round-robin across ranks (every rank must be given the same
     ``homographies`` / ``masks``, see parallel.broadcast_homographies) and sums the two accumulators
     with ``all_reduce`` before the finish.  Without ``shard`` everything runs in one fused launch
     in the reference's summation order."""
     if shard is None or shard[1] == 1:
-        return _adaptation_core(images, is_optical, net, config, second, homographies, masks, 0, 1, True)[:, None]
+        return _adaptation_core(images, is_optical, net, config, second, homographies, masks, 0, 1, True, normalized)[:, None]
     rank, world, all_reduce = shard
     if homographies is None:
         raise ValueError("sharded homographic adaptation needs pre-sampled homographies shared by all ranks")
-    prob_sum, count_sum = _adaptation_core(images, is_optical, net, config, second, homographies, masks, rank, world, False)
+    prob_sum, count_sum = _adaptation_core(images, is_optical, net, config, second, homographies, masks, rank, world, False, normalized)
     all_reduce(prob_sum)
     all_reduce(count_sum)
     agg = config['aggregation'] if second is not None else 'none'
     return adaptation_finish(prob_sum, count_sum, agg, config['min_count'])[:, None]
 
 
-def homographic_adaptation(data, net, homographic_adaptation_config={}, homographies=None, masks=None, shard=None):
+def homographic_adaptation(data, net, homographic_adaptation_config={}, homographies=None, masks=None, shard=None,
+                           normalized_matrices=None):
     """Drop-in for utils.homographic_adaptation (homographies.py:130-189).  ``net`` is any callable
     dict -> {'prob': (B,1,H,W)}.  Optional ``homographies`` / ``masks`` replace the host sampling
-    (tests, multi-GPU broadcast); ``shard`` see _adaptation."""
+    (tests, multi-GPU broadcast); ``shard`` see _adaptation; ``normalized_matrices=(A_warp, A_unwarp)`` (n,3,3)
+    replaces the 3x3 normalisation algebra of warp_perspective_tensor by given matrices (parity tests pin the
+    per-pixel arithmetic with it)."""
     config = _check_ha_config(homographic_adaptation_config)
     device = data['image'].device
-    out = _adaptation(data['image'], data.get('is_optical'), net, config, None, homographies, masks, shard)
+    out = _adaptation(data['image'], data.get('is_optical'), net, config, None, homographies, masks, shard, normalized_matrices)
     return out.to(device)
 
 
-def homographic_adaptation_multispectral(data, net, homographic_adaptation_config={}, homographies=None, masks=None, shard=None):
+def homographic_adaptation_multispectral(data, net, homographic_adaptation_config={}, homographies=None, masks=None, shard=None,
+                                         normalized_matrices=None):
     """Drop-in for utils.homographic_adaptation_multispectral (homographies.py:38-128)."""
     config = _check_ha_config(homographic_adaptation_config)
     device = data['optical']['image'].device
     if config['aggregation'] not in ('prod', 'sum'):
         raise ValueError('Unknown aggregation: ' + config['aggregation'])
     out = _adaptation(data['optical']['image'], data['optical'].get('is_optical'), net, config,
-                      (data['thermal']['image'], data['thermal'].get('is_optical')), homographies, masks, shard)
+                      (data['thermal']['image'], data['thermal'].get('is_optical')), homographies, masks, shard, normalized_matrices)
     return out.to(device)

@@ -436,6 +436,21 @@ def gen_adaptation():
             data = {'optical': {'image': img_o.clone(), 'is_optical': torch.ones(2, 1, dtype=torch.bool)},
                     'thermal': {'image': img_t.clone(), 'is_optical': torch.zeros(2, 1, dtype=torch.bool)}}
             out["multi_" + agg] = hom.homographic_adaptation_multispectral(data, net, cfg).numpy()
+        # the Gaussian-filter branch (filter_size > 0, homographies.py:54-58,100-102,145-149,177-178) on the same stream
+        np.random.seed(5)
+        out["single_f5"] = hom.homographic_adaptation({'image': img_o.clone()}, net, dict(base, aggregation='prod', filter_size=5)).numpy()
+        np.random.seed(5)
+        data = {'optical': {'image': img_o.clone(), 'is_optical': torch.ones(2, 1, dtype=torch.bool)},
+                'thermal': {'image': img_t.clone(), 'is_optical': torch.zeros(2, 1, dtype=torch.bool)}}
+        out["multi_prod_f5"] = hom.homographic_adaptation_multispectral(data, net, dict(base, aggregation='prod', filter_size=5)).numpy()
+        # the filter itself (utils.py:124-157): weights for three sizes / an explicit sigma, and its action on a heatmap
+        for k, sg in ((3, None), (5, None), (7, 1.5)):
+            f = utils.get_gaussian_filter(k) if sg is None else utils.get_gaussian_filter(k, sg)
+            out["gauss_w_%d" % k] = f.weight.detach().numpy()
+        f5 = utils.get_gaussian_filter(5)
+        p_in = net({'image': img_o})['prob']
+        out["gauss_in"] = p_in.numpy()
+        out["gauss_out_5"] = f5(torch.nn.ReflectionPad2d(2)(p_in)).detach().numpy()
         # the homographies / masks the calls above consumed (same RNG stream)
         np.random.seed(5)
         Hs, masks = [], []
@@ -505,7 +520,7 @@ def gen_model():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["heads", "nms", "interp", "matching", "homographies", "adaptation", "model"]
+    which = sys.argv[1:] or ["heads", "magicleap", "nms", "interp", "matching", "homographies", "adaptation", "model", "evaluation"]
     errs = {}
     for w in which:
         r = globals()["gen_" + w]()

@@ -256,3 +256,18 @@ def test_folded_batchnorm_cache_follows_training_mode_updates():
     bn.eval()
     scale, _ = models.MultiPoint._folded_bn(bn)
     torch.testing.assert_close(scale, bn.weight.detach() / torch.sqrt(bn.running_var + bn.eps), rtol=1e-6, atol=0)
+
+
+def test_gaussian_filter_matches_reference_fixture():
+    """Row 12 (utils.get_gaussian_filter, multipoint/utils/utils.py:124-157): weights for three sizes (default and
+    explicit sigma) and the filter's action with the adaptation's reflection padding, against the reference's own
+    outputs frozen by oracle/gen_golden.py."""
+    import torch
+    from multipoint_b200 import utils
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "adaptation.npz"))
+    for k, sg in ((3, None), (5, None), (7, 1.5)):
+        f = utils.get_gaussian_filter(k) if sg is None else utils.get_gaussian_filter(k, sg)
+        assert isinstance(f, torch.nn.Conv2d) and f.bias is None and not f.weight.requires_grad
+        np.testing.assert_array_equal(f.weight.detach().numpy(), g["gauss_w_%d" % k])
+    out = utils.get_gaussian_filter(5)(torch.nn.ReflectionPad2d(2)(torch.from_numpy(g["gauss_in"]))).detach().numpy()
+    np.testing.assert_allclose(out, g["gauss_out_5"], rtol=1e-6, atol=1e-9)
