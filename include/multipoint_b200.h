@@ -74,6 +74,11 @@ MP_API int mp_depth_to_space_f32(const float *x, int B, int C, int Hc, int Wc, i
  * may be NULL.  The channels-last copy feeds mp_sample_descriptors_f32 with coalesced rows. */
 MP_API int mp_normalize_descriptors_f32(const float *x, int B, int D, int HW, float *out_nchw,
                                         float *out_nhwc, mp_stream_t stream);
+/* (B,D,HW) -> channels-last (B,HW,D) copy of a descriptor map (no arithmetic): the layout change
+ * utils.interpolate_descriptors (utils.py:159-167) makes once per call before sampling, because a
+ * bilinear corner is then one contiguous D*4 B row instead of D strided words. */
+MP_API int mp_transpose_descriptors_f32(const float *x, int B, int D, int HW, float *out_nhwc,
+                                        mp_stream_t stream);
 
 /* ---- row 4: utils.box_nms, multipoint/utils/utils.py:78-122 -------------------------------
  * Greedy IoU NMS of size x size boxes centred on every pixel with prob > min_prob (strict,

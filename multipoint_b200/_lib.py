@@ -25,6 +25,7 @@ SIGNATURES = {
     "mp_heatmap_magicleap_f32": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "mp_depth_to_space_f32": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "mp_normalize_descriptors_f32": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
+    "mp_transpose_descriptors_f32": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "mp_box_nms_workspace_bytes": (_sz, [_i, _i, _i]),
     "mp_box_nms_f32": (_i, [_vp, _i, _i, _i, _d, _d, _d, _i, _vp, _vp, _vp, _vp, _i, _vp, _sz, _vp]),
     "mp_extract_keypoints_workspace_bytes": (_sz, [_i, _i, _i]),

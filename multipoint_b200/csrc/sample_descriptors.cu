@@ -81,27 +81,26 @@ sample_descriptors_kernel(const int64_t *__restrict__ kp, const int32_t *__restr
     }
 }
 
-// Channels-last fast path: D = 32 * V * NV, every lane moves V-wide vectors (128-bit for V=4), so a
-// corner row of D*4 bytes is NV fully coalesced requests instead of D/32 scalar ones.
-template <int V, int NV>
+// Channels-last fast path: a group of LPK lanes per keypoint, every lane moving 128-bit vectors: D = 4 * LPK * NV.
+// A corner row of D*4 bytes is NV fully coalesced requests.  D = 64 (the shipped descriptor size) uses 16 lanes per
+// keypoint, i.e. two keypoints per warp: with a whole warp per keypoint and 64-bit vectors it spent as many
+// instructions per keypoint as D = 256 on a quarter of the bytes (47 % of the HBM roofline).
+template <int LPK, int NV>
 __global__ void __launch_bounds__(SD_WARPS * 32)
 sample_descriptors_nhwc_vec_kernel(const int64_t *__restrict__ kp, const int32_t *__restrict__ counts,
                                    const float *__restrict__ desc, float *__restrict__ out, int B, int K, int Hc, int Wc,
                                    float half_h, float half_w) {
-    constexpr int D = 32 * V * NV;
-    const int lane = threadIdx.x & 31;
-    const long long item = (long long)blockIdx.x * SD_WARPS + (threadIdx.x >> 5);
-    if (item >= (long long)B * K) return;
-    const int b = (int)(item / K), k = (int)(item - (long long)b * K);
-    float *o = out + (size_t)item * D;
+    constexpr int D = 4 * LPK * NV, KPW = 32 / LPK;   // keypoints per warp
+    const int lane = threadIdx.x & 31, sub = lane % LPK;
+    const long long item = ((long long)blockIdx.x * SD_WARPS + (threadIdx.x >> 5)) * KPW + lane / LPK;
+    const bool in_range = item < (long long)B * K;     // ragged last warp: the lanes still take part in the shuffles
+    const int b = in_range ? (int)(item / K) : 0, k = in_range ? (int)(item - (long long)b * K) : 0;
     const int n = counts ? min(counts[b], K) : K;
-    float v[NV][V];
-    if (k >= n) {
+    float4 v[NV];
 #pragma unroll
-        for (int j = 0; j < NV; ++j)
-#pragma unroll
-            for (int e = 0; e < V; ++e) v[j][e] = 0.f;
-    } else {
+    for (int j = 0; j < NV; ++j) v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool live = in_range && k < n;
+    if (live) {
         const float y = (float)kp[2 * item], x = (float)kp[2 * item + 1];
         const float yn = __fsub_rn(__fdiv_rn(y, half_h), 1.0f);
         const float xn = __fsub_rn(__fdiv_rn(x, half_w), 1.0f);
@@ -113,46 +112,41 @@ sample_descriptors_nhwc_vec_kernel(const int64_t *__restrict__ kp, const int32_t
                              __fmul_rn((float)x1 - ix, iy - (float)y0), __fmul_rn(ix - (float)x0, iy - (float)y0)};
         const int cy[4] = {y0, y0, y1, y1}, cx[4] = {x0, x1, x0, x1};
         const float *m = desc + (size_t)b * Hc * Wc * D;
+        // all corner rows are requested before the first is used (nw, ne, sw, se = the reference's accumulation order)
+        float4 t[4][NV];
 #pragma unroll
-        for (int j = 0; j < NV; ++j)
+        for (int c = 0; c < 4; ++c) {
+            const bool ok = cy[c] >= 0 && cy[c] < Hc && cx[c] >= 0 && cx[c] < Wc;
+            const float4 *rowp = reinterpret_cast<const float4 *>(m + ((size_t)(ok ? cy[c] : 0) * Wc + (ok ? cx[c] : 0)) * D);
 #pragma unroll
-            for (int e = 0; e < V; ++e) v[j][e] = 0.f;
+            for (int j = 0; j < NV; ++j) t[c][j] = ok ? __ldg(rowp + sub + LPK * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {  // nw, ne, sw, se in the reference's accumulation order
-            if (cy[c] < 0 || cy[c] >= Hc || cx[c] < 0 || cx[c] >= Wc) continue;
-            const float *rowp = m + ((size_t)cy[c] * Wc + cx[c]) * D;
+        for (int c = 0; c < 4; ++c) {
+            if (cy[c] < 0 || cy[c] >= Hc || cx[c] < 0 || cx[c] >= Wc) continue;   // a corner outside contributes nothing (not +0)
 #pragma unroll
             for (int j = 0; j < NV; ++j) {
-                float t[V];
-                if (V == 4) {
-                    const float4 q = __ldg(reinterpret_cast<const float4 *>(rowp) + lane + 32 * j);
-                    t[0] = q.x; t[1] = q.y; t[2 % V] = q.z; t[3 % V] = q.w;
-                } else {
-                    const float2 q = __ldg(reinterpret_cast<const float2 *>(rowp) + lane + 32 * j);
-                    t[0] = q.x; t[1] = q.y;
-                }
-#pragma unroll
-                for (int e = 0; e < V; ++e) v[j][e] = __fadd_rn(v[j][e], __fmul_rn(t[e], w4[c]));
+                v[j].x = __fadd_rn(v[j].x, __fmul_rn(t[c][j].x, w4[c]));
+                v[j].y = __fadd_rn(v[j].y, __fmul_rn(t[c][j].y, w4[c]));
+                v[j].z = __fadd_rn(v[j].z, __fmul_rn(t[c][j].z, w4[c]));
+                v[j].w = __fadd_rn(v[j].w, __fmul_rn(t[c][j].w, w4[c]));
             }
         }
-        float ss = 0.f;
+    }
+    float ss = 0.f;
 #pragma unroll
-        for (int j = 0; j < NV; ++j)
+    for (int j = 0; j < NV; ++j) ss += v[j].x * v[j].x + v[j].y * v[j].y + v[j].z * v[j].z + v[j].w * v[j].w;
 #pragma unroll
-            for (int e = 0; e < V; ++e) ss += v[j][e] * v[j][e];
-#pragma unroll
-        for (int s = 16; s > 0; s >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, s);
+    for (int s = LPK / 2; s > 0; s >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, s);
+    if (!in_range) return;
+    if (live) {
         const float denom = fmaxf(sqrtf(ss), 1e-12f);
 #pragma unroll
-        for (int j = 0; j < NV; ++j)
-#pragma unroll
-            for (int e = 0; e < V; ++e) v[j][e] = v[j][e] / denom;
+        for (int j = 0; j < NV; ++j) { v[j].x = v[j].x / denom; v[j].y = v[j].y / denom; v[j].z = v[j].z / denom; v[j].w = v[j].w / denom; }
     }
+    float4 *o = reinterpret_cast<float4 *>(out + (size_t)item * D);
 #pragma unroll
-    for (int j = 0; j < NV; ++j) {
-        if (V == 4) reinterpret_cast<float4 *>(o)[lane + 32 * j] = make_float4(v[j][0], v[j][1], v[j][2 % V], v[j][3 % V]);
-        else reinterpret_cast<float2 *>(o)[lane + 32 * j] = make_float2(v[j][0], v[j][1]);
-    }
+    for (int j = 0; j < NV; ++j) o[sub + LPK * j] = v[j];
 }
 
 }  // namespace mp
@@ -173,9 +167,10 @@ extern "C" int mp_sample_descriptors_f32(const int64_t *keypoints, const int32_t
     const bool aligned = (((uintptr_t)desc | (uintptr_t)out) & 15) == 0;
     cudaStream_t s = (cudaStream_t)stream;
     if (layout == MP_LAYOUT_NHWC && aligned && (D == 64 || D == 128 || D == 256)) {
-        if (D == 64) mp::sample_descriptors_nhwc_vec_kernel<2, 1><<<grid, mp::SD_WARPS * 32, 0, s>>>(keypoints, kp_counts, desc, out, B, K, Hc, Wc, hh, hw);
-        else if (D == 128) mp::sample_descriptors_nhwc_vec_kernel<4, 1><<<grid, mp::SD_WARPS * 32, 0, s>>>(keypoints, kp_counts, desc, out, B, K, Hc, Wc, hh, hw);
-        else mp::sample_descriptors_nhwc_vec_kernel<4, 2><<<grid, mp::SD_WARPS * 32, 0, s>>>(keypoints, kp_counts, desc, out, B, K, Hc, Wc, hh, hw);
+        const unsigned grid2 = (unsigned)((items + 2 * mp::SD_WARPS - 1) / (2 * mp::SD_WARPS));   // two keypoints per warp
+        if (D == 64) mp::sample_descriptors_nhwc_vec_kernel<16, 1><<<grid2, mp::SD_WARPS * 32, 0, s>>>(keypoints, kp_counts, desc, out, B, K, Hc, Wc, hh, hw);
+        else if (D == 128) mp::sample_descriptors_nhwc_vec_kernel<32, 1><<<grid, mp::SD_WARPS * 32, 0, s>>>(keypoints, kp_counts, desc, out, B, K, Hc, Wc, hh, hw);
+        else mp::sample_descriptors_nhwc_vec_kernel<32, 2><<<grid, mp::SD_WARPS * 32, 0, s>>>(keypoints, kp_counts, desc, out, B, K, Hc, Wc, hh, hw);
     } else if (layout == MP_LAYOUT_NHWC)
         mp::sample_descriptors_kernel<MP_LAYOUT_NHWC><<<grid, mp::SD_WARPS * 32, 0, (cudaStream_t)stream>>>(
             keypoints, kp_counts, desc, out, B, K, D, Hc, Wc, hh, hw);
