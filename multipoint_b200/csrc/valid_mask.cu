@@ -14,8 +14,10 @@
 //
 // One CTA owns VM_TH output rows of one mask: raw bits for VM_TH + 2r rows go to shared memory as
 // one bit per pixel (warp ballot), the erosion is funnel-shift ANDs along the row and ANDs down the
-// column, and the result leaves as bytes.  ~35 double operations per pixel and 1 B written: far
-// from any roofline that matters (99 masks of 512x640 = 32 MB).
+// column, and the result leaves as bytes.  The ~35 double operations (one of them a division) per pixel made the kernel
+// the largest of the adaptation batch (0.33 ms for 99 masks, fp64 pipe + the division's instruction sequence); a pixel
+// is now classified in fp32 first, with an explicit error bound, and only falls through to the exact sequence when its
+// source position is within that bound of the image border.
 #include "mp_common.cuh"
 
 namespace mp {
@@ -46,36 +48,63 @@ valid_mask_kernel(const double *__restrict__ Minv, int H, int W, int r, int mask
     const uint32_t border = mask_border ? 0u : 0xffffffffu;
 
     double M[9];
+    float Mf[9];
 #pragma unroll
-    for (int i = 0; i < 9; ++i) M[i] = Minv[(size_t)n * 9 + i];
+    for (int i = 0; i < 9; ++i) { M[i] = Minv[(size_t)n * 9 + i]; Mf[i] = (float)M[i]; }
 
-    // phase 1: raw bits, one warp per (row, word)
-    for (int t = warp; t < rows * nw; t += VM_THREADS / 32) {
-        const int rr = t / nw, w = t - rr * nw;
+    // phase 1: raw bits, one warp per row, word after word
+    // Fast classification in fp32 with a per-pixel error bound: only pixels whose source position lies within that bound of
+    // the image border (a curve: ~1 % of the warps) pay for OpenCV's exact double sequence.  With c = (size - 1) / 2:
+    //   inside  <=> |p - c| <= size / 2 (both axes),  so  surely inside  <=> |p - c| + e <= size / 2
+    //                                                     surely outside <=> |p - c| - e >  size / 2 (either axis)
+    // e >= 8x the fp32 error (matrix entries rounded to fp32, three fused terms per sum, approximate reciprocal, product:
+    // <= 4e-7 * (sum of magnitudes of the numerator + |quotient| * those of the denominator) / |denominator|) + 1e-4 px.
+    const float a6 = fabsf(Mf[6]), a0 = fabsf(Mf[0]), a3 = fabsf(Mf[3]);
+    const float cxm = 0.5f * (float)(W - 1), cym = 0.5f * (float)(H - 1), hw_ = 0.5f * (float)W, hh_ = 0.5f * (float)H;
+    for (int rr = warp; rr < rows; rr += VM_THREADS / 32) {
         const int y = y0 - r + rr;
-        uint32_t word;
+        uint32_t *dst = raw + rr * ld + 1;
         if (y < 0 || y >= H) {
-            word = border;
-        } else {
+            for (int w = lane; w < nw; w += 32) dst[w] = border;
+            continue;
+        }
+        const float fy = (float)y;
+        const float cden = fmaf(Mf[7], fy, Mf[8]), csd = fmaf(fabsf(Mf[7]), fy, fabsf(Mf[8]));
+        const float cnx = fmaf(Mf[1], fy, Mf[2]), csx = fmaf(fabsf(Mf[1]), fy, fabsf(Mf[2]));
+        const float cny = fmaf(Mf[4], fy, Mf[5]), csy = fmaf(fabsf(Mf[4]), fy, fabsf(Mf[5]));
+        for (int w = 0; w < nw; ++w) {
             const int x = 32 * w + lane;
             bool in = false;
             if (x < W) {
-                const int xb = (x / bw0) * bw0, x1 = x - xb;
-                const double dy = (double)y, dxb = (double)xb, dx1 = (double)x1;
-                const double X0 = __dadd_rn(__dadd_rn(__dmul_rn(M[0], dxb), __dmul_rn(M[1], dy)), M[2]);
-                const double Y0 = __dadd_rn(__dadd_rn(__dmul_rn(M[3], dxb), __dmul_rn(M[4], dy)), M[5]);
-                const double W0 = __dadd_rn(__dadd_rn(__dmul_rn(M[6], dxb), __dmul_rn(M[7], dy)), M[8]);
-                double wv = __dadd_rn(W0, __dmul_rn(M[6], dx1));
-                wv = (wv != 0.0) ? __ddiv_rn(1.0, wv) : 0.0;
-                const int sx = vm_round_sat(__dmul_rn(__dadd_rn(X0, __dmul_rn(M[0], dx1)), wv));
-                const int sy = vm_round_sat(__dmul_rn(__dadd_rn(Y0, __dmul_rn(M[3], dx1)), wv));
-                in = sx >= 0 && sx < W && sy >= 0 && sy < H;
+                const float fx = (float)x;
+                const float den = fmaf(Mf[6], fx, cden), sd = fmaf(a6, fx, csd);
+                const float rd = __fdividef(1.0f, den), ard = fabsf(rd);
+                const float px = fmaf(Mf[0], fx, cnx) * rd, py = fmaf(Mf[3], fx, cny) * rd;
+                const float ex = fmaf(3.2e-6f * ard, fmaf(fabsf(px), sd, fmaf(a0, fx, csx)), 1e-4f);
+                const float ey = fmaf(3.2e-6f * ard, fmaf(fabsf(py), sd, fmaf(a3, fx, csy)), 1e-4f);
+                const float dx = fabsf(px - cxm), dyv = fabsf(py - cym);
+                const bool sane = fabsf(den) > 1e-3f * sd && dx < 1e6f && dyv < 1e6f;   // false for NaN / infinities
+                const bool fast_in = sane && dx + ex <= hw_ && dyv + ey <= hh_;
+                const bool fast_out = sane && (dx - ex > hw_ || dyv - ey > hh_);
+                in = fast_in;
+                if (!fast_in && !fast_out) {
+                    const int xb = (x / bw0) * bw0, x1 = x - xb;
+                    const double dy = (double)y, dxb = (double)xb, dx1 = (double)x1;
+                    const double X0 = __dadd_rn(__dadd_rn(__dmul_rn(M[0], dxb), __dmul_rn(M[1], dy)), M[2]);
+                    const double Y0 = __dadd_rn(__dadd_rn(__dmul_rn(M[3], dxb), __dmul_rn(M[4], dy)), M[5]);
+                    const double W0 = __dadd_rn(__dadd_rn(__dmul_rn(M[6], dxb), __dmul_rn(M[7], dy)), M[8]);
+                    double wv = __dadd_rn(W0, __dmul_rn(M[6], dx1));
+                    wv = (wv != 0.0) ? __ddiv_rn(1.0, wv) : 0.0;
+                    const int sx = vm_round_sat(__dmul_rn(__dadd_rn(X0, __dmul_rn(M[0], dx1)), wv));
+                    const int sy = vm_round_sat(__dmul_rn(__dadd_rn(Y0, __dmul_rn(M[3], dx1)), wv));
+                    in = sx >= 0 && sx < W && sy >= 0 && sy < H;
+                }
             }
-            word = __ballot_sync(0xffffffffu, in);
+            uint32_t word = __ballot_sync(0xffffffffu, in);
             const int tail = W - 32 * w;           // pixels of this word that exist
             if (tail < 32) word = (word & ((1u << tail) - 1u)) | (border & ~((1u << tail) - 1u));
+            if (lane == 0) dst[w] = word;
         }
-        if (lane == 0) raw[rr * ld + 1 + w] = word;
     }
     for (int rr = threadIdx.x; rr < rows; rr += VM_THREADS) {
         raw[rr * ld] = border;
