@@ -388,7 +388,7 @@ def main():
         logits = torch.randn((2 * P, 65, H // 8, W // 8), generator=g, device=dev) * 2.0
         logits[:, 64] += 5.0
         raw = torch.randn((2 * P, args.desc, H // 8, W // 8), generator=g, device=dev)
-        pipe = KeypointPipeline(None, nms=4, detection_threshold=0.015, topk=args.topk, metric='l2', cross_check=True)
+        pipe = KeypointPipeline(None, nms=4, detection_threshold=0.015, topk=args.topk, metric='l2', cross_check=True, dense_nms_map=False)
 
         def hot_only():
             ext = pipe.extract_from_backbone(logits, raw, H, W)
@@ -418,7 +418,7 @@ def main():
         return 0
 
     net = build_net(args.desc, dev)
-    pipe = KeypointPipeline(net, nms=4, detection_threshold=0.015, topk=args.topk, metric='l2', cross_check=True)
+    pipe = KeypointPipeline(net, nms=4, detection_threshold=0.015, topk=args.topk, metric='l2', cross_check=True, dense_nms_map=False)
     batch = syn.image_pair_batch(1000 + rank, P, H, W)
     host = {s: {k: torch.from_numpy(v).pin_memory() for k, v in batch[s].items() if k != 'valid_mask'} for s in ('optical', 'thermal')}
     resident = {s: {k: v.to(dev) for k, v in host[s].items()} for s in host}
@@ -520,8 +520,9 @@ def main():
     stages = {
         "detector_head": (lambda: ops.detector_head(logits), B2 * (65 * 5120 * 4 + H * W * 4)),
         "nms_tile(+fixup launch)": (lambda: ops.box_nms(prob, 4, 0.015), B2 * 2 * H * W * 4),
-        "nms_full(top-k+keypoints)": (lambda: ops.box_nms(prob, 4, 0.015, keep_top_k=args.topk, want_keypoints=True, kp_cap=args.topk),
-                                      B2 * (2 * H * W * 4 + 20 * args.topk)),
+        "nms_full(top-k+keypoints, no dense map)": (lambda: ops.box_nms(prob, 4, 0.015, keep_top_k=args.topk, want_keypoints=True, kp_cap=args.topk,
+                                                                        want_dense=False),
+                                                    B2 * (H * W * 4 + 20 * args.topk)),
         "normalize_desc_nhwc": (lambda: ops.normalize_descriptors(raw, nchw=False, nhwc=True), B2 * 2 * 4 * args.desc * 5120),
         "sample_descriptors": (lambda: ops.sample_descriptors(kp, ops.normalize_descriptors(raw, nchw=False, nhwc=True)[1], H, W, counts=cnt, channels_last=True), None),
         "match(both directions+select)": (lambda: ops.match(desc_s[:P], desc_s[P:], metric='l2', kind='mutual', cross_check=True, n1=cnt[:P], n2=cnt[P:]), None),
@@ -573,7 +574,7 @@ def main():
     algorithmic = {  # per launch: ("hbm", bytes) or ("tensor", flops); SURVEY.md 8d / DESIGN.md section 4
         "detector_head_kernel": ("hbm", B2 * (65 * 5120 * 4 + H * W * 4)),
         "nms_tile_fast_kernel": ("hbm", B2 * 2 * H * W * 4),
-        "nms_candidates_kernel": ("hbm", B2 * 2 * H * W * 4),   # heatmap read + dense map written (the candidate list is extra)
+        "nms_candidates_kernel": ("hbm", B2 * H * W * 4),       # heatmap read (keypoints only: no dense map; the candidate list is extra)
         "normalize_desc_kernel": ("hbm", B2 * 2 * 4 * Dd * 5120),
         "sample_descriptors_kernel": ("hbm", B2 * (min(16 * Kp * Dd, 4 * Dd * 5120) + 4 * Kp * Dd + 16 * Kp)),
         "match_prep_vec_kernel": ("hbm", P * Kp * Dd * (4 + 2 + 2)),

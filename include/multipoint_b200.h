@@ -87,8 +87,10 @@ MP_API int mp_transpose_descriptors_f32(const float *x, int B, int D, int HW, fl
  * Optional ordered outputs (the torch.nonzero idiom of predict_align_image_pair.py:170-171):
  *   keypoints (B,kp_cap,2) int64 (y,x) in row-major order, kp_scores (B,kp_cap),
  *   kp_counts (B) = survivors per image (may exceed kp_cap: only kp_cap are written).
- * Pass NULL for the three to skip them.  min_prob must be >= 0 (MP_ERR_UNSUPPORTED otherwise:
- * probabilities are non-negative, and the dense result cannot represent a kept zero). */
+ * Pass NULL for the three to skip them.  prob_nms may be NULL when kp_counts is given (keypoints
+ * only: the dense map is then neither zero-filled nor written -- the sync-free pipeline's case).
+ * min_prob must be >= 0 (MP_ERR_UNSUPPORTED otherwise: probabilities are non-negative, and the
+ * dense result cannot represent a kept zero). */
 MP_API size_t mp_box_nms_workspace_bytes(int B, int H, int W);
 MP_API int mp_box_nms_f32(const float *prob, int B, int H, int W, double size, double min_prob,
                           double iou, int keep_top_k, float *prob_nms, int64_t *keypoints,

@@ -24,7 +24,7 @@
 //  sparse top-k path (keep_top_k > 0, the shipped configuration; see the comment above nms_candidates_kernel)
 //   1'. nms_candidates_kernel  streams the heatmap once: zero-fills the dense map, lists the candidates and
 //                        histograms their scores.
-//   2'. nms_sparse_kernel  one CTA per image settles only the candidates that can reach the top k.
+//   2'. nms_sparse2_kernel one CTA per image settles only the candidates that can reach the top k, cuts to k and emits.
 //  both
 //   3. nms_select_kernel one CTA per image; optional top-k by radix select on (score desc, index
 //                        asc), then ordered (row-major) compaction of the survivors through a
@@ -871,16 +871,15 @@ __device__ void emit_from_bitmap(const uint32_t *bitmap, int words, int W, const
 //  1. nms_candidates_kernel streams the heatmap once (HBM-bound): zero-fills the dense output,
 //     appends every candidate (pixel, score bits) to a per-image list and histograms the scores
 //     into 128 monotone bins (exponent + 4 mantissa bits),
-//  2. nms_sparse_kernel (one CTA per image) picks the bin threshold that admits ~1.5 k
+//  2. nms_sparse2_kernel (one CTA per image) picks the bin threshold that admits ~1.5 k
 //     candidates, settles exactly those with the same fixed point as the tile kernel -- whole image
-//     in one CTA, so no apron and no fix-up; candidate bitmap in shared memory, signed state in the
-//     dense map (L2) -- and lowers the threshold and repeats while fewer than k survive,
-//  3. nms_select_kernel cuts to k and emits the keypoints as before.
-// An image that does not fit (more than SP_CAND_CAP candidates, or more than SP_LIST_CAP needed)
+//     in one CTA, so no apron and no fix-up; candidate bitmap, ranks and signed state all in shared
+//     memory -- lowers the threshold and repeats while fewer than k survive, then cuts to k and
+//     emits the keypoints in row-major order itself (nms_select_kernel only serves redone images).
+// An image that does not fit (more than SP_CAND_CAP candidates, or more than SP2_CAP needed)
 // raises its flag and is redone by the tile + fix-up kernels, which otherwise exit at once.
 constexpr int SP_BINS = 128;
 constexpr int SP_CAND_CAP = 1 << 16;  // candidates listed per image
-constexpr int SP_LIST_CAP = 8192;     // candidates settled per image by the sparse kernel
 constexpr int SP_CHUNK = 4096;        // pixels per CTA of the candidates kernel
 constexpr int SP_PAD = 3;             // footprint reach handled here
 
@@ -888,18 +887,20 @@ __device__ __forceinline__ int sp_bin(uint32_t bits) {  // monotone in the (posi
     return bits <= 0x3C000000u ? 0 : min(SP_BINS - 1, (int)((bits - 0x3C000000u) >> 19));
 }
 
-template <bool VEC>
+template <bool VEC, bool ZERO>   // ZERO: also zero-fill the dense output map (only when the caller asked for it)
 __global__ void __launch_bounds__(NMS_THREADS)  // 71 registers, 3 CTAs/SM; capping at 48 (5 CTAs/SM) measured the same 81 us
 nms_candidates_kernel(const float *__restrict__ prob, float *__restrict__ out, int HW, float thr,
                       uint2 *__restrict__ cands, int *__restrict__ cand_count, int *__restrict__ hist) {
-    __shared__ int sh_hist[SP_BINS];
+    // one histogram per warp: the scores cluster in a few bins just above the threshold, and a single shared histogram
+    // serialised its atomics there (ncu: 465 k bank conflicts per launch)
+    __shared__ int sh_hist[NMS_THREADS / 32][SP_BINS];
     __shared__ int warp_sums[NMS_THREADS / 32];
     __shared__ int sh_base;
     const int b = blockIdx.y, tid = threadIdx.x;
     const int p0 = blockIdx.x * SP_CHUNK;
     const float *img = prob + (size_t)b * HW;
-    float *dst = out + (size_t)b * HW;
-    if (tid < SP_BINS) sh_hist[tid] = 0;
+    float *dst = ZERO ? out + (size_t)b * HW : nullptr;
+    for (int i = tid; i < (NMS_THREADS / 32) * SP_BINS; i += NMS_THREADS) (&sh_hist[0][0])[i] = 0;
     constexpr int PER = SP_CHUNK / NMS_THREADS;  // 16 pixels per thread
     float v[PER];
     if (VEC) {
@@ -909,7 +910,7 @@ nms_candidates_kernel(const float *__restrict__ prob, float *__restrict__ out, i
             float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
             if (i < HW) {  // HW % 4 == 0 on this path
                 q = ld_stream_f4(reinterpret_cast<const float4 *>(img + i));
-                st_stream_f4(reinterpret_cast<float4 *>(dst + i), make_float4(0.f, 0.f, 0.f, 0.f));
+                if (ZERO) st_stream_f4(reinterpret_cast<float4 *>(dst + i), make_float4(0.f, 0.f, 0.f, 0.f));
             }
             v[4 * k + 0] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w;
         }
@@ -918,16 +919,17 @@ nms_candidates_kernel(const float *__restrict__ prob, float *__restrict__ out, i
         for (int k = 0; k < PER; ++k) {
             const int i = p0 + tid + k * NMS_THREADS;
             v[k] = 0.f;
-            if (i < HW) { v[k] = img[i]; dst[i] = 0.f; }
+            if (i < HW) { v[k] = img[i]; if (ZERO) dst[i] = 0.f; }
         }
     }
     __syncthreads();
     int mine = 0;
+    int *my_hist = sh_hist[tid >> 5];
 #pragma unroll
     for (int k = 0; k < PER; ++k)
         if (v[k] > thr) {  // strict, fp32 (utils.py:97); NaN is not a candidate
             ++mine;
-            atomicAdd(&sh_hist[sp_bin(__float_as_uint(v[k]))], 1);
+            atomicAdd(&my_hist[sp_bin(__float_as_uint(v[k]))], 1);
         }
     int total;
     const int off = block_exclusive_scan(mine, warp_sums, total);
@@ -944,248 +946,11 @@ nms_candidates_kernel(const float *__restrict__ prob, float *__restrict__ out, i
                 ++slot;
             }
     }
-    if (tid < SP_BINS && sh_hist[tid]) atomicAdd(hist + b * SP_BINS + tid, sh_hist[tid]);
-}
-
-__global__ void __launch_bounds__(1024, 1)
-nms_sparse_kernel(float *__restrict__ out, int H, int W, int keep_top_k, const NmsFootprint fp,
-                  const uint2 *__restrict__ cands, const int *__restrict__ cand_count, const int *__restrict__ hist,
-                  uint2 *__restrict__ survivors, int *__restrict__ surv_count, int cap, int *__restrict__ redo_flags) {
-    extern __shared__ __align__(16) uint8_t sp_smem[];
-    const int BWR = (W + 31) / 32 + 2;                 // one pad word on each side
-    const int BROWS = H + 2 * SP_PAD;
-    uint32_t *bm = reinterpret_cast<uint32_t *>(sp_smem);                       // [BROWS][BWR] candidate bitmap
-    uint64_t *mask = reinterpret_cast<uint64_t *>(bm + ((BROWS * BWR + 1) & ~1));  // [SP_LIST_CAP]
-    uint32_t *pos = reinterpret_cast<uint32_t *>(mask + SP_LIST_CAP);           // [SP_LIST_CAP] pixel of id
-    uint32_t *score = pos + SP_LIST_CAP;                                        // [SP_LIST_CAP] score bits of id
-    uint16_t *ids_a = reinterpret_cast<uint16_t *>(score + SP_LIST_CAP), *ids_b = ids_a + SP_LIST_CAP;
-    __shared__ int sh_hist[SP_BINS];
-    __shared__ int n_list, n_kept;
-    __shared__ int n_next[3];
-    __shared__ uint32_t fp7[7];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int b = blockIdx.x;
-    float *img = out + (size_t)b * H * W;
-    uint2 *surv = survivors + (size_t)b * cap;
-    const int n_all = cand_count[b];
-    if (n_all > SP_CAND_CAP) {  // list truncated: the dense kernels redo this image (block-uniform)
-        if (tid == 0) { redo_flags[b] = 1; surv_count[b] = 0; }
-        return;
-    }
-    const uint2 *list = cands + (size_t)b * SP_CAND_CAP;
-    if (tid < SP_BINS) sh_hist[tid] = hist[b * SP_BINS + tid];
-    if (tid < 7) {
-        const int dy = tid - SP_PAD;
-        fp7[tid] = (dy >= -fp.R && dy <= fp.R) ? (fp.rows[dy + fp.R] << (SP_PAD - fp.R)) : 0u;
-    }
-    __syncthreads();
-    // a kept candidate: final state in the dense map and an entry on the survivor list (warp-aggregated slot)
-    auto commit_kept = [&](bool kept, int e, uint32_t sbits) {
-        const unsigned bal = __ballot_sync(0xffffffffu, kept);
-        if (bal) {
-            int slot = 0;
-            if (lane == (__ffs(bal) - 1)) slot = atomicAdd(&n_kept, __popc(bal));
-            slot = __shfl_sync(0xffffffffu, slot, __ffs(bal) - 1);
-            if (kept) {
-                __stcg(img + e, __uint_as_float(sbits));
-                surv[slot + __popc(bal & ((1u << lane) - 1))] = make_uint2((uint32_t)e, sbits);
-            }
-        }
-    };
-
-    int target = min(SP_LIST_CAP, keep_top_k + keep_top_k / 2 + 256);
-    while (true) {
-        // threshold bin: the highest bin t with (number of candidates in bins >= t) >= target, or 0
-        int tb = 0, n_sel = 0;
-        {
-            int cum = 0;
-            tb = 0;
-            for (int t = SP_BINS - 1; t >= 0; --t) {  // 128 shared-memory reads per thread, uniform
-                cum += sh_hist[t];
-                if (cum >= target) { tb = t; break; }
-            }
-            n_sel = cum;  // when the loop ran out: every candidate
-        }
-        if (n_sel > SP_LIST_CAP) {
-            if (tid == 0) { redo_flags[b] = 1; surv_count[b] = 0; }
-            return;
-        }
-        // ---- list + bitmap + undecided state (-score) for the admitted candidates ----
-        for (int i = tid; i < BROWS * BWR; i += 1024) bm[i] = 0;
-        if (tid == 0) { n_list = 0; n_kept = 0; n_next[0] = n_next[1] = n_next[2] = 0; }
-        __syncthreads();
-        // pass 1 over the whole candidate list (42 k entries on the benchmark maps, 8 % admitted): nothing but
-        // the bin test and a warp-aggregated append of (pixel, score) -- eight independent loads per thread
-        constexpr int SCAN = 8;
-        for (int i0 = 0; i0 < n_all; i0 += 1024 * SCAN) {
-            uint2 c[SCAN];
+    if (tid < SP_BINS) {
+        int t = 0;
 #pragma unroll
-            for (int u = 0; u < SCAN; ++u) {
-                const int i = i0 + u * 1024 + tid;
-                c[u] = i < n_all ? __ldg(list + i) : make_uint2(0u, 0u);
-            }
-            uint32_t takes = 0;
-#pragma unroll
-            for (int u = 0; u < SCAN; ++u)
-                if ((i0 + u * 1024 + tid) < n_all && sp_bin(c[u].y) >= tb) takes |= 1u << u;
-            const int cnt = __popc(takes);
-            int inc = cnt;  // inclusive scan of the lanes' counts: one shared-memory atomic per warp and pass
-#pragma unroll
-            for (int sft = 1; sft < 32; sft <<= 1) {
-                const int t = __shfl_up_sync(0xffffffffu, inc, sft);
-                if (lane >= sft) inc += t;
-            }
-            int slot = 0;
-            if (lane == 31 && inc) slot = atomicAdd(&n_list, inc);
-            slot = __shfl_sync(0xffffffffu, slot, 31) + inc - cnt;
-#pragma unroll
-            for (int u = 0; u < SCAN; ++u)
-                if (takes & (1u << u)) { pos[slot] = c[u].x; score[slot] = c[u].y; ++slot; }
-        }
-        __syncthreads();
-        // pass 2 over the admitted ones only: bitmap bit and undecided state
-        for (int id = tid; id < n_list; id += 1024) {
-            const uint32_t e = pos[id];
-            const int y = (int)e / W, x = (int)e - y * W;
-            atomicOr(&bm[(y + SP_PAD) * BWR + ((x + 32) >> 5)], 1u << ((x + 32) & 31));
-            __stcg(img + e, -__uint_as_float(score[id]));
-        }
-        __syncthreads();
-        const int n0 = n_list;
-
-        // ---- round 0: higher-priority admitted neighbours of every admitted candidate ----
-        // mask bit 8*r + c  <=>  neighbour at (dy, dx) = (r - 3, c - 3).  Neighbour scores are read as |state|,
-        // so a neighbour that is already marked kept (+s) compares like an undecided one (-s).
-        for (int base = warp * 32; base < n0; base += 1024) {
-            const int id = base + lane;
-            bool still = false, kept = false;
-            int e = 0;
-            uint32_t sb = 0;
-            if (id < n0) {
-                e = (int)pos[id];
-                sb = score[id];
-                const int y = e / W, x = e - y * W;
-                const int bitpos = x + 32 - SP_PAD, w = bitpos >> 5, sh = bitpos & 31;
-                uint32_t lo = 0, hi = 0;
-#pragma unroll
-                for (int r = 0; r < 7; ++r) {
-                    const uint32_t *bw = bm + (y + r) * BWR + w;  // row y + r - 3, padded by 3
-                    const uint32_t win = __funnelshift_r(bw[0], bw[1], sh) & fp7[r];
-                    if (r < 4) lo |= win << (8 * r); else hi |= win << (8 * (r - 4));
-                }
-                const float *vb = img + e - SP_PAD * W - SP_PAD;
-                // earlier in row-major order (bits 0..26) wins ties; later ones need a strictly larger score.
-                // Up to four neighbour scores are fetched per round trip (the loop is pure L2 latency).
-                uint64_t higher = 0;
-                for (uint64_t m = ((uint64_t)hi << 32) | lo; m;) {
-                    int kk[4];
-                    uint32_t nb_[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        kk[j] = -1;
-                        if (m) {
-                            kk[j] = __ffsll((long long)m) - 1;
-                            m &= m - 1;
-                            nb_[j] = __float_as_uint(__ldcg(vb + (kk[j] >> 3) * W + (kk[j] & 7))) & 0x7fffffffu;
-                        }
-                    }
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (kk[j] >= 0 && (kk[j] < 27 ? nb_[j] >= sb : nb_[j] > sb)) higher |= 1ull << kk[j];
-                }
-                const uint32_t hlo = (uint32_t)higher, hhi = (uint32_t)(higher >> 32);
-                if ((hlo | hhi) == 0) {
-                    kept = true;  // local maximum
-                } else {
-                    mask[id] = ((uint64_t)hhi << 32) | hlo;
-                    still = true;
-                }
-            }
-            commit_kept(kept, e, sb);
-            const unsigned bal = __ballot_sync(0xffffffffu, still);
-            if (bal) {
-                int slot = 0;
-                if (lane == (__ffs(bal) - 1)) slot = atomicAdd(&n_next[0], __popc(bal));
-                slot = __shfl_sync(0xffffffffu, slot, __ffs(bal) - 1);
-                if (still) ids_a[slot + __popc(bal & ((1u << lane) - 1))] = (uint16_t)id;
-            }
-        }
-        __syncthreads();
-
-        // ---- rounds over the cached masks; the whole image is here, so every round makes progress ----
-        int n = n_next[0];
-        uint16_t *cur = ids_a, *nxt = ids_b;
-        for (int round = 1; n > 0; ++round) {
-            if (round > 96) {  // a long dependency chain (ramps, plateaus): the dense kernels handle those
-                if (tid == 0) { redo_flags[b] = 1; surv_count[b] = 0; }
-                return;
-            }
-            int *cnt = &n_next[round % 3];
-            if (tid == 0) n_next[(round + 1) % 3] = 0;
-            for (int base = warp * 32; base < n; base += 1024) {
-                const int i = base + lane;
-                bool still = false, kept = false;
-                int id = 0, e = 0;
-                if (i < n) {
-                    id = cur[i];
-                    e = (int)pos[id];
-                    const float *vb = img + e - SP_PAD * W - SP_PAD;
-                    const uint64_t old = mask[id];
-                    uint64_t left = old;
-                    bool sup = false;
-                    for (uint64_t m = old; m && !sup;) {  // up to four neighbour states per round trip
-                        int kk[4];
-                        float nv[4];
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            kk[j] = -1;
-                            if (m) {
-                                kk[j] = __ffsll((long long)m) - 1;
-                                m &= m - 1;
-                                nv[j] = __ldcg(vb + (kk[j] >> 3) * W + (kk[j] & 7));
-                            }
-                        }
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            if (kk[j] >= 0) {
-                                if (nv[j] > 0.f) sup = true;                       // kept higher-priority neighbour
-                                else if (nv[j] == 0.f) left &= ~(1ull << kk[j]);   // it was suppressed: no longer blocks
-                            }
-                    }
-                    if (sup) __stcg(img + e, 0.f);
-                    else if (left == 0) kept = true;
-                    else {
-                        if (left != old) mask[id] = left;
-                        still = true;
-                    }
-                }
-                commit_kept(kept, e, kept ? score[id] : 0u);
-                const unsigned bal = __ballot_sync(0xffffffffu, still);
-                if (bal) {
-                    int slot = 0;
-                    if (lane == (__ffs(bal) - 1)) slot = atomicAdd(cnt, __popc(bal));
-                    slot = __shfl_sync(0xffffffffu, slot, __ffs(bal) - 1);
-                    if (still) nxt[slot + __popc(bal & ((1u << lane) - 1))] = (uint16_t)id;
-                }
-            }
-            __syncthreads();
-            n = *cnt;
-            uint16_t *tmp = cur; cur = nxt; nxt = tmp;
-        }
-        __syncthreads();
-        const int kept_total = n_kept;
-        if (kept_total >= keep_top_k || tb == 0) {  // enough survivors, or every candidate was admitted
-            if (tid == 0) surv_count[b] = kept_total;
-            return;
-        }
-        // too few: admit about twice as many (at least one more bin) and settle again from scratch
-        target = min(SP_LIST_CAP, max(2 * n_sel, target));
-        if (target <= n_sel) target = n_sel + 1;
-        if (n_sel >= SP_LIST_CAP) {
-            if (tid == 0) { redo_flags[b] = 1; surv_count[b] = 0; }
-            return;
-        }
-        __syncthreads();
+        for (int w = 0; w < NMS_THREADS / 32; ++w) t += sh_hist[w][tid];
+        if (t) atomicAdd(hist + b * SP_BINS + tid, t);
     }
 }
 
@@ -1210,6 +975,313 @@ __device__ __forceinline__ void select_find_bin(const int *hist, int remaining, 
     __syncthreads();
 }
 
+// Sparse top-k NMS, one CTA per image, everything in shared memory (no dense state map, no survivor list, no
+// separate select launch):
+//   - the admitted candidates (score bin >= the histogram threshold) set bits in a padded candidate bitmap;
+//   - a prefix count per bitmap word turns a position into a dense id (row-major rank), so state[id] / mask[id]
+//     live in shared memory and a neighbour's state is two shared-memory reads and a popcount away -- the first version
+//     kept the state in the dense output map and paid an L2 round trip per neighbour (51 us, latency-bound), and
+//     needed the map zero-filled (168 MB per step);
+//   - the same three-valued fixed point as the tile kernel (round 0 builds the higher-priority neighbour masks);
+//   - top-k cut by radix select over the kept scores, ties to the lower row-major index, and -- ids being in
+//     row-major order already -- ordered emission of the keypoints with one block scan.
+// `dense` (optional) must be zero-filled (nms_candidates_kernel<.., true>): the kept scores are scattered into it.
+// An image that does not fit raises redo_flags[b] and is redone by the tile + fix-up + select kernels.
+constexpr int SP2_CAP = 7168;      // candidates settled per image
+constexpr int SP2_PER = SP2_CAP / 1024;
+
+struct Sp2Layout {
+    int BWR, BROWS, words;
+    size_t mask, bm, pos, st, wbase, ids_a, ids_b, total;
+    __host__ __device__ Sp2Layout(int H, int W) {
+        BWR = (W + 31) / 32 + 2;               // one pad word on each side
+        BROWS = H + 2 * SP_PAD;
+        words = BROWS * BWR;
+        size_t off = 0;
+        mask = off;  off += sizeof(uint64_t) * SP2_CAP;
+        bm = off;    off += sizeof(uint32_t) * (size_t)((words + 1) & ~1);
+        pos = off;   off += sizeof(uint32_t) * SP2_CAP;
+        st = off;    off += sizeof(float) * SP2_CAP;
+        wbase = off; off += sizeof(uint16_t) * (size_t)((words + 1) & ~1);
+        ids_a = off; off += sizeof(uint16_t) * SP2_CAP;
+        ids_b = off; off += sizeof(uint16_t) * SP2_CAP;
+        total = off;
+    }
+};
+
+__global__ void __launch_bounds__(1024, 1)
+nms_sparse2_kernel(const float *__restrict__ prob, float *__restrict__ dense, int H, int W, int keep_top_k, const NmsFootprint fp,
+                   const uint2 *__restrict__ cands, const int *__restrict__ cand_count, const int *__restrict__ hist,
+                   int64_t *__restrict__ keypoints, float *__restrict__ kp_scores, int32_t *__restrict__ kp_counts, int kp_cap,
+                   int *__restrict__ surv_count, int *__restrict__ redo_flags) {
+    extern __shared__ __align__(16) uint8_t sp_smem[];
+    const Sp2Layout L(H, W);
+    const int BWR = L.BWR;
+    uint64_t *mask = reinterpret_cast<uint64_t *>(sp_smem + L.mask);
+    uint32_t *bm = reinterpret_cast<uint32_t *>(sp_smem + L.bm);
+    uint32_t *pos = reinterpret_cast<uint32_t *>(sp_smem + L.pos);
+    volatile float *st = reinterpret_cast<volatile float *>(sp_smem + L.st);   // -s undecided, +s kept, 0 suppressed
+    uint16_t *wbase = reinterpret_cast<uint16_t *>(sp_smem + L.wbase);
+    uint16_t *ids_a = reinterpret_cast<uint16_t *>(sp_smem + L.ids_a), *ids_b = reinterpret_cast<uint16_t *>(sp_smem + L.ids_b);
+    __shared__ int sh_hist[SP_BINS];
+    __shared__ int warp_sums[32];
+    __shared__ int n_kept, sel_bin, sel_remaining;
+    __shared__ int n_next[3];
+    __shared__ uint32_t fp7[7];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.x;
+    const float *img = prob + (size_t)b * H * W;
+    const int n_all = cand_count[b];
+    if (n_all > SP_CAND_CAP) {  // list truncated: the dense kernels redo this image (block-uniform)
+        if (tid == 0) { redo_flags[b] = 1; surv_count[b] = 0; }
+        return;
+    }
+    const uint2 *list = cands + (size_t)b * SP_CAND_CAP;
+    if (tid < SP_BINS) sh_hist[tid] = hist[b * SP_BINS + tid];
+    if (tid < 7) {
+        const int dy = tid - SP_PAD;
+        fp7[tid] = (dy >= -fp.R && dy <= fp.R) ? (fp.rows[dy + fp.R] << (SP_PAD - fp.R)) : 0u;
+    }
+    __syncthreads();
+    // id of the candidate at padded row r, padded bit position xb (= x + 32)
+    auto id_at = [&](int r, int xb) -> int {
+        const int wi = r * BWR + (xb >> 5);
+        return (int)wbase[wi] + __popc(bm[wi] & ((1u << (xb & 31)) - 1u));
+    };
+
+    int target = min(SP2_CAP, keep_top_k + keep_top_k / 2 + 256);
+    int n0 = 0;
+    while (true) {
+        // threshold bin: the highest bin t with (number of candidates in bins >= t) >= target, or 0
+        int tb = 0, n_sel = 0;
+        {
+            int cum = 0;
+            for (int t = SP_BINS - 1; t >= 0; --t) {  // 128 shared-memory reads per thread, uniform
+                cum += sh_hist[t];
+                if (cum >= target) { tb = t; break; }
+            }
+            n_sel = cum;  // when the loop ran out: every candidate
+        }
+        if (n_sel > SP2_CAP) {
+            if (tid == 0) { redo_flags[b] = 1; surv_count[b] = 0; }
+            return;
+        }
+        for (int i = tid; i < L.words; i += 1024) bm[i] = 0;
+        if (tid == 0) { n_kept = 0; n_next[0] = n_next[1] = n_next[2] = 0; }
+        __syncthreads();
+        // ---- pass 1 over the whole candidate list: set the bitmap bit of every admitted candidate (eight loads in flight)
+        constexpr int SCAN = 8;
+        for (int i0 = 0; i0 < n_all; i0 += 1024 * SCAN) {
+            uint2 c[SCAN];
+#pragma unroll
+            for (int u = 0; u < SCAN; ++u) {
+                const int i = i0 + u * 1024 + tid;
+                c[u] = i < n_all ? __ldg(list + i) : make_uint2(0u, 0u);
+            }
+#pragma unroll
+            for (int u = 0; u < SCAN; ++u)
+                if ((i0 + u * 1024 + tid) < n_all && sp_bin(c[u].y) >= tb) {
+                    const int y = (int)c[u].x / W, x = (int)c[u].x - y * W;
+                    atomicOr(&bm[(y + SP_PAD) * BWR + ((x + 32) >> 5)], 1u << ((x + 32) & 31));
+                }
+        }
+        __syncthreads();
+        // ---- ranks: candidates before each bitmap word (row-major), then id -> (pixel, -score)
+        const int wper = (L.words + 1023) / 1024;
+        const int w0 = min(L.words, tid * wper), w1 = min(L.words, w0 + wper);
+        int cnt = 0;
+        for (int w = w0; w < w1; ++w) cnt += __popc(bm[w]);
+        int total;
+        int base = block_exclusive_scan(cnt, warp_sums, total);
+        n0 = total;   // == n_sel
+        for (int w = w0; w < w1; ++w) {
+            wbase[w] = (uint16_t)base;
+            uint32_t bits = bm[w];
+            const int r = w / BWR, wc = w - r * BWR;
+            while (bits) {
+                const int bit = __ffs(bits) - 1;
+                bits &= bits - 1;
+                const int e = (r - SP_PAD) * W + (wc * 32 + bit - 32);
+                pos[base] = (uint32_t)e;
+                st[base] = -__ldg(img + e);
+                ++base;
+            }
+        }
+        __syncthreads();
+
+        // ---- round 0: higher-priority admitted neighbours of every admitted candidate ----
+        // mask bit 8*r + c  <=>  neighbour at (dy, dx) = (r - 3, c - 3); scores are |state| (nobody is suppressed yet)
+        for (int base0 = warp * 32; base0 < n0; base0 += 1024) {
+            const int id = base0 + lane;
+            bool still = false;
+            if (id < n0) {
+                const int e = (int)pos[id];
+                const uint32_t sb = __float_as_uint(st[id]) & 0x7fffffffu;
+                const int y = e / W, x = e - y * W;
+                const int bitpos = x + 32 - SP_PAD, w = bitpos >> 5, sh = bitpos & 31;
+                uint32_t lo = 0, hi = 0;
+#pragma unroll
+                for (int r = 0; r < 7; ++r) {
+                    const uint32_t *bw = bm + (y + r) * BWR + w;  // row y + r - 3, padded by 3
+                    const uint32_t win = __funnelshift_r(bw[0], bw[1], sh) & fp7[r];
+                    if (r < 4) lo |= win << (8 * r); else hi |= win << (8 * (r - 4));
+                }
+                // earlier in row-major order (bits 0..26) wins ties; later ones need a strictly larger score
+                uint64_t higher = 0;
+                for (uint64_t m = ((uint64_t)hi << 32) | lo; m;) {
+                    const int k = __ffsll((long long)m) - 1;
+                    m &= m - 1;
+                    const uint32_t nb_ = __float_as_uint(st[id_at(y + (k >> 3), bitpos + (k & 7))]) & 0x7fffffffu;
+                    if (k < 27 ? nb_ >= sb : nb_ > sb) higher |= 1ull << k;
+                }
+                if (higher == 0) {
+                    st[id] = __uint_as_float(sb);   // local maximum: kept
+                    atomicAdd(&n_kept, 1);
+                } else {
+                    mask[id] = higher;
+                    still = true;
+                }
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, still);
+            if (bal) {
+                int slot = 0;
+                if (lane == (__ffs(bal) - 1)) slot = atomicAdd(&n_next[0], __popc(bal));
+                slot = __shfl_sync(0xffffffffu, slot, __ffs(bal) - 1);
+                if (still) ids_a[slot + __popc(bal & ((1u << lane) - 1))] = (uint16_t)id;
+            }
+        }
+        __syncthreads();
+
+        // ---- rounds over the cached masks; the whole image is here, so every round makes progress ----
+        int n = n_next[0];
+        uint16_t *cur = ids_a, *nxt = ids_b;
+        for (int round = 1; n > 0; ++round) {
+            if (round > 96) {  // a long dependency chain (ramps, plateaus): the dense kernels handle those
+                if (tid == 0) { redo_flags[b] = 1; surv_count[b] = 0; }
+                return;
+            }
+            int *cntp = &n_next[round % 3];
+            if (tid == 0) n_next[(round + 1) % 3] = 0;
+            for (int base0 = warp * 32; base0 < n; base0 += 1024) {
+                const int i = base0 + lane;
+                bool still = false;
+                int id = 0;
+                if (i < n) {
+                    id = cur[i];
+                    const int e = (int)pos[id];
+                    const int y = e / W, x = e - y * W, bitpos = x + 32 - SP_PAD;
+                    const uint64_t old = mask[id];
+                    uint64_t left = old;
+                    bool sup = false;
+                    for (uint64_t m = old; m && !sup;) {
+                        const int k = __ffsll((long long)m) - 1;
+                        m &= m - 1;
+                        const float nv = st[id_at(y + (k >> 3), bitpos + (k & 7))];
+                        if (nv > 0.f) sup = true;                      // kept higher-priority neighbour
+                        else if (nv == 0.f) left &= ~(1ull << k);      // it was suppressed: no longer blocks
+                    }
+                    if (sup) st[id] = 0.f;
+                    else if (left == 0) { st[id] = -st[id]; atomicAdd(&n_kept, 1); }
+                    else {
+                        if (left != old) mask[id] = left;
+                        still = true;
+                    }
+                }
+                const unsigned bal = __ballot_sync(0xffffffffu, still);
+                if (bal) {
+                    int slot = 0;
+                    if (lane == (__ffs(bal) - 1)) slot = atomicAdd(cntp, __popc(bal));
+                    slot = __shfl_sync(0xffffffffu, slot, __ffs(bal) - 1);
+                    if (still) nxt[slot + __popc(bal & ((1u << lane) - 1))] = (uint16_t)id;
+                }
+            }
+            __syncthreads();
+            n = *cntp;
+            uint16_t *tmp = cur; cur = nxt; nxt = tmp;
+        }
+        __syncthreads();
+        if (n_kept >= keep_top_k || tb == 0) break;  // enough survivors, or every candidate was admitted
+        // too few: admit about twice as many (at least one more bin) and settle again from scratch
+        target = min(SP2_CAP, max(2 * n_sel, target));
+        if (target <= n_sel) target = n_sel + 1;
+        if (n_sel >= SP2_CAP) {
+            if (tid == 0) { redo_flags[b] = 1; surv_count[b] = 0; }
+            return;
+        }
+        __syncthreads();
+    }
+
+    // ---- top-k cut: the keep_top_k highest scores, ties to the lower row-major index (= the lower id) ----
+    // every thread owns SP2_PER consecutive ids, so block scans over the threads run in id (= row-major) order
+    const int kept_total = n_kept;
+    uint32_t sc[SP2_PER];   // score bits of my kept ids, 0 otherwise
+#pragma unroll
+    for (int j = 0; j < SP2_PER; ++j) {
+        const int id = tid * SP2_PER + j;
+        const float v = id < n0 ? st[id] : 0.f;
+        sc[j] = v > 0.f ? __float_as_uint(v) : 0u;
+    }
+    uint32_t cut_score = 0;
+    int take_ties = 0x7fffffff;          // how many of the entries that score exactly cut_score are kept
+    if (keep_top_k > 0 && kept_total > keep_top_k) {
+        int *shist = reinterpret_cast<int *>(mask);   // the neighbour masks are dead: 2048 bins fit in their place
+        uint32_t prefix = 0;
+        int remaining = keep_top_k;
+        const int shifts[3] = {21, 10, 0}, widths[3] = {11, 11, 10};
+        for (int pass = 0; pass < 3; ++pass) {
+            for (int i = tid; i < SEL_BINS; i += 1024) shist[i] = 0;
+            __syncthreads();
+            const int sh = shifts[pass], hi_sh = sh + widths[pass];
+            const uint32_t dmask = (1u << widths[pass]) - 1u;
+#pragma unroll
+            for (int j = 0; j < SP2_PER; ++j)
+                if (sc[j] && (pass == 0 || (sc[j] >> hi_sh) == (prefix >> hi_sh))) atomicAdd(&shist[(sc[j] >> sh) & dmask], 1);
+            __syncthreads();
+            select_find_bin<true>(shist, remaining, warp_sums, &sel_bin, &sel_remaining);
+            prefix |= (uint32_t)sel_bin << sh;
+            remaining = sel_remaining;
+            __syncthreads();
+        }
+        cut_score = prefix;       // the k-th highest score
+        take_ties = remaining;    // of the survivors with exactly that score, the first `remaining` in row-major order
+    }
+    int ties = 0;
+#pragma unroll
+    for (int j = 0; j < SP2_PER; ++j) ties += (sc[j] != 0 && sc[j] == cut_score) ? 1 : 0;
+    int tot_ties;
+    int tie_rank = block_exclusive_scan(ties, warp_sums, tot_ties);
+    bool keep[SP2_PER];
+    int mine = 0;
+#pragma unroll
+    for (int j = 0; j < SP2_PER; ++j) {
+        keep[j] = false;
+        if (sc[j] > cut_score) keep[j] = true;
+        else if (sc[j] != 0 && sc[j] == cut_score) { keep[j] = tie_rank < take_ties; ++tie_rank; }
+        mine += keep[j] ? 1 : 0;
+    }
+    int total_kept;
+    int slot = block_exclusive_scan(mine, warp_sums, total_kept);
+    float *dmap = dense ? dense + (size_t)b * H * W : nullptr;
+    int64_t *kp = keypoints ? keypoints + (size_t)b * kp_cap * 2 : nullptr;
+    float *ks = kp_scores ? kp_scores + (size_t)b * kp_cap : nullptr;
+#pragma unroll
+    for (int j = 0; j < SP2_PER; ++j) {
+        if (!keep[j]) continue;
+        const int e = (int)pos[tid * SP2_PER + j];
+        const float v = __uint_as_float(sc[j]);
+        if (dmap) dmap[e] = v;
+        if (slot < kp_cap) {
+            if (kp) { kp[2 * (size_t)slot] = e / W; kp[2 * (size_t)slot + 1] = e % W; }
+            if (ks) ks[slot] = v;
+        }
+        ++slot;
+    }
+    if (tid == 0) {
+        if (kp_counts) kp_counts[b] = total_kept;
+        surv_count[b] = -1;   // finished here: the select kernel skips this image
+    }
+}
+
 __global__ void __launch_bounds__(1024)
 nms_select_kernel(float *__restrict__ out, int H, int W, int keep_top_k, const uint2 *__restrict__ survivors,
                   const int *__restrict__ surv_count, int cap, uint32_t *__restrict__ bitmaps, int words,
@@ -1220,6 +1292,7 @@ nms_select_kernel(float *__restrict__ out, int H, int W, int keep_top_k, const u
     __shared__ int sel_bin, sel_remaining;
     const int b = blockIdx.x, tid = threadIdx.x;
     const int n = surv_count[b];
+    if (n < 0) return;   // settled, cut and emitted by nms_sparse2_kernel
     const uint2 *surv = survivors + (size_t)b * cap;
     float *img = out + (size_t)b * H * W;
     const bool want_kp = keypoints != nullptr || kp_counts != nullptr;
@@ -1346,7 +1419,7 @@ static bool footprint_hit(double size, double iou, int dy, int dx) {
 
 struct NmsLayout {
     int cap, words;
-    size_t survivors, worklist, counts, counts_bytes, bitmaps, cands, total;
+    size_t survivors, worklist, counts, counts_bytes, bitmaps, cands, dense_scratch, total;
     NmsLayout(int B, int H, int W) {
         cap = H * W;
         words = (H * W + 31) / 32;
@@ -1358,6 +1431,9 @@ struct NmsLayout {
         survivors = off; off = align_up(off + sizeof(uint2) * (size_t)B * cap, 256);
         worklist = off;  off = align_up(off + sizeof(uint32_t) * (size_t)B * cap, 256);
         bitmaps = off;   off = align_up(off + sizeof(uint32_t) * (size_t)B * words, 256);
+        // stand-in for the dense output when the caller only wants keypoints (prob_nms == NULL): the tile kernels that
+        // redo an image the sparse path gave up on keep their state in a dense map
+        dense_scratch = off; off = align_up(off + sizeof(float) * (size_t)B * cap, 256);
         total = off;
     }
 };
@@ -1447,7 +1523,8 @@ extern "C" int mp_box_nms_f32(const float *prob, int B, int H, int W, double siz
         return MP_ERR_UNSUPPORTED;
     }
     if (B == 0) return MP_OK;
-    MP_CHECK_ARG(prob && prob_nms, "mp_box_nms_f32: null pointer");
+    MP_CHECK_ARG(prob != nullptr, "mp_box_nms_f32: null pointer");
+    MP_CHECK_ARG(prob_nms != nullptr || kp_counts != nullptr, "mp_box_nms_f32: no output requested (prob_nms and kp_counts are both NULL)");
     MP_CHECK_ARG(keypoints == nullptr || kp_counts != nullptr, "mp_box_nms_f32: keypoints need kp_counts");
 
     // footprint: reach and translation invariance
@@ -1490,25 +1567,29 @@ extern "C" int mp_box_nms_f32(const float *prob, int B, int H, int W, double siz
     uint2 *cands = (uint2 *)(ws + L.cands);
 
     const float thr = (float)min_prob;
+    const bool want_dense = prob_nms != nullptr;
+    if (!want_dense) prob_nms = (float *)(ws + L.dense_scratch);   // keypoints only: the map is scratch for the tile kernels
     const bool vec = (W % 4 == 0) && (((uintptr_t)prob & 15) == 0) && (((uintptr_t)prob_nms & 15) == 0);
     int rc;
     static const int tile_variant = getenv("MP_NMS_TILE") ? atoi(getenv("MP_NMS_TILE")) : 0;  // tuning aid
     static const bool no_sparse = getenv("MP_NMS_NO_SPARSE") != nullptr;                      // tuning aid
 
-    // sparse top-k path: settle only the candidates that can reach the top k (see nms_sparse_kernel)
-    const size_t sp_bm_words = (size_t)(H + 2 * SP_PAD) * ((W + 31) / 32 + 2);
-    const size_t sp_smem = ((sp_bm_words + 1) & ~(size_t)1) * 4 + (size_t)SP_LIST_CAP * (8 + 4 + 4 + 2 + 2);
+    // sparse top-k path: settle only the candidates that can reach the top k (see nms_sparse2_kernel)
+    const size_t sp_smem = Sp2Layout(H, W).total;
     const int *only_flagged = nullptr;
-    if (!no_sparse && keep_top_k > 0 && keep_top_k <= SP_LIST_CAP / 2 && R <= SP_PAD && sp_smem <= 224 * 1024) {
+    if (!no_sparse && keep_top_k > 0 && keep_top_k <= SP2_CAP / 2 && R <= SP_PAD && sp_smem <= 220 * 1024) {
         const int HW = H * W;
         dim3 cgrid((unsigned)((HW + SP_CHUNK - 1) / SP_CHUNK), (unsigned)B);
         const bool cvec = (HW % 4 == 0) && (((uintptr_t)prob & 15) == 0) && (((uintptr_t)prob_nms & 15) == 0);
-        if (cvec) nms_candidates_kernel<true><<<cgrid, NMS_THREADS, 0, s>>>(prob, prob_nms, HW, thr, cands, cand_count, hist);
-        else nms_candidates_kernel<false><<<cgrid, NMS_THREADS, 0, s>>>(prob, prob_nms, HW, thr, cands, cand_count, hist);
+        // the dense map is zero-filled only when the caller asked for it: the sparse kernel keeps its state in shared memory
+        if (cvec && want_dense) nms_candidates_kernel<true, true><<<cgrid, NMS_THREADS, 0, s>>>(prob, prob_nms, HW, thr, cands, cand_count, hist);
+        else if (cvec) nms_candidates_kernel<true, false><<<cgrid, NMS_THREADS, 0, s>>>(prob, prob_nms, HW, thr, cands, cand_count, hist);
+        else if (want_dense) nms_candidates_kernel<false, true><<<cgrid, NMS_THREADS, 0, s>>>(prob, prob_nms, HW, thr, cands, cand_count, hist);
+        else nms_candidates_kernel<false, false><<<cgrid, NMS_THREADS, 0, s>>>(prob, prob_nms, HW, thr, cands, cand_count, hist);
         MP_LAUNCH_OK_S("nms_candidates_kernel", s);
-        MP_CUDA_OK(cudaFuncSetAttribute(nms_sparse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp_smem));
-        nms_sparse_kernel<<<B, 1024, sp_smem, s>>>(prob_nms, H, W, keep_top_k, fp, cands, cand_count, hist, surv, surv_count,
-                                                   L.cap, redo_flags);
+        MP_CUDA_OK(cudaFuncSetAttribute(nms_sparse2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp_smem));
+        nms_sparse2_kernel<<<B, 1024, sp_smem, s>>>(prob, want_dense ? prob_nms : nullptr, H, W, keep_top_k, fp, cands, cand_count, hist,
+                                                    keypoints, kp_scores, kp_counts, kp_cap, surv_count, redo_flags);
         MP_LAUNCH_OK_S("nms_sparse_kernel", s);
         only_flagged = redo_flags;  // the dense kernels below only redo images the sparse path gave up on
     }

@@ -97,12 +97,16 @@ def normalize_descriptors(x, nchw=True, nhwc=False):
     return o1, o2
 
 
-def box_nms(prob, size, min_prob, iou=0.1, keep_top_k=0, want_keypoints=False, kp_cap=None):
-    """prob (B,H,W) fp32 -> dense NMS map (B,H,W) [+ keypoints (B,cap,2) int64, scores (B,cap), counts (B)]."""
+def box_nms(prob, size, min_prob, iou=0.1, keep_top_k=0, want_keypoints=False, kp_cap=None, want_dense=True):
+    """prob (B,H,W) fp32 -> dense NMS map (B,H,W) [+ keypoints (B,cap,2) int64, scores (B,cap), counts (B)].
+    ``want_dense=False`` (with want_keypoints) skips the dense map -- it is returned as None: on the sparse top-k path
+    nothing of its size is then written at all."""
     prob = _cuda(prob, torch.float32, "prob")
     B, H, W = prob.shape
     dev = prob.device
-    out = torch.empty_like(prob)
+    if not want_dense and not want_keypoints:
+        raise ValueError("box_nms: nothing requested (want_dense=False needs want_keypoints=True)")
+    out = torch.empty_like(prob) if want_dense else None
     lib = _lib.load()
     kp = sc = cnt = None
     cap = 0

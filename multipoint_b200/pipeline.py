@@ -12,7 +12,7 @@ from . import ops
 
 class KeypointPipeline:
     def __init__(self, net, nms=4, detection_threshold=0.015, topk=2048, iou=0.1, metric='l2', cross_check=True,
-                 match_threshold=-1.0, algo=None, trust_spectrum_keys=True):
+                 match_threshold=-1.0, algo=None, trust_spectrum_keys=True, dense_nms_map=True):
         """trust_spectrum_keys: data['optical'] really holds optical images and data['thermal'] thermal ones (what
         ImagePairDataset yields), so the encoder routing of MultiPoint.py:107-122 needs no device->host read of
         ``is_optical``.  Set it to False to route every row by its ``is_optical`` flag like the reference."""
@@ -21,6 +21,9 @@ class KeypointPipeline:
         self.net, self.nms, self.thr, self.topk, self.iou = net, nms, detection_threshold, int(topk), iou
         self.metric, self.cross_check, self.match_threshold, self.algo = metric, cross_check, match_threshold, algo
         self.trust_spectrum_keys = bool(trust_spectrum_keys)
+        # dense_nms_map=False: 'prob_nms' (the dense map utils.box_nms returns) is not materialised -- keypoints, scores
+        # and counts are the product of this chain, and the sparse top-k NMS then writes nothing of the map's size
+        self.dense_nms_map = bool(dense_nms_map)
 
     @torch.no_grad()
     def extract_from_backbone(self, logits, raw_desc, H, W, valid_mask=None):
@@ -32,10 +35,13 @@ class KeypointPipeline:
         prob = ops.detector_head(logits, valid_mask)
         B = prob.shape[0]
         dense, kp, scores, counts = ops.box_nms(prob.reshape(B, H, W), self.nms, self.thr, iou=self.iou,
-                                                keep_top_k=self.topk, want_keypoints=True, kp_cap=self.topk)
+                                                keep_top_k=self.topk, want_keypoints=True, kp_cap=self.topk,
+                                                want_dense=self.dense_nms_map)
         desc = ops.sample_descriptors(kp, desc_nhwc, H, W, counts=counts, channels_last=True)
-        return {'prob': prob, 'prob_nms': dense.reshape(B, 1, H, W), 'keypoints': kp, 'scores': scores,
-                'counts': counts, 'desc': desc}
+        out = {'prob': prob, 'keypoints': kp, 'scores': scores, 'counts': counts, 'desc': desc}
+        if dense is not None:
+            out['prob_nms'] = dense.reshape(B, 1, H, W)
+        return out
 
     @torch.no_grad()
     def extract(self, data):

@@ -39,6 +39,9 @@ def main():
         if sigma == 2.0:
             cases.append(("top-k 2048 + keypoints %.1f%%" % (100 * dens),
                           lambda: ops.box_nms(prob, 4, 0.015, keep_top_k=2048, want_keypoints=True, kp_cap=2048), B * (2 * H * W * 4 + 20 * 2048)))
+            cases.append(("top-k 2048 keypoints only (no dense map) %.1f%%" % (100 * dens),
+                          lambda: ops.box_nms(prob, 4, 0.015, keep_top_k=2048, want_keypoints=True, kp_cap=2048, want_dense=False),
+                          B * (H * W * 4 + 20 * 2048)))
         for name, fn, nbytes in cases:
             if args.only and args.only not in name:
                 continue
