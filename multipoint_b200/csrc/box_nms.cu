@@ -889,10 +889,13 @@ __device__ __forceinline__ int sp_bin(uint32_t bits) {  // monotone in the (posi
 
 template <bool VEC, bool ZERO>   // ZERO: also zero-fill the dense output map (only when the caller asked for it)
 __global__ void __launch_bounds__(NMS_THREADS)  // 71 registers, 3 CTAs/SM; capping at 48 (5 CTAs/SM) measured the same 81 us
-nms_candidates_kernel(const float *__restrict__ prob, float *__restrict__ out, int HW, float thr,
+nms_candidates_kernel(const float *__restrict__ prob, float *__restrict__ out, int W, int HW, float thr,
                       uint2 *__restrict__ cands, int *__restrict__ cand_count, int *__restrict__ hist) {
-    // one histogram per warp: the scores cluster in a few bins just above the threshold, and a single shared histogram
-    // serialised its atomics there (ncu: 465 k bank conflicts per launch)
+    // One histogram per warp: the scores cluster in a few bins just above the threshold, and a single shared histogram
+    // serialised its atomics there (ncu: 465 k bank conflicts per launch).  One global atomic per CTA reserves its run
+    // of the image's candidate list (per-warp reservations were measured at 109 us against 65: the L2 serialises the
+    // 640 atomics an image then sends to one address).  List entry: (pixel index, score bits) -- splitting the index
+    // into (y, x) here costs a division per candidate (86 us against 65); the sparse kernel does it for the admitted 8 %.
     __shared__ int sh_hist[NMS_THREADS / 32][SP_BINS];
     __shared__ int warp_sums[NMS_THREADS / 32];
     __shared__ int sh_base;
@@ -953,6 +956,8 @@ nms_candidates_kernel(const float *__restrict__ prob, float *__restrict__ out, i
         if (t) atomicAdd(hist + b * SP_BINS + tid, t);
     }
 }
+
+
 
 // One CTA per image: top-k (optional) + ordered compaction.
 // Top-k = the k smallest keys (~score_bits, index), i.e. highest scores first, ties to the lower
@@ -1051,24 +1056,40 @@ nms_sparse2_kernel(const float *__restrict__ prob, float *__restrict__ dense, in
 
     int target = min(SP2_CAP, keep_top_k + keep_top_k / 2 + 256);
     int n0 = 0;
+    const float inv_w = 1.0f / (float)W;
     while (true) {
-        // threshold bin: the highest bin t with (number of candidates in bins >= t) >= target, or 0
-        int tb = 0, n_sel = 0;
-        {
-            int cum = 0;
-            for (int t = SP_BINS - 1; t >= 0; --t) {  // 128 shared-memory reads per thread, uniform
-                cum += sh_hist[t];
-                if (cum >= target) { tb = t; break; }
+        // threshold bin: the highest bin t with (number of candidates in bins >= t) >= target, or 0 (one warp searches:
+        // four bins per lane, a suffix scan over the lanes, then the four bins of the lane that crosses the target)
+        if (warp == 0) {
+            const int h0 = sh_hist[4 * lane], h1 = sh_hist[4 * lane + 1], h2 = sh_hist[4 * lane + 2], h3 = sh_hist[4 * lane + 3];
+            int suf = h0 + h1 + h2 + h3;      // inclusive suffix sum over lanes >= this one
+#pragma unroll
+            for (int sft = 1; sft < 32; sft <<= 1) {
+                const int t = __shfl_down_sync(0xffffffffu, suf, sft);
+                if (lane + sft < 32) suf += t;
             }
-            n_sel = cum;  // when the loop ran out: every candidate
-        }
-        if (n_sel > SP2_CAP) {
-            if (tid == 0) { redo_flags[b] = 1; surv_count[b] = 0; }
-            return;
+            const unsigned reach = __ballot_sync(0xffffffffu, suf >= target);
+            int tbv = 0, nsel = __shfl_sync(0xffffffffu, suf, 0);   // not reached: every candidate
+            if (reach) {
+                const int l = 31 - __clz(reach);                   // highest lane whose suffix reaches the target
+                if (lane == l) {
+                    int cum = suf - (h0 + h1 + h2 + h3);           // candidates in the bins above this lane's
+                    const int hh[4] = {h0, h1, h2, h3};
+                    int t = 3;
+                    for (; t >= 0; --t) { cum += hh[t]; if (cum >= target) break; }
+                    sel_bin = 4 * l + t; sel_remaining = cum;
+                }
+                __syncwarp();
+            } else if (lane == 0) { sel_bin = tbv; sel_remaining = nsel; }
         }
         for (int i = tid; i < L.words; i += 1024) bm[i] = 0;
         if (tid == 0) { n_kept = 0; n_next[0] = n_next[1] = n_next[2] = 0; }
         __syncthreads();
+        const int tb = sel_bin, n_sel = sel_remaining;
+        if (n_sel > SP2_CAP) {
+            if (tid == 0) { redo_flags[b] = 1; surv_count[b] = 0; }
+            return;
+        }
         // ---- pass 1 over the whole candidate list: set the bitmap bit of every admitted candidate (eight loads in flight)
         constexpr int SCAN = 8;
         for (int i0 = 0; i0 < n_all; i0 += 1024 * SCAN) {
@@ -1081,7 +1102,13 @@ nms_sparse2_kernel(const float *__restrict__ prob, float *__restrict__ dense, in
 #pragma unroll
             for (int u = 0; u < SCAN; ++u)
                 if ((i0 + u * 1024 + tid) < n_all && sp_bin(c[u].y) >= tb) {
-                    const int y = (int)c[u].x / W, x = (int)c[u].x - y * W;
+                    // pixel index -> (y, x) without an integer division: H * W < 2^24 here (the bitmap fits shared memory),
+                    // so the float quotient is within one of the row and two compares settle it
+                    const int e = (int)c[u].x;
+                    int y = (int)((float)e * inv_w);
+                    y -= (y * W > e) ? 1 : 0;
+                    y += ((y + 1) * W <= e) ? 1 : 0;
+                    const int x = e - y * W;
                     atomicOr(&bm[(y + SP_PAD) * BWR + ((x + 32) >> 5)], 1u << ((x + 32) & 31));
                 }
         }
@@ -1094,18 +1121,23 @@ nms_sparse2_kernel(const float *__restrict__ prob, float *__restrict__ dense, in
         int total;
         int base = block_exclusive_scan(cnt, warp_sums, total);
         n0 = total;   // == n_sel
-        for (int w = w0; w < w1; ++w) {
-            wbase[w] = (uint16_t)base;
-            uint32_t bits = bm[w];
-            const int r = w / BWR, wc = w - r * BWR;
-            while (bits) {
-                const int bit = __ffs(bits) - 1;
-                bits &= bits - 1;
-                const int e = (r - SP_PAD) * W + (wc * 32 + bit - 32);
-                pos[base] = (uint32_t)e;
-                st[base] = -__ldg(img + e);
-                ++base;
+        {
+            int r = w0 / BWR, wc = w0 - r * BWR;
+            for (int w = w0; w < w1; ++w) {
+                wbase[w] = (uint16_t)base;
+                uint32_t bits = bm[w];
+                while (bits) {
+                    const int bit = __ffs(bits) - 1;
+                    bits &= bits - 1;
+                    pos[base++] = ((uint32_t)(r - SP_PAD) << 16) | (uint32_t)(wc * 32 + bit - 32);   // (y, x)
+                }
+                if (++wc == BWR) { wc = 0; ++r; }
             }
+        }
+        __syncthreads();
+        for (int id = tid; id < n0; id += 1024) {   // the scores, all loads of a thread in flight together
+            const uint32_t yx = pos[id];
+            st[id] = -__ldg(img + (int)(yx >> 16) * W + (int)(yx & 0xffffu));
         }
         __syncthreads();
 
@@ -1115,9 +1147,9 @@ nms_sparse2_kernel(const float *__restrict__ prob, float *__restrict__ dense, in
             const int id = base0 + lane;
             bool still = false;
             if (id < n0) {
-                const int e = (int)pos[id];
+                const uint32_t yx = pos[id];
                 const uint32_t sb = __float_as_uint(st[id]) & 0x7fffffffu;
-                const int y = e / W, x = e - y * W;
+                const int y = (int)(yx >> 16), x = (int)(yx & 0xffffu);
                 const int bitpos = x + 32 - SP_PAD, w = bitpos >> 5, sh = bitpos & 31;
                 uint32_t lo = 0, hi = 0;
 #pragma unroll
@@ -1168,8 +1200,8 @@ nms_sparse2_kernel(const float *__restrict__ prob, float *__restrict__ dense, in
                 int id = 0;
                 if (i < n) {
                     id = cur[i];
-                    const int e = (int)pos[id];
-                    const int y = e / W, x = e - y * W, bitpos = x + 32 - SP_PAD;
+                    const uint32_t yx = pos[id];
+                    const int y = (int)(yx >> 16), x = (int)(yx & 0xffffu), bitpos = x + 32 - SP_PAD;
                     const uint64_t old = mask[id];
                     uint64_t left = old;
                     bool sup = false;
@@ -1267,11 +1299,12 @@ nms_sparse2_kernel(const float *__restrict__ prob, float *__restrict__ dense, in
 #pragma unroll
     for (int j = 0; j < SP2_PER; ++j) {
         if (!keep[j]) continue;
-        const int e = (int)pos[tid * SP2_PER + j];
+        const uint32_t yx = pos[tid * SP2_PER + j];
+        const int y = (int)(yx >> 16), x = (int)(yx & 0xffffu);
         const float v = __uint_as_float(sc[j]);
-        if (dmap) dmap[e] = v;
+        if (dmap) dmap[y * W + x] = v;
         if (slot < kp_cap) {
-            if (kp) { kp[2 * (size_t)slot] = e / W; kp[2 * (size_t)slot + 1] = e % W; }
+            if (kp) { kp[2 * (size_t)slot] = y; kp[2 * (size_t)slot + 1] = x; }
             if (ks) ks[slot] = v;
         }
         ++slot;
@@ -1577,15 +1610,15 @@ extern "C" int mp_box_nms_f32(const float *prob, int B, int H, int W, double siz
     // sparse top-k path: settle only the candidates that can reach the top k (see nms_sparse2_kernel)
     const size_t sp_smem = Sp2Layout(H, W).total;
     const int *only_flagged = nullptr;
-    if (!no_sparse && keep_top_k > 0 && keep_top_k <= SP2_CAP / 2 && R <= SP_PAD && sp_smem <= 220 * 1024) {
+    if (!no_sparse && keep_top_k > 0 && keep_top_k <= SP2_CAP / 2 && R <= SP_PAD && sp_smem <= 220 * 1024 && (long long)H * W < (1ll << 24)) {
         const int HW = H * W;
         dim3 cgrid((unsigned)((HW + SP_CHUNK - 1) / SP_CHUNK), (unsigned)B);
         const bool cvec = (HW % 4 == 0) && (((uintptr_t)prob & 15) == 0) && (((uintptr_t)prob_nms & 15) == 0);
         // the dense map is zero-filled only when the caller asked for it: the sparse kernel keeps its state in shared memory
-        if (cvec && want_dense) nms_candidates_kernel<true, true><<<cgrid, NMS_THREADS, 0, s>>>(prob, prob_nms, HW, thr, cands, cand_count, hist);
-        else if (cvec) nms_candidates_kernel<true, false><<<cgrid, NMS_THREADS, 0, s>>>(prob, prob_nms, HW, thr, cands, cand_count, hist);
-        else if (want_dense) nms_candidates_kernel<false, true><<<cgrid, NMS_THREADS, 0, s>>>(prob, prob_nms, HW, thr, cands, cand_count, hist);
-        else nms_candidates_kernel<false, false><<<cgrid, NMS_THREADS, 0, s>>>(prob, prob_nms, HW, thr, cands, cand_count, hist);
+        if (cvec && want_dense) nms_candidates_kernel<true, true><<<cgrid, NMS_THREADS, 0, s>>>(prob, prob_nms, W, HW, thr, cands, cand_count, hist);
+        else if (cvec) nms_candidates_kernel<true, false><<<cgrid, NMS_THREADS, 0, s>>>(prob, prob_nms, W, HW, thr, cands, cand_count, hist);
+        else if (want_dense) nms_candidates_kernel<false, true><<<cgrid, NMS_THREADS, 0, s>>>(prob, prob_nms, W, HW, thr, cands, cand_count, hist);
+        else nms_candidates_kernel<false, false><<<cgrid, NMS_THREADS, 0, s>>>(prob, prob_nms, W, HW, thr, cands, cand_count, hist);
         MP_LAUNCH_OK_S("nms_candidates_kernel", s);
         MP_CUDA_OK(cudaFuncSetAttribute(nms_sparse2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp_smem));
         nms_sparse2_kernel<<<B, 1024, sp_smem, s>>>(prob, want_dense ? prob_nms : nullptr, H, W, keep_top_k, fp, cands, cand_count, hist,
