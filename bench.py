@@ -271,20 +271,20 @@ def adaptation_bench(net, dev, rank, world, hbm_peak, n_pairs=2, num=100, steps=
     ms = e0.elapsed_time(e1) / steps
     n = num - 1
     HW = H * W
-    algorithmic = {   # bytes per launch: warped plane read + written; heatmaps + mask read, accumulators once
-        "warp_kernel": n * n_pairs * 2 * HW * 4,
-        "ha_aggregate_kernel": n * (2 * n_pairs * HW * 4 + HW) + 2 * n_pairs * HW * 4,
+    algorithmic = {   # bytes per BATCH (the samples go through in chunks, so a batch is several launches)
+        "warp_kernel": 2 * n * n_pairs * 2 * HW * 4,              # both spectra: every warped plane read + written
+        "ha_aggregate_kernel": n * (2 * n_pairs * HW * 4 + HW) + 2 * n_pairs * HW * 4,   # heatmaps + mask read, result written
         "valid_mask_kernel": n * HW,
     }
     rows = []
     for name in ("warp_kernel", "ha_aggregate_kernel", "valid_mask_kernel", "detector_head_kernel", "nms_tile_fast_kernel"):
         if name in prof:
             rec = prof[name]
-            avg_ms = rec["total_ms"] / max(rec["launches"], 1)
-            row = {"kernel": name, "launches_per_batch": rec["launches"] / steps, "avg_us": round(avg_ms * 1e3, 1)}
+            ms_batch = rec["total_ms"] / steps
+            row = {"kernel": name, "launches_per_batch": rec["launches"] / steps, "us_per_batch": round(ms_batch * 1e3, 1)}
             if name in algorithmic:
-                row.update(algorithmic_bytes_per_launch=algorithmic[name], achieved_GBps=round(algorithmic[name] / avg_ms / 1e6, 1),
-                           frac_of_hbm=round(algorithmic[name] / avg_ms / 1e6 / hbm_peak, 4))
+                row.update(algorithmic_bytes_per_batch=algorithmic[name], achieved_GBps=round(algorithmic[name] / ms_batch / 1e6, 1),
+                           frac_of_hbm=round(algorithmic[name] / ms_batch / 1e6 / hbm_peak, 4))
             rows.append(row)
     lib_ms = sum(v["total_ms"] for k, v in prof.items() if k in ("warp_kernel", "ha_aggregate_kernel", "valid_mask_kernel")) / steps
     res = {"workload": "config 4: homographic_adaptation_multispectral(num=%d, prod) + box_nms(topk=0) on %d synthetic 512x640 pairs "
