@@ -593,6 +593,7 @@ def main():
             tj = json.load(open(tpath if os.path.exists(tpath) else os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")))
             traffic = {k: v["dram_bytes"] for k, v in tj["per_launch"].items()}
             traffic["sample_descriptors_kernel"] = traffic.get("sample_descriptors_nhwc_vec_kernel")
+            traffic["nms_sparse_kernel"] = traffic.get("nms_sparse2_kernel", traffic.get("nms_sparse_kernel"))
             # the glue kernel's launches differ per layer: DRAM bytes / algorithmic bytes of the captured full-resolution
             # launches, applied to the average algorithmic bytes per launch
             if "relu_bn_pad_kernel_dram_over_algorithmic" in tj and glue["calls"]:

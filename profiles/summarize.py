@@ -2,7 +2,9 @@
 
     python profiles/summarize.py launches gpurun_out/launches_hot.csv profiles/r1_launches_hot.csv
     python profiles/summarize.py full gpurun_out/prof_hot.ncu-rep profiles/r1_ncu_full_hot.csv
+    python profiles/summarize.py traffic gpurun_out/r2_prof_hot.ncu-rep profiles/r2_ncu_traffic.json "<source note>"
 """
+import json
 import collections
 import csv
 import subprocess
@@ -13,7 +15,11 @@ FULL_COLS = ['Kernel Name', 'gpu__time_duration.sum', 'dram__bytes_read.sum', 'd
              'sm__throughput.avg.pct_of_peak_sustained_elapsed', 'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active',
              'smsp__issue_active.avg.pct_of_peak_sustained_active', 'sm__warps_active.avg.pct_of_peak_sustained_active',
              'launch__registers_per_thread', 'launch__grid_size', 'launch__block_size',
-             'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum']
+             'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum',
+             'l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed', 'sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active',
+             'sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active', 'smsp__inst_executed.sum',
+             'smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio',
+             'smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio']
 
 
 def _us(value, unit):
@@ -56,5 +62,26 @@ def full(src, dst):
     print(open(dst).read())
 
 
+def traffic(src, dst, note=""):
+    """Per-launch DRAM bytes of every captured kernel (first capture of each name) -> the table bench.py reads."""
+    raw = subprocess.run(['ncu', '-i', src, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units = rows[0], rows[1]
+    col = {h: i for i, h in enumerate(hdr)}
+    scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+    out = {}
+    for r in rows[2:]:
+        name = r[col['Kernel Name']].split('(')[0].split('<')[0].split('::')[-1].replace('void ', '').strip()
+        if name in out:
+            continue
+        rd = float(r[col['dram__bytes_read.sum']].replace(',', '')) * scale.get(units[col['dram__bytes_read.sum']], 1.0)
+        wr = float(r[col['dram__bytes_write.sum']].replace(',', '')) * scale.get(units[col['dram__bytes_write.sum']], 1.0)
+        us = _us(r[col['gpu__time_duration.sum']], units[col['gpu__time_duration.sum']])
+        out[name] = {'dram_bytes': int(rd + wr), 'dram_read_MB': round(rd / 1e6, 2), 'dram_write_MB': round(wr / 1e6, 2), 'ncu_time_us': round(us, 2)}
+    with open(dst, 'w') as f:
+        json.dump({'source': note, 'per_launch': out}, f, indent=1)
+    print(json.dumps(out, indent=1))
+
+
 if __name__ == '__main__':
-    {'launches': launches, 'full': full}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {'launches': launches, 'full': full, 'traffic': traffic}[sys.argv[1]](*sys.argv[2:])
