@@ -190,6 +190,10 @@ MP_API int mp_warp_f32(const float *src, int N, int n_mats, int H, int W, const 
 #define MP_AGG_SUM 2
 #define MP_HA_INIT 1
 #define MP_HA_FINISH 2
+/* MP_HA_STAGED (optional): stage each sample's source window in shared memory with TMA instead of gathering
+ * through L1.  Bit-identical results; measured slower than the direct gathers at 512x640,
+ * kept as the measured alternative, not the default. */
+#define MP_HA_STAGED 4
 MP_API int mp_ha_aggregate_f32(const float *prob0, const float *probw_a, const float *probw_b,
                                const uint8_t *masks, const float *Ainv, int n, int B, int H, int W,
                                const float *xs, const float *ys, int aggregation, int min_count,

@@ -17,7 +17,11 @@
 // space, computed on the host) -> multiply by 1/z (|z| > 1e-8) -> ATen grid_sample with
 // align_corners=True.  Every fp32 operation is issued un-fused (__fmul_rn / __fadd_rn) in the
 // oracle's order so the sampling position matches bit for bit.
+#include <stdlib.h>
+#include <string.h>
+
 #include "mp_common.cuh"
+#include "mp_tma.cuh"
 
 namespace mp {
 
@@ -179,6 +183,222 @@ ha_aggregate_kernel(const float *__restrict__ prob0, const float *__restrict__ p
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Staged unwarp + aggregate.  The direct kernel above is bound by L1 wavefronts: a warp's gather touches one cache
+// line per source row of its patch's footprint (7-9 lines per request on the reference's +-180 degree homography
+// distribution; ncu: l1tex data-pipe wavefronts 86 %, issue active 67 %).  Here a CTA owns a 32 x 32 block of output
+// pixels (four per thread), and for every sample
+//   1. all threads compute their source coordinates and reduce the bounding box of the taps they will read
+//      (warp-collective min / max, then shared-memory atomics),
+//   2. one thread has the TMA engine copy that window of the sample's heatmap(s) and mask into shared memory --
+//      box sizes 40 / 56 / 72 (the smallest that holds the window; texels outside the image arrive as zeros, which is
+//      exactly the zero padding of the unwarp) -- bypassing L1,
+//   3. the taps are read from shared memory (box widths are 8 mod 16 words: an 8 x 4 patch is conflict-free).
+// A window larger than 72 x 72 (extreme perspective) falls back to the direct gathers for that sample.
+// Arithmetic, tap order and accumulation order are those of the direct kernel: results are bit-identical.
+constexpr int HS_T = 32;                          // tile side
+constexpr int HS_BOX[3] = {40, 56, 72};           // float box sides
+constexpr int HS_MBOX[3] = {64, 80, 96};          // mask box widths (bytes: multiples of 16)
+constexpr int HS_MAXBOX = 72, HS_MAXMBOX = 96;
+// The innermost start coordinate of a TMA window must be 16-byte aligned (measured: an unaligned start traps with an
+// illegal instruction, tools/microbench/tma_window.cu), so the float windows start at x & ~3 and the mask windows at
+// x & ~15: a box of side S then serves tap windows up to S - 3 wide, and the mask box is S + 24 bytes wide.
+
+struct HaMaps {
+    CUtensorMap a[3], b[3], m[3];
+};
+
+template <int AGG, bool TWO>
+__global__ void __launch_bounds__(256)
+ha_aggregate_staged_kernel(const __grid_constant__ HaMaps maps, const float *__restrict__ prob0, const float *__restrict__ pa,
+                           const float *__restrict__ pb, const uint8_t *__restrict__ masks, const float *__restrict__ Ainv,
+                           int n, int B, int H, int W, const float *__restrict__ xs, const float *__restrict__ ys,
+                           int min_count, int flags, float *__restrict__ prob_acc, float *__restrict__ count_acc,
+                           float *__restrict__ out) {
+    extern __shared__ __align__(128) uint8_t hs_smem_raw[];
+    uint8_t *hs_smem = hs_smem_raw + ((128u - (smem_u32(hs_smem_raw) & 127u)) & 127u);   // TMA destinations: 128-byte aligned
+    float *sa = reinterpret_cast<float *>(hs_smem);
+    float *sb = sa + HS_MAXBOX * HS_MAXBOX;
+    uint8_t *smk = reinterpret_cast<uint8_t *>(sb + (TWO ? HS_MAXBOX * HS_MAXBOX : 0));
+    float *As = reinterpret_cast<float *>(smk + HS_MAXMBOX * HS_MAXBOX);
+    __shared__ int bbox[3][4];                     // per sample (mod 3): xlo, ylo, xhi, yhi
+    __shared__ __align__(8) uint64_t bar_mem;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.z;
+    const uint32_t bar = smem_u32(&bar_mem);
+    for (int i = tid; i < n * 9; i += 256) As[i] = Ainv[i];
+    if (tid < 12) (&bbox[0][0])[tid] = (tid & 2) ? INT_MIN : INT_MAX;
+    if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
+    __syncthreads();
+
+    // four pixels per thread: patch q = 4 * warp + p of the 8 (across) x 4 (down) patches of the tile
+    const size_t HW = (size_t)H * W;
+    int px[4], py[4];
+    bool live[4];
+    float xv[4], yv[4], prob[4], count[4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const int q = 4 * warp + p;
+        px[p] = blockIdx.x * HS_T + (q & 3) * 8 + (lane & 7);
+        py[p] = blockIdx.y * HS_T + (q >> 2) * 4 + (lane >> 3);
+        live[p] = px[p] < W && py[p] < H;
+        xv[p] = live[p] ? xs[px[p]] : 0.f;
+        yv[p] = live[p] ? ys[py[p]] : 0.f;
+        const size_t o = (size_t)b * HW + (size_t)py[p] * W + px[p];
+        if (!live[p]) { prob[p] = 0.f; count[p] = 1.f; }
+        else if (flags & MP_HA_INIT) { prob[p] = prob0[o]; count[p] = 1.0f; }
+        else { prob[p] = prob_acc[o]; count[p] = count_acc[o]; }
+    }
+
+    uint32_t phase = 0;
+    for (int i = 0; i < n; ++i) {
+        const int slot = i % 3;
+        // ---- 1. coordinates and the window of this CTA's taps
+        float ix[4], iy[4];
+        int lo_x = INT_MAX, lo_y = INT_MAX, hi_x = INT_MIN, hi_y = INT_MIN;
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            src_coord(As + 9 * i, xv[p], yv[p], W, H, ix[p], iy[p]);
+            if (!live[p]) continue;
+            const float fx = floorf(ix[p]), fy = floorf(iy[p]);
+            if (fx >= -1.f && fx <= (float)W && fy >= -1.f && fy <= (float)H) {   // bilinear_setup's `any`
+                lo_x = min(lo_x, (int)fx); hi_x = max(hi_x, (int)fx + 1);
+                lo_y = min(lo_y, (int)fy); hi_y = max(hi_y, (int)fy + 1);
+            }
+            const float rx = rintf(ix[p]), ry = rintf(iy[p]);
+            if (rx >= 0.f && rx < (float)W && ry >= 0.f && ry < (float)H) {
+                lo_x = min(lo_x, (int)rx); hi_x = max(hi_x, (int)rx);
+                lo_y = min(lo_y, (int)ry); hi_y = max(hi_y, (int)ry);
+            }
+        }
+        lo_x = __reduce_min_sync(0xffffffffu, lo_x); lo_y = __reduce_min_sync(0xffffffffu, lo_y);
+        hi_x = __reduce_max_sync(0xffffffffu, hi_x); hi_y = __reduce_max_sync(0xffffffffu, hi_y);
+        if (lane == 0 && lo_x <= hi_x) {
+            atomicMin(&bbox[slot][0], lo_x); atomicMin(&bbox[slot][1], lo_y);
+            atomicMax(&bbox[slot][2], hi_x); atomicMax(&bbox[slot][3], hi_y);
+        }
+        __syncthreads();
+        const int xlo = bbox[slot][0], ylo = bbox[slot][1];
+        const int ext = max(bbox[slot][2] - xlo + 3, bbox[slot][3] - ylo) + 1;   // block-uniform; + 3: aligned window start
+        const int xf = (xlo >> 2) << 2, xm = (xlo >> 4) << 4;                  // floor to 16 bytes (also for xlo = -1)
+        if (tid == 0) {
+            const int nslot = (i + 1) % 3;           // next sample's window accumulators (last read two samples ago)
+            bbox[nslot][0] = INT_MAX; bbox[nslot][1] = INT_MAX; bbox[nslot][2] = INT_MIN; bbox[nslot][3] = INT_MIN;
+        }
+        if (xlo == INT_MAX) {                        // no tap of this sample lands in the image
+            __syncthreads();                         // (the reset above before anybody's next atomics)
+            continue;
+        }
+        const int v = ext <= 40 ? 0 : ext <= 56 ? 1 : ext <= 72 ? 2 : -1;   // HS_BOX
+        const int bw = 40 + 16 * v, mw = 64 + 16 * v;                          // HS_BOX[v], HS_MBOX[v]
+        // ---- 2. the window -> shared memory
+        if (tid == 0) {
+            if (v >= 0) {
+                const uint32_t bytes = (uint32_t)(bw * bw * 4 * (TWO ? 2 : 1) + mw * bw);
+                mbar_expect_tx(bar, bytes);          // (release: the reset above is visible to whoever sees this phase complete)
+                // (constant indices: a dynamically indexed kernel parameter would be copied to local memory, where the
+                // TMA unit cannot read a tensor map)
+                const CUtensorMap *ma = v == 0 ? &maps.a[0] : v == 1 ? &maps.a[1] : &maps.a[2];
+                const CUtensorMap *mb = v == 0 ? &maps.b[0] : v == 1 ? &maps.b[1] : &maps.b[2];
+                const CUtensorMap *mm = v == 0 ? &maps.m[0] : v == 1 ? &maps.m[1] : &maps.m[2];
+                tma_load_3d(smem_u32(sa), ma, bar, xf, ylo, i * B + b);
+                if (TWO) tma_load_3d(smem_u32(sb), mb, bar, xf, ylo, i * B + b);
+                tma_load_3d(smem_u32(smk), mm, bar, xm, ylo, i);
+            }
+        }
+        if (v >= 0) {
+            mbar_wait(bar, phase);
+            phase ^= 1;
+        } else {
+            __syncthreads();                         // no TMA hand-shake on this path: order the reset above
+        }
+        // ---- 3. taps
+        const float *ga = pa + ((size_t)i * B + b) * HW;
+        const float *gb = TWO ? pb + ((size_t)i * B + b) * HW : nullptr;
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            if (!live[p]) continue;
+            const float rx = rintf(ix[p]), ry = rintf(iy[p]);
+            const bool near_in = rx >= 0.f && rx < (float)W && ry >= 0.f && ry < (float)H;
+            const Bilinear q = bilinear_setup(ix[p], iy[p], W, H);
+            float cs = 0.f, val = 0.f;
+            if (v >= 0) {
+                if (near_in) cs = (float)smk[((int)ry - ylo) * mw + ((int)rx - xm)];
+                if (q.any) {
+                    // the window holds zeros wherever a tap falls outside the image: adding 0 * w leaves the sum as
+                    // skipping the tap does, so no per-tap validity test is needed
+                    const int o = (q.y0 - ylo) * bw + (q.x0 - xf);
+                    float t0, t1, t2, t3;
+                    if (TWO) {
+                        if (AGG == MP_AGG_PROD) {
+                            t0 = __fmul_rn(sa[o], sb[o]); t1 = __fmul_rn(sa[o + 1], sb[o + 1]);
+                            t2 = __fmul_rn(sa[o + bw], sb[o + bw]); t3 = __fmul_rn(sa[o + bw + 1], sb[o + bw + 1]);
+                        } else {
+                            t0 = __fadd_rn(sa[o], sb[o]); t1 = __fadd_rn(sa[o + 1], sb[o + 1]);
+                            t2 = __fadd_rn(sa[o + bw], sb[o + bw]); t3 = __fadd_rn(sa[o + bw + 1], sb[o + bw + 1]);
+                        }
+                    } else {
+                        t0 = sa[o]; t1 = sa[o + 1]; t2 = sa[o + bw]; t3 = sa[o + bw + 1];
+                    }
+                    val = __fadd_rn(val, __fmul_rn(t0, q.nw));
+                    val = __fadd_rn(val, __fmul_rn(t1, q.ne));
+                    val = __fadd_rn(val, __fmul_rn(t2, q.sw));
+                    val = __fadd_rn(val, __fmul_rn(t3, q.se));
+                }
+            } else {   // window too large for shared memory: the direct gathers
+                if (near_in) cs = (float)__ldg(masks + (size_t)i * HW + (int)ry * W + (int)rx);
+                if (TWO) {
+                    val = bilinear_apply(q, W, [&](int off) {
+                        return AGG == MP_AGG_PROD ? __fmul_rn(__ldg(ga + off), __ldg(gb + off)) : __fadd_rn(__ldg(ga + off), __ldg(gb + off));
+                    });
+                } else {
+                    val = bilinear_apply(q, W, [&](int off) { return __ldg(ga + off); });
+                }
+            }
+            count[p] = __fadd_rn(count[p], cs);
+            prob[p] = __fadd_rn(prob[p], __fmul_rn(val, cs));
+        }
+    }
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        if (!live[p]) continue;
+        const size_t o = (size_t)b * HW + (size_t)py[p] * W + px[p];
+        if (flags & MP_HA_FINISH) {
+            float r = __fdiv_rn(prob[p], count[p]);
+            if (AGG == MP_AGG_PROD) r = sqrtf(r);
+            else if (AGG == MP_AGG_SUM) r = __fmul_rn(r, 0.5f);
+            if (min_count > 0 && count[p] < (float)min_count) r = 0.f;
+            out[o] = r;
+        } else {
+            prob_acc[o] = prob[p];
+            count_acc[o] = count[p];
+        }
+    }
+}
+
+// (W, H, planes) tensor of `elem_bytes`-wide elements -> 3-D tiled map with a (box_w, box_h, 1) box, no swizzle
+static int make_window_map(CUtensorMap *map, const void *ptr, CUtensorMapDataType dt, int elem_bytes, int W, int H, long long planes,
+                           int box_w, int box_h) {
+    PFN_encodeTiled enc = get_encode_fn();
+    if (enc == nullptr) {
+        set_error("mp_ha_aggregate_f32: cuTensorMapEncodeTiled not available from the driver");
+        return MP_ERR_CUDA;
+    }
+    cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)planes};
+    cuuint64_t strides[2] = {(cuuint64_t)W * elem_bytes, (cuuint64_t)W * H * elem_bytes};
+    cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(map, dt, 3, const_cast<void *>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("mp_ha_aggregate_f32: cuTensorMapEncodeTiled failed with CUresult %d (W=%d H=%d planes=%lld box=%dx%d)", (int)r, W, H,
+                  planes, box_w, box_h);
+        return MP_ERR_CUDA;
+    }
+    return MP_OK;
+}
+
 }  // namespace mp
 
 extern "C" int mp_warp_f32(const float *src, int N, int n_mats, int H, int W, const float *A,
@@ -218,9 +438,38 @@ extern "C" int mp_ha_aggregate_f32(const float *prob0, const float *probw_a, con
     MP_CHECK_ARG((flags & MP_HA_INIT) || (prob_acc && count_acc), "mp_ha_aggregate_f32: continuing needs prob_acc/count_acc");
     MP_CHECK_ARG(!(flags & MP_HA_FINISH) || out, "mp_ha_aggregate_f32: MP_HA_FINISH needs out");
     MP_CHECK_ARG((flags & MP_HA_FINISH) || (prob_acc && count_acc), "mp_ha_aggregate_f32: partial result needs prob_acc/count_acc");
+    cudaStream_t s = (cudaStream_t)stream;
+    // staged path: TMA needs 16-byte aligned bases and row pitches (floats: W % 4, mask bytes: W % 16)
+    static const bool env_staged = getenv("MP_HA_STAGED") != nullptr;   // tuning aid: the staged kernel for every call
+    const bool two = probw_b != nullptr;
+    const bool staged = (env_staged || (flags & MP_HA_STAGED)) && n > 0 && W % 16 == 0 && (((uintptr_t)probw_a | (uintptr_t)masks | (two ? (uintptr_t)probw_b : 0)) & 15) == 0;
+    if (staged) {
+        HaMaps maps;
+        memset(&maps, 0, sizeof(maps));
+        int rc;
+        for (int v = 0; v < 3; ++v) {
+            if ((rc = make_window_map(&maps.a[v], probw_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, W, H, (long long)n * B, HS_BOX[v], HS_BOX[v])) != MP_OK) return rc;
+            if (two && (rc = make_window_map(&maps.b[v], probw_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, W, H, (long long)n * B, HS_BOX[v], HS_BOX[v])) != MP_OK) return rc;
+            if ((rc = make_window_map(&maps.m[v], masks, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, W, H, n, HS_MBOX[v], HS_BOX[v])) != MP_OK) return rc;
+        }
+        dim3 grid((W + HS_T - 1) / HS_T, (H + HS_T - 1) / HS_T, B);
+        const size_t smem = 128 + (size_t)HS_MAXBOX * HS_MAXBOX * 4 * (two ? 2 : 1) + (size_t)HS_MAXMBOX * HS_MAXBOX + (size_t)n * 9 * sizeof(float);
+#define MP_HA_LAUNCH_STAGED(AGG, TWO)                                                                          \
+    do {                                                                                                \
+        auto k = ha_aggregate_staged_kernel<AGG, TWO>;                                                  \
+        MP_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
+        k<<<grid, 256, smem, s>>>(maps, prob0, probw_a, probw_b, masks, Ainv, n, B, H, W, xs, ys, min_count, flags, \
+                                  prob_acc, count_acc, out);                                            \
+    } while (0)
+        if (aggregation == MP_AGG_PROD) MP_HA_LAUNCH_STAGED(MP_AGG_PROD, true);
+        else if (aggregation == MP_AGG_SUM) MP_HA_LAUNCH_STAGED(MP_AGG_SUM, true);
+        else MP_HA_LAUNCH_STAGED(MP_AGG_NONE, false);
+#undef MP_HA_LAUNCH_STAGED
+        MP_LAUNCH_OK_S("ha_aggregate_kernel", s);
+        return MP_OK;
+    }
     dim3 grid((W + 31) / 32, (H + 7) / 8, B), block(32, 8);
     const size_t smem = (size_t)n * 9 * sizeof(float);
-    cudaStream_t s = (cudaStream_t)stream;
 #define MP_HA_LAUNCH(AGG, TWO)                                                                          \
     do {                                                                                                \
         auto k = ha_aggregate_kernel<AGG, TWO>;                                                         \

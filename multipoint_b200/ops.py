@@ -13,7 +13,7 @@ from . import _lib
 METRIC = {'nn': 0, 'l2': 1}
 ALGO = {'tensor': 0, 'simt': 1}
 AGG = {None: 0, 'none': 0, 'prod': 1, 'sum': 2}
-HA_INIT, HA_FINISH = 1, 2
+HA_INIT, HA_FINISH, HA_STAGED = 1, 2, 4
 
 
 def _cuda(t, dtype, name):
@@ -320,8 +320,9 @@ def valid_masks(Minv, H, W, erosion_radius=0, mask_border=False, device=None):
 
 
 def ha_aggregate(prob0, probw_a, probw_b, masks, Ainv, aggregation, min_count, init=True, finish=True,
-                 prob_acc=None, count_acc=None, tables=None):
-    """Unwarp + accumulate + finish of homographic adaptation; see mp_ha_aggregate_f32."""
+                 prob_acc=None, count_acc=None, tables=None, staged=False):
+    """Unwarp + accumulate + finish of homographic adaptation; see mp_ha_aggregate_f32.  ``staged=True`` selects the
+    TMA-staged kernel (bit-identical, measured slower at 512x640)."""
     probw_a = _cuda(probw_a, torch.float32, "probw_a")
     n, B, H, W = probw_a.shape
     dev = probw_a.device
@@ -337,7 +338,7 @@ def ha_aggregate(prob0, probw_a, probw_b, masks, Ainv, aggregation, min_count, i
         if prob_acc is None:
             prob_acc = torch.zeros((B, H, W), dtype=torch.float32, device=dev)
             count_acc = torch.zeros((B, H, W), dtype=torch.float32, device=dev)
-    flags = (HA_INIT if init else 0) | (HA_FINISH if finish else 0)
+    flags = (HA_INIT if init else 0) | (HA_FINISH if finish else 0) | (HA_STAGED if staged else 0)
     with torch.cuda.device(dev):
         _lib.check(_lib.load().mp_ha_aggregate_f32(_ptr(prob0), _ptr(probw_a), _ptr(probw_b), _ptr(masks), _ptr(Ainv), n, B,
                                                    H, W, _ptr(xs), _ptr(ys), AGG[aggregation], int(min_count), flags,

@@ -547,6 +547,9 @@ def test_homographic_adaptation_vs_restatement_and_oracle(utils, ops, oracle):
         want, wcount = oracle.ha_aggregate(p0, pa, second, masks.astype(np.float32), g["A_unwarp"], agg, 2)
         got = ops.ha_aggregate(cu(p0), cu(pa), None if second is None else cu(second), cu(masks), cu(g["A_unwarp"]), agg, 2)
         np.testing.assert_allclose(got.cpu().numpy(), want, rtol=1e-6, atol=1e-7)
+        # the TMA-staged variant (source windows in shared memory) takes the same taps in the same order: same bits
+        got_st = ops.ha_aggregate(cu(p0), cu(pa), None if second is None else cu(second), cu(masks), cu(g["A_unwarp"]), agg, 2, staged=True)
+        assert torch.equal(got_st, got)
         # split into two partial accumulations (the multi-GPU path) and finish: same result to fp32 rounding
         acc = ops.ha_aggregate(cu(p0), cu(pa[:3]), None if second is None else cu(second[:3]), cu(masks[:3]),
                                cu(g["A_unwarp"][:3]), agg, 2, init=True, finish=False)

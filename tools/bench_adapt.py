@@ -76,7 +76,9 @@ def main():
         print(json.dumps(r), flush=True)
     # the two aggregate flavours separately (events around single calls)
     for name, fn in (("ha_aggregate prod (pairs)", lambda: ops.ha_aggregate(p0, pa, pb, masks, A_unwarp, 'prod', cfg['min_count'], tables=tables)),
-                     ("ha_aggregate single", lambda: ops.ha_aggregate(p0, pa, None, masks, A_unwarp, 'none', cfg['min_count'], tables=tables))):
+                     ("ha_aggregate single", lambda: ops.ha_aggregate(p0, pa, None, masks, A_unwarp, 'none', cfg['min_count'], tables=tables)),
+                     ("ha_aggregate prod (pairs), TMA-staged variant", lambda: ops.ha_aggregate(p0, pa, pb, masks, A_unwarp, 'prod', cfg['min_count'], tables=tables, staged=True)),
+                     ("ha_aggregate single, TMA-staged variant", lambda: ops.ha_aggregate(p0, pa, None, masks, A_unwarp, 'none', cfg['min_count'], tables=tables, staged=True))):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(args.iters):
