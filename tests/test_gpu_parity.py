@@ -409,6 +409,32 @@ def test_matching_bench_sizes_properties(ops):
         assert int(c[0]) == N and bool((q[0] == torch.arange(N, device="cuda")).all())
 
 
+def test_column_side_equals_row_side_of_the_swapped_problem(ops):
+    """The fused matcher takes idx21 (argmin over axis 0, matching.py:58-59) from the SAME GEMM as idx12, through a
+    different code path (warp-collective reductions per 32-row chunk + the chunk-merge kernel) than the in-thread row
+    side.  Swapping the operands exchanges the two paths, so at BASELINE sizes, ragged counts, both metrics and both
+    descriptor sizes: nearest(a, b).idx21 == nearest(b, a).idx12 and vice versa, index for index (both are the exact
+    fp64 argmin with ties to the lowest index); the approximate best similarities agree within the error bound."""
+    g = torch.Generator(device="cuda").manual_seed(77)
+    for P, N1, N2, D in ((8, 2048, 1900, 256), (8, 2048, 2048, 64), (1, 16384, 16000, 256), (2, 333, 4097, 128)):
+        a = torch.nn.functional.normalize(torch.randn((P, N1, D), generator=g, device="cuda"), dim=2)
+        b = torch.nn.functional.normalize(torch.randn((P, N2, D), generator=g, device="cuda"), dim=2)
+        m = min(N1, N2)
+        b[:, :m] = torch.nn.functional.normalize(a[:, torch.randperm(N1, generator=g, device="cuda")[:m]]
+                                                 + 0.3 * torch.randn((P, m, D), generator=g, device="cuda") / D ** 0.5, dim=2)
+        b[:, 5] = b[:, 4]                                     # exact duplicates: ties to the lowest index on both sides
+        n1 = torch.full((P,), N1, dtype=torch.int32, device="cuda"); n1[-1] = N1 - 37
+        n2 = torch.full((P,), N2, dtype=torch.int32, device="cuda"); n2[0] = N2 - 129
+        for metric in ("l2", "nn"):
+            ab = ops.nearest(a, b, metric=metric, algo="tensor", n1=n1, n2=n2)
+            ba = ops.nearest(b, a, metric=metric, algo="tensor", n1=n2, n2=n1)
+            for p in range(P):
+                k1, k2 = int(n1[p]), int(n2[p])
+                assert torch.equal(ab["idx21"][p, :k2], ba["idx12"][p, :k2]), (P, N1, N2, D, metric, p)
+                assert torch.equal(ab["idx12"][p, :k1], ba["idx21"][p, :k1]), (P, N1, N2, D, metric, p)
+                assert float((ab["best21"][p, :k2] - ba["best12"][p, :k2]).abs().max()) < 1e-4
+
+
 def test_get_matches_dropin(utils):
     import cv2
     g = load_golden("matching")
