@@ -185,7 +185,11 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args, {"sample": "1 pair per step (bounded sample of the 64-pair workload)"}),
+            "config": workload_config(args, {"sample": "1 pair per step (bounded sample of the 64-pair workload; value is per pair, so it compares "
+                                                       "with the 64-pair step's pairs/s)",
+                                             "backbone": "multipoint_b200.models.MultiPoint on the CPU through torch's own modules (same module list and "
+                                                         "state dict as the reference class, which cannot be imported on the GPU box); everything after it "
+                                                         "is the reference's own library calls (oracle/reference_port.py)"}),
             "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": threads, "kind": "port",
                              "sample": "1 pair per step: torch CPU backbone x2 + oracle/reference_port.py "
                                        "(torch softmax, torchvision batched_nms, grid_sample, cv2.BFMatcher crossCheck)"},
