@@ -528,8 +528,9 @@ def main():
                                                                         want_dense=False),
                                                     B2 * (H * W * 4 + 20 * args.topk)),
         "normalize_desc_nhwc": (lambda: ops.normalize_descriptors(raw, nchw=False, nhwc=True), B2 * 2 * 4 * args.desc * 5120),
-        "sample_descriptors": (lambda: ops.sample_descriptors(kp, ops.normalize_descriptors(raw, nchw=False, nhwc=True)[1], H, W, counts=cnt, channels_last=True), None),
-        "match(both directions+select)": (lambda: ops.match(desc_s[:P], desc_s[P:], metric='l2', kind='mutual', cross_check=True, n1=cnt[:P], n2=cnt[P:]), None),
+        "sample_descriptors": (lambda: ops.sample_descriptors(kp, ops.normalize_descriptors(raw, nchw=False, nhwc=True)[1], H, W, counts=cnt, channels_last=True,
+                                                              split=args.desc in (64, 128, 256)), None),
+        "match(both directions+select)": (lambda: pipe.match({k: v[:P] for k, v in ext.items()}, {k: v[P:] for k, v in ext.items()}), None),
     }
     kernels = {}
     for name, (fn, nbytes) in stages.items():
@@ -539,10 +540,11 @@ def main():
             kernels[name]["algorithmic_GBps"] = nbytes / ms / 1e6
     # sample_descriptors timed above includes the normalise it depends on; subtract
     kernels["sample_descriptors"]["ms"] = max(0.0, kernels["sample_descriptors"]["ms"] - kernels["normalize_desc_nhwc"]["ms"])
-    kernels["sample_descriptors"]["algorithmic_GBps"] = B2 * (16 * args.topk * args.desc + 4 * args.topk * args.desc + 16 * args.topk) / max(kernels["sample_descriptors"]["ms"], 1e-6) / 1e6
+    # gathered corner rows + the fp32 rows written + (split) the two bf16 planes and the squared norms written for the matcher
+    kernels["sample_descriptors"]["algorithmic_GBps"] = B2 * (16 * args.topk * args.desc + 8 * args.topk * args.desc + 20 * args.topk) / max(kernels["sample_descriptors"]["ms"], 1e-6) / 1e6
     flops = 2.0 * P * args.topk * args.topk * args.desc
     kernels["match(both directions+select)"]["algorithmic_TFLOPs"] = flops / kernels["match(both directions+select)"]["ms"] / 1e9
-    kernels["match(both directions+select)"]["executed_TFLOPs"] = 6 * flops / kernels["match(both directions+select)"]["ms"] / 1e9
+    kernels["match(both directions+select)"]["executed_TFLOPs"] = 3 * flops / kernels["match(both directions+select)"]["ms"] / 1e9   # one GEMM, three bf16 passes
 
     peaks = {}
     try:
@@ -580,7 +582,8 @@ def main():
         "nms_tile_fast_kernel": ("hbm", B2 * 2 * H * W * 4),
         "nms_candidates_kernel": ("hbm", B2 * H * W * 4),       # heatmap read (keypoints only: no dense map; the candidate list is extra)
         "normalize_desc_kernel": ("hbm", B2 * 2 * 4 * Dd * 5120),
-        "sample_descriptors_kernel": ("hbm", B2 * (min(16 * Kp * Dd, 4 * Dd * 5120) + 4 * Kp * Dd + 16 * Kp)),
+        # descriptor map read once + fp32 rows written + the matcher's bf16 planes (2 x 2 B) and squared norms written
+        "sample_descriptors_kernel": ("hbm", B2 * (min(16 * Kp * Dd, 4 * Dd * 5120) + 8 * Kp * Dd + 20 * Kp)),
         "match_prep_vec_kernel": ("hbm", P * Kp * Dd * (4 + 2 + 2)),
         "match_top2_tc_kernel": ("tensor", 2.0 * P * Kp * Kp * Dd),
     }

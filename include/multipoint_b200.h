@@ -117,6 +117,13 @@ MP_API int mp_extract_keypoints_f32(const float *prob, const uint8_t *mask, int 
 MP_API int mp_sample_descriptors_f32(const int64_t *keypoints, const int32_t *kp_counts, int B,
                                      int K, const float *desc, int D, int Hc, int Wc, int layout,
                                      int H, int W, float *out, mp_stream_t stream);
+/* The same, and the rows once more in the form the tensor-core matcher consumes (mp_match_split_f32): bf16 planes
+ * hi = bf16(v), mid = bf16(v - hi), both (B,K,D), and the squared norms (B,K) of the rows as written.  Saves the
+ * matcher its own pass over the descriptors.  Channels-last layout, D in {64, 128, 256}. */
+MP_API int mp_sample_descriptors_split_f32(const int64_t *keypoints, const int32_t *kp_counts, int B,
+                                           int K, const float *desc, int D, int Hc, int Wc, int layout,
+                                           int H, int W, float *out, void *hi_bf16, void *mid_bf16,
+                                           float *sq_norms, mp_stream_t stream);
 
 /* ---- rows 6-8: utils.get_matches, multipoint/utils/matching.py:4-99 -----------------------
  * P independent problems (image pairs).  d1 (P,N1,D), d2 (P,N2,D); n1/n2 (P) device counts of
@@ -154,6 +161,16 @@ MP_API int mp_match_f32(const float *d1, const int32_t *n1, int N1, const float 
                         int cross_check, double threshold, double ratio, int32_t *query,
                         int32_t *train, float *dist, int32_t *counts, void *workspace,
                         size_t workspace_bytes, mp_stream_t stream);
+/* mp_match_f32 on the tensor-core path with operands already split by mp_sample_descriptors_split_f32:
+ * d (P,N,D) fp32 (exact recheck and distances), hi / mid (P,N,D) bf16, sq_norms (P,N), max_norm (P) = float bits of
+ * an upper bound of the largest row norm of the pair's set (1.000001f for unit-norm descriptors). */
+MP_API int mp_match_split_f32(const float *d1, const void *hi1, const void *mid1, const float *sq_norms1,
+                              const uint32_t *max_norm1, const int32_t *n1, int N1, const float *d2,
+                              const void *hi2, const void *mid2, const float *sq_norms2,
+                              const uint32_t *max_norm2, const int32_t *n2, int N2, int P, int D, int metric,
+                              int kind, int cross_check, double threshold, double ratio, int32_t *query,
+                              int32_t *train, float *dist, int32_t *counts, void *workspace,
+                              size_t workspace_bytes, mp_stream_t stream);
 
 /* ThresholdMatcher.match, matching.py:74-99: every pair with sqrt(2-2clip(a.b)) < threshold in
  * row-major order.  One problem per call.  total_host receives the number of pairs found (the

@@ -31,9 +31,12 @@ SIGNATURES = {
     "mp_extract_keypoints_workspace_bytes": (_sz, [_i, _i, _i]),
     "mp_extract_keypoints_f32": (_i, [_vp, _vp, _i, _i, _i, _d, _vp, _vp, _vp, _i, _vp, _sz, _vp]),
     "mp_sample_descriptors_f32": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "mp_sample_descriptors_split_f32": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "mp_match_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "mp_nearest_f32": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "mp_match_f32": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _d, _d, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "mp_match_split_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _d, _d,
+                                _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "mp_match_threshold_f32": (_i, [_vp, _i, _vp, _i, _i, _d, _vp, _vp, _vp, _i64, _c.POINTER(_i64), _vp, _sz, _vp]),
     "mp_warp_f32": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _vp]),
     "mp_valid_mask_u8": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp]),

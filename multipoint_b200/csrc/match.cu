@@ -832,20 +832,29 @@ MatchLayout::MatchLayout(int P, int N1, int N2, int D) {
     total = off;
 }
 
+// Operands of one descriptor set already split for the tensor path (mp_sample_descriptors_split_f32): bf16 planes,
+// squared norms, and an upper bound of the largest norm per pair (float bits).
+struct SplitSet {
+    const __nv_bfloat16 *hi, *mid;
+    const float *norms;
+    const unsigned *max_norm;
+};
+
 // Fills ws.idx12 / ws.idx21 (exact) and ws.top12 / ws.top21 (approximate keys).
 static int run_nearest(const float *d1, const int32_t *n1, int N1, const float *d2, const int32_t *n2, int N2,
-                       int P, int D, int metric, int algo, const MatchLayout &L, char *ws, cudaStream_t s) {
+                       int P, int D, int metric, int algo, const MatchLayout &L, char *ws, cudaStream_t s,
+                       const SplitSet *s1 = nullptr, const SplitSet *s2 = nullptr) {
     unsigned *scal = (unsigned *)(ws + L.scalars);
-    unsigned *max1 = scal, *max2 = scal + P;
+    const unsigned *max1 = s1 ? s1->max_norm : scal, *max2 = s2 ? s2->max_norm : scal + P;
     int *n_flagged = (int *)(scal + 2 * P), *n_pairs = (int *)(scal + 4 * P);
-    float *norms1 = (float *)(ws + L.norms1), *norms2 = (float *)(ws + L.norms2);
+    const float *norms1 = s1 ? s1->norms : (float *)(ws + L.norms1), *norms2 = s2 ? s2->norms : (float *)(ws + L.norms2);
     Top2 *top12 = (Top2 *)(ws + L.top12), *top21 = (Top2 *)(ws + L.top21);
     int32_t *idx12 = (int32_t *)(ws + L.idx12), *idx21 = (int32_t *)(ws + L.idx21);
     int32_t *flagged1 = (int32_t *)(ws + L.flagged1), *flagged2 = (int32_t *)(ws + L.flagged2);
     int32_t *pairs1 = (int32_t *)(ws + L.pairs1), *pairs2 = (int32_t *)(ws + L.pairs2);
     const bool tensor = algo == MP_ALGO_TENSOR;
-    __nv_bfloat16 *hi1 = tensor ? (__nv_bfloat16 *)(ws + L.hi1) : nullptr, *mid1 = (__nv_bfloat16 *)(ws + L.mid1);
-    __nv_bfloat16 *hi2 = tensor ? (__nv_bfloat16 *)(ws + L.hi2) : nullptr, *mid2 = (__nv_bfloat16 *)(ws + L.mid2);
+    const __nv_bfloat16 *hi1 = s1 ? s1->hi : tensor ? (__nv_bfloat16 *)(ws + L.hi1) : nullptr, *mid1 = s1 ? s1->mid : (__nv_bfloat16 *)(ws + L.mid1);
+    const __nv_bfloat16 *hi2 = s2 ? s2->hi : tensor ? (__nv_bfloat16 *)(ws + L.hi2) : nullptr, *mid2 = s2 ? s2->mid : (__nv_bfloat16 *)(ws + L.mid2);
     const int use_bias = metric == MP_METRIC_L2;
 
     MP_CUDA_OK(cudaMemsetAsync(scal, 0, sizeof(unsigned) * (6 * (size_t)P + 4 + 2 * (size_t)P * RK_ROW_MAX), s));
@@ -858,10 +867,14 @@ static int run_nearest(const float *d1, const int32_t *n1, int N1, const float *
         else if (D <= 128) match_prep_vec_kernel<2><<<(unsigned)((rows + 15) / 16), 256, 0, s>>>(d, n, N, D, P, norms, mx, h, m);
         else match_prep_vec_kernel<1><<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(d, n, N, D, P, norms, mx, h, m);
     };
-    prep(d1, n1, N1, r1, norms1, max1, hi1, mid1);
-    MP_LAUNCH_OK_S("match_prep_vec_kernel", s);
-    prep(d2, n2, N2, r2, norms2, max2, hi2, mid2);
-    MP_LAUNCH_OK_S("match_prep_vec_kernel", s);
+    if (!s1) {
+        prep(d1, n1, N1, r1, (float *)(ws + L.norms1), scal, (__nv_bfloat16 *)hi1, (__nv_bfloat16 *)mid1);
+        MP_LAUNCH_OK_S("match_prep_vec_kernel", s);
+    }
+    if (!s2) {
+        prep(d2, n2, N2, r2, (float *)(ws + L.norms2), scal + P, (__nv_bfloat16 *)hi2, (__nv_bfloat16 *)mid2);
+        MP_LAUNCH_OK_S("match_prep_vec_kernel", s);
+    }
 
     if (tensor) {
         // one GEMM per pair: rows of set 1 against set 2 (top12) and, from the same accumulators, the columns' view
@@ -976,27 +989,26 @@ extern "C" int mp_nearest_f32(const float *d1, const int32_t *n1, int N1, const 
     return MP_OK;
 }
 
-extern "C" int mp_match_f32(const float *d1, const int32_t *n1, int N1, const float *d2,
-                            const int32_t *n2, int N2, int P, int D, int metric, int algo, int kind,
-                            int cross_check, double threshold, double ratio, int32_t *query,
-                            int32_t *train, float *dist, int32_t *counts, void *workspace,
-                            size_t workspace_bytes, mp_stream_t stream) {
-    mp::prof_entry((cudaStream_t)stream);
+static int match_impl(const char *fn, const float *d1, const int32_t *n1, int N1, const float *d2,
+                      const int32_t *n2, int N2, int P, int D, int metric, int algo, int kind,
+                      int cross_check, double threshold, double ratio, int32_t *query,
+                      int32_t *train, float *dist, int32_t *counts, void *workspace,
+                      size_t workspace_bytes, mp_stream_t stream, const mp::SplitSet *s1, const mp::SplitSet *s2) {
     using namespace mp;
     const MatchLayout L(P > 0 ? P : 0, N1 > 0 ? N1 : 0, N2 > 0 ? N2 : 0, D > 0 ? D : 1);
-    int rc = check_match_args("mp_match_f32", d1, N1, d2, N2, P, D, metric, algo, workspace, workspace_bytes, L);
+    int rc = check_match_args(fn, d1, N1, d2, N2, P, D, metric, algo, workspace, workspace_bytes, L);
     if (rc != MP_OK) return rc;
-    MP_CHECK_ARG(kind == MP_MATCH_MUTUAL || kind == MP_MATCH_RATIO, "mp_match_f32: bad kind %d", kind);
+    MP_CHECK_ARG(kind == MP_MATCH_MUTUAL || kind == MP_MATCH_RATIO, "%s: bad kind %d", fn, kind);
     if (P == 0) return MP_OK;
-    MP_CHECK_ARG(counts != nullptr, "mp_match_f32: counts is required");
+    MP_CHECK_ARG(counts != nullptr, "%s: counts is required", fn);
     cudaStream_t s = (cudaStream_t)stream;
     if ((long long)P * N1 == 0 || (long long)P * N2 == 0) {
         MP_CUDA_OK(cudaMemsetAsync(counts, 0, sizeof(int32_t) * P, s));
         return MP_OK;
     }
-    MP_CHECK_ARG(query && train && dist, "mp_match_f32: null output pointer");
+    MP_CHECK_ARG(query && train && dist, "%s: null output pointer", fn);
     char *ws = (char *)workspace;
-    rc = run_nearest(d1, n1, N1, d2, n2, N2, P, D, metric, algo, L, ws, s);
+    rc = run_nearest(d1, n1, N1, d2, n2, N2, P, D, metric, algo, L, ws, s, s1, s2);
     if (rc != MP_OK) return rc;
     const long long r1 = (long long)P * N1;
     int32_t *train_tmp = (int32_t *)(ws + L.train_tmp);
@@ -1019,6 +1031,34 @@ extern "C" int mp_match_f32(const float *d1, const int32_t *n1, int N1, const fl
     match_compact_kernel<<<P, 1024, 0, s>>>(train_tmp, dist_tmp, N1, query, train, dist, counts);
     MP_LAUNCH_OK_S("match_compact_kernel", s);
     return MP_OK;
+}
+
+extern "C" int mp_match_f32(const float *d1, const int32_t *n1, int N1, const float *d2,
+                            const int32_t *n2, int N2, int P, int D, int metric, int algo, int kind,
+                            int cross_check, double threshold, double ratio, int32_t *query,
+                            int32_t *train, float *dist, int32_t *counts, void *workspace,
+                            size_t workspace_bytes, mp_stream_t stream) {
+    mp::prof_entry((cudaStream_t)stream);
+    return match_impl("mp_match_f32", d1, n1, N1, d2, n2, N2, P, D, metric, algo, kind, cross_check, threshold, ratio, query, train,
+                      dist, counts, workspace, workspace_bytes, stream, nullptr, nullptr);
+}
+
+extern "C" int mp_match_split_f32(const float *d1, const void *hi1, const void *mid1, const float *sq_norms1,
+                                  const uint32_t *max_norm1, const int32_t *n1, int N1, const float *d2,
+                                  const void *hi2, const void *mid2, const float *sq_norms2,
+                                  const uint32_t *max_norm2, const int32_t *n2, int N2, int P, int D, int metric,
+                                  int kind, int cross_check, double threshold, double ratio, int32_t *query,
+                                  int32_t *train, float *dist, int32_t *counts, void *workspace,
+                                  size_t workspace_bytes, mp_stream_t stream) {
+    mp::prof_entry((cudaStream_t)stream);
+    MP_CHECK_ARG(hi1 && mid1 && sq_norms1 && max_norm1 && hi2 && mid2 && sq_norms2 && max_norm2,
+                 "mp_match_split_f32: null split operand");
+    MP_CHECK_ARG((((uintptr_t)hi1 | (uintptr_t)mid1 | (uintptr_t)hi2 | (uintptr_t)mid2) & 15) == 0,
+                 "mp_match_split_f32: the bf16 planes must be 16-byte aligned (TMA)");
+    const mp::SplitSet s1 = {(const __nv_bfloat16 *)hi1, (const __nv_bfloat16 *)mid1, sq_norms1, max_norm1};
+    const mp::SplitSet s2 = {(const __nv_bfloat16 *)hi2, (const __nv_bfloat16 *)mid2, sq_norms2, max_norm2};
+    return match_impl("mp_match_split_f32", d1, n1, N1, d2, n2, N2, P, D, metric, MP_ALGO_TENSOR, kind, cross_check, threshold, ratio,
+                      query, train, dist, counts, workspace, workspace_bytes, stream, &s1, &s2);
 }
 
 extern "C" int mp_match_threshold_f32(const float *d1, int N1, const float *d2, int N2, int D,

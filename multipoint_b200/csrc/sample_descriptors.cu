@@ -11,6 +11,8 @@
 // HBM-bound gather: one warp per keypoint, lanes across channels.  With the channels-last map
 // (B,Hc,Wc,D) produced by mp_normalize_descriptors_f32 every corner is one contiguous D*4 B row;
 // with NCHW each lane gathers strided words (kept for drop-in use on the reference's layout).
+#include <cuda_bf16.h>
+
 #include "mp_common.cuh"
 
 namespace mp {
@@ -85,11 +87,14 @@ sample_descriptors_kernel(const int64_t *__restrict__ kp, const int32_t *__restr
 // A corner row of D*4 bytes is NV fully coalesced requests.  D = 64 (the shipped descriptor size) uses 16 lanes per
 // keypoint, i.e. two keypoints per warp: with a whole warp per keypoint and 64-bit vectors it spent as many
 // instructions per keypoint as D = 256 on a quarter of the bytes (47 % of the HBM roofline).
-template <int LPK, int NV>
+// SPLIT: also write what the tensor-core matcher consumes -- the rows split into bf16 planes (hi = bf16(v),
+// mid = bf16(v - hi)) and their squared norms -- so that mp_match_split_f32 needs no prep pass over the descriptors.
+template <int LPK, int NV, bool SPLIT>
 __global__ void __launch_bounds__(SD_WARPS * 32)
 sample_descriptors_nhwc_vec_kernel(const int64_t *__restrict__ kp, const int32_t *__restrict__ counts,
                                    const float *__restrict__ desc, float *__restrict__ out, int B, int K, int Hc, int Wc,
-                                   float half_h, float half_w) {
+                                   float half_h, float half_w, __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ mid,
+                                   float *__restrict__ norms) {
     constexpr int D = 4 * LPK * NV, KPW = 32 / LPK;   // keypoints per warp
     const int lane = threadIdx.x & 31, sub = lane % LPK;
     const long long item = ((long long)blockIdx.x * SD_WARPS + (threadIdx.x >> 5)) * KPW + lane / LPK;
@@ -138,45 +143,97 @@ sample_descriptors_nhwc_vec_kernel(const int64_t *__restrict__ kp, const int32_t
     for (int j = 0; j < NV; ++j) ss += v[j].x * v[j].x + v[j].y * v[j].y + v[j].z * v[j].z + v[j].w * v[j].w;
 #pragma unroll
     for (int s = LPK / 2; s > 0; s >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, s);
-    if (!in_range) return;
+    if (!SPLIT && !in_range) return;   // (SPLIT: the lanes still take part in the norm reduction below)
     if (live) {
         const float denom = fmaxf(sqrtf(ss), 1e-12f);
 #pragma unroll
         for (int j = 0; j < NV; ++j) { v[j].x = v[j].x / denom; v[j].y = v[j].y / denom; v[j].z = v[j].z / denom; v[j].w = v[j].w / denom; }
     }
-    float4 *o = reinterpret_cast<float4 *>(out + (size_t)item * D);
+    if (in_range) {
+        float4 *o = reinterpret_cast<float4 *>(out + (size_t)item * D);
 #pragma unroll
-    for (int j = 0; j < NV; ++j) o[sub + LPK * j] = v[j];
+        for (int j = 0; j < NV; ++j) o[sub + LPK * j] = v[j];
+    }
+    if (SPLIT) {
+        float s2 = 0.f;     // squared norm of the row as written (the matcher's L2 term), lanes of the group reduce it
+        uint2 *oh = reinterpret_cast<uint2 *>(hi + (size_t)item * D), *om = reinterpret_cast<uint2 *>(mid + (size_t)item * D);
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            const float e[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+            __align__(8) __nv_bfloat16 h[4], m[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                h[c] = __float2bfloat16_rn(e[c]);
+                m[c] = __float2bfloat16_rn(e[c] - __bfloat162float(h[c]));
+                s2 += e[c] * e[c];
+            }
+            if (in_range) {
+                oh[sub + LPK * j] = *reinterpret_cast<const uint2 *>(h);
+                om[sub + LPK * j] = *reinterpret_cast<const uint2 *>(m);
+            }
+        }
+#pragma unroll
+        for (int sft = LPK / 2; sft > 0; sft >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, sft);
+        if (sub == 0 && in_range) norms[item] = s2;
+    }
 }
 
 }  // namespace mp
+
+static int sample_descriptors_impl(const char *fn, const int64_t *keypoints, const int32_t *kp_counts, int B, int K, const float *desc,
+                                   int D, int Hc, int Wc, int layout, int H, int W, float *out, __nv_bfloat16 *hi,
+                                   __nv_bfloat16 *mid, float *norms, cudaStream_t s) {
+    using namespace mp;
+    MP_CHECK_ARG(B >= 0 && K >= 0 && D > 0 && Hc > 0 && Wc > 0 && H > 0 && W > 0, "%s: bad shape", fn);
+    MP_CHECK_ARG(D <= 32 * SD_MAX_CPL, "%s: D=%d > %d unsupported", fn, D, 32 * SD_MAX_CPL);
+    MP_CHECK_ARG(layout == MP_LAYOUT_NCHW || layout == MP_LAYOUT_NHWC, "%s: bad layout %d", fn, layout);
+    if ((long long)B * K == 0) return MP_OK;
+    MP_CHECK_ARG(keypoints && desc && out, "%s: null pointer", fn);
+    const long long items = (long long)B * K;
+    const unsigned grid = (unsigned)((items + SD_WARPS - 1) / SD_WARPS);
+    const float hh = (float)H * 0.5f, hw = (float)W * 0.5f;
+    const bool aligned = (((uintptr_t)desc | (uintptr_t)out) & 15) == 0;
+    const bool split = hi != nullptr;
+    if (split) {
+        if (!(layout == MP_LAYOUT_NHWC && aligned && (D == 64 || D == 128 || D == 256) && mid && norms &&
+              (((uintptr_t)hi | (uintptr_t)mid) & 7) == 0)) {
+            set_error("%s: the split outputs need the channels-last layout, D in {64,128,256} and aligned buffers", fn);
+            return MP_ERR_UNSUPPORTED;
+        }
+    }
+    if (layout == MP_LAYOUT_NHWC && aligned && (D == 64 || D == 128 || D == 256)) {
+        const unsigned grid2 = (unsigned)((items + 2 * SD_WARPS - 1) / (2 * SD_WARPS));   // two keypoints per warp
+#define MP_SD_LAUNCH(LPK, NV, G)                                                                                                  \
+    do {                                                                                                                          \
+        if (split) sample_descriptors_nhwc_vec_kernel<LPK, NV, true><<<G, SD_WARPS * 32, 0, s>>>(keypoints, kp_counts, desc, out, B, K, Hc, Wc, hh, hw, hi, mid, norms);   \
+        else sample_descriptors_nhwc_vec_kernel<LPK, NV, false><<<G, SD_WARPS * 32, 0, s>>>(keypoints, kp_counts, desc, out, B, K, Hc, Wc, hh, hw, nullptr, nullptr, nullptr); \
+    } while (0)
+        if (D == 64) MP_SD_LAUNCH(16, 1, grid2);
+        else if (D == 128) MP_SD_LAUNCH(32, 1, grid);
+        else MP_SD_LAUNCH(32, 2, grid);
+#undef MP_SD_LAUNCH
+    } else if (layout == MP_LAYOUT_NHWC)
+        sample_descriptors_kernel<MP_LAYOUT_NHWC><<<grid, SD_WARPS * 32, 0, s>>>(keypoints, kp_counts, desc, out, B, K, D, Hc, Wc, hh, hw);
+    else
+        sample_descriptors_kernel<MP_LAYOUT_NCHW><<<grid, SD_WARPS * 32, 0, s>>>(keypoints, kp_counts, desc, out, B, K, D, Hc, Wc, hh, hw);
+    MP_LAUNCH_OK_S("sample_descriptors_kernel", s);
+    return MP_OK;
+}
 
 extern "C" int mp_sample_descriptors_f32(const int64_t *keypoints, const int32_t *kp_counts, int B,
                                          int K, const float *desc, int D, int Hc, int Wc, int layout,
                                          int H, int W, float *out, mp_stream_t stream) {
     mp::prof_entry((cudaStream_t)stream);
-    MP_CHECK_ARG(B >= 0 && K >= 0 && D > 0 && Hc > 0 && Wc > 0 && H > 0 && W > 0,
-                 "mp_sample_descriptors_f32: bad shape");
-    MP_CHECK_ARG(D <= 32 * mp::SD_MAX_CPL, "mp_sample_descriptors_f32: D=%d > %d unsupported", D, 32 * mp::SD_MAX_CPL);
-    MP_CHECK_ARG(layout == MP_LAYOUT_NCHW || layout == MP_LAYOUT_NHWC, "mp_sample_descriptors_f32: bad layout %d", layout);
-    if ((long long)B * K == 0) return MP_OK;
-    MP_CHECK_ARG(keypoints && desc && out, "mp_sample_descriptors_f32: null pointer");
-    const long long items = (long long)B * K;
-    const unsigned grid = (unsigned)((items + mp::SD_WARPS - 1) / mp::SD_WARPS);
-    const float hh = (float)H * 0.5f, hw = (float)W * 0.5f;
-    const bool aligned = (((uintptr_t)desc | (uintptr_t)out) & 15) == 0;
-    cudaStream_t s = (cudaStream_t)stream;
-    if (layout == MP_LAYOUT_NHWC && aligned && (D == 64 || D == 128 || D == 256)) {
-        const unsigned grid2 = (unsigned)((items + 2 * mp::SD_WARPS - 1) / (2 * mp::SD_WARPS));   // two keypoints per warp
-        if (D == 64) mp::sample_descriptors_nhwc_vec_kernel<16, 1><<<grid2, mp::SD_WARPS * 32, 0, s>>>(keypoints, kp_counts, desc, out, B, K, Hc, Wc, hh, hw);
-        else if (D == 128) mp::sample_descriptors_nhwc_vec_kernel<32, 1><<<grid, mp::SD_WARPS * 32, 0, s>>>(keypoints, kp_counts, desc, out, B, K, Hc, Wc, hh, hw);
-        else mp::sample_descriptors_nhwc_vec_kernel<32, 2><<<grid, mp::SD_WARPS * 32, 0, s>>>(keypoints, kp_counts, desc, out, B, K, Hc, Wc, hh, hw);
-    } else if (layout == MP_LAYOUT_NHWC)
-        mp::sample_descriptors_kernel<MP_LAYOUT_NHWC><<<grid, mp::SD_WARPS * 32, 0, (cudaStream_t)stream>>>(
-            keypoints, kp_counts, desc, out, B, K, D, Hc, Wc, hh, hw);
-    else
-        mp::sample_descriptors_kernel<MP_LAYOUT_NCHW><<<grid, mp::SD_WARPS * 32, 0, (cudaStream_t)stream>>>(
-            keypoints, kp_counts, desc, out, B, K, D, Hc, Wc, hh, hw);
-    MP_LAUNCH_OK_S("sample_descriptors_kernel", s);
-    return MP_OK;
+    return sample_descriptors_impl("mp_sample_descriptors_f32", keypoints, kp_counts, B, K, desc, D, Hc, Wc, layout, H, W, out,
+                                   nullptr, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int mp_sample_descriptors_split_f32(const int64_t *keypoints, const int32_t *kp_counts, int B,
+                                               int K, const float *desc, int D, int Hc, int Wc, int layout,
+                                               int H, int W, float *out, void *hi_bf16, void *mid_bf16,
+                                               float *sq_norms, mp_stream_t stream) {
+    mp::prof_entry((cudaStream_t)stream);
+    MP_CHECK_ARG(hi_bf16 && mid_bf16 && sq_norms, "mp_sample_descriptors_split_f32: null split output");
+    return sample_descriptors_impl("mp_sample_descriptors_split_f32", keypoints, kp_counts, B, K, desc, D, Hc, Wc, layout, H, W, out,
+                                   (__nv_bfloat16 *)hi_bf16, (__nv_bfloat16 *)mid_bf16, sq_norms, (cudaStream_t)stream);
 }

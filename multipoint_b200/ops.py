@@ -157,12 +157,14 @@ def transpose_descriptors(desc):
     return out
 
 
-def sample_descriptors(keypoints, desc, H, W, counts=None, channels_last=False, transpose=None):
+def sample_descriptors(keypoints, desc, H, W, counts=None, channels_last=False, transpose=None, split=False):
     """keypoints (B,K,2) int64 (y,x); desc (B,D,Hc,Wc) or, channels_last, (B,Hc,Wc,D) -> (B,K,D) unit rows.
     An NCHW map is copied to channels-last first when the gather is large enough to pay for it (``transpose=None``:
     K*16 >= Hc*Wc, i.e. the four corners of all keypoints touch at least as many descriptor rows as the copy moves;
     True / False force it): the strided NCHW gather moves 4x the sectors of the contiguous-row one (measured 1.02 ms
-    against 0.17 ms at 128 x 2048 keypoints, D = 256).  Results are bit-identical either way."""
+    against 0.17 ms at 128 x 2048 keypoints, D = 256).  Results are bit-identical either way.
+    ``split=True`` also returns the rows in the matcher's operand form -- a dict with 'hi', 'mid' (B,K,D) bf16,
+    'sq_norms' (B,K) and 'max_norm' (B) int32 float bits -- for ``match(..., split1=, split2=)``."""
     keypoints = _cuda(keypoints, torch.int64, "keypoints")
     desc = _cuda(desc, torch.float32, "desc")
     B, K = keypoints.shape[:2]
@@ -178,6 +180,20 @@ def sample_descriptors(keypoints, desc, H, W, counts=None, channels_last=False, 
     if counts is not None:
         counts = _cuda(counts, torch.int32, "counts")
     out = torch.empty((B, K, D), dtype=torch.float32, device=desc.device)
+    if split:
+        if not channels_last or D not in (64, 128, 256):
+            raise NotImplementedError("sample_descriptors(split=True) needs a channels-last map with D in {64, 128, 256}")
+        sp = {'hi': torch.empty((B, K, D), dtype=torch.bfloat16, device=desc.device),
+              'mid': torch.empty((B, K, D), dtype=torch.bfloat16, device=desc.device),
+              'sq_norms': torch.empty((B, K), dtype=torch.float32, device=desc.device),
+              # the rows are unit-norm by construction (or zero): an upper bound of the largest norm, as float bits
+              'max_norm': torch.full((B,), 0x3F800008, dtype=torch.int32, device=desc.device)}   # 1.000001f
+        with torch.cuda.device(desc.device):
+            _lib.check(_lib.load().mp_sample_descriptors_split_f32(_ptr(keypoints), _ptr(counts), B, K, _ptr(desc), D, Hc, Wc, 1,
+                                                                   int(H), int(W), _ptr(out), _ptr(sp['hi']), _ptr(sp['mid']),
+                                                                   _ptr(sp['sq_norms']), _stream(desc)),
+                       "mp_sample_descriptors_split_f32")
+        return out, sp
     with torch.cuda.device(desc.device):
         _lib.check(_lib.load().mp_sample_descriptors_f32(_ptr(keypoints), _ptr(counts), B, K, _ptr(desc), D, Hc, Wc,
                                                          1 if channels_last else 0, int(H), int(W), _ptr(out),
@@ -222,8 +238,10 @@ def nearest(d1, d2, metric='nn', algo=None, n1=None, n2=None, want_scores=True):
     return dict(idx12=i12, idx21=i21, best12=outs[0], second12=outs[1], best21=outs[2], second21=outs[3])
 
 
-def match(d1, d2, metric='l2', algo=None, kind='mutual', cross_check=True, threshold=-1.0, ratio=0.9, n1=None, n2=None):
-    """Match lists for P pairs: query (P,N1), train (P,N1) int32, dist (P,N1) fp32, counts (P) int32."""
+def match(d1, d2, metric='l2', algo=None, kind='mutual', cross_check=True, threshold=-1.0, ratio=0.9, n1=None, n2=None,
+          split1=None, split2=None):
+    """Match lists for P pairs: query (P,N1), train (P,N1) int32, dist (P,N1) fp32, counts (P) int32.
+    split1 / split2: the operand dicts of ``sample_descriptors(split=True)`` for d1 / d2 (tensor path; no prep pass)."""
     d1, d2, n1, n2, P, N1, N2, D = _match_args(d1, d2, n1, n2)
     dev = d1.device
     algo = algo or default_algo(D)
@@ -234,6 +252,18 @@ def match(d1, d2, metric='l2', algo=None, kind='mutual', cross_check=True, thres
     lib = _lib.load()
     nbytes = lib.mp_match_workspace_bytes(P, N1, N2, D)
     ws = _ws(nbytes, dev)
+    if split1 is not None and split2 is not None and ALGO[algo] == 0:
+        for sp, N in ((split1, N1), (split2, N2)):
+            if tuple(sp['hi'].shape) != (P, N, D) or not (sp['hi'].is_contiguous() and sp['mid'].is_contiguous() and sp['sq_norms'].is_contiguous()):
+                raise ValueError("match: split operands must be contiguous (P,N,D) planes of the same descriptor sets")
+        with torch.cuda.device(dev):
+            _lib.check(lib.mp_match_split_f32(_ptr(d1), _ptr(split1['hi']), _ptr(split1['mid']), _ptr(split1['sq_norms']), _ptr(split1['max_norm']),
+                                              _ptr(n1), N1, _ptr(d2), _ptr(split2['hi']), _ptr(split2['mid']), _ptr(split2['sq_norms']),
+                                              _ptr(split2['max_norm']), _ptr(n2), N2, P, D, METRIC[metric],
+                                              {'mutual': 0, 'ratio': 1}[kind], int(bool(cross_check)), float(threshold), float(ratio),
+                                              _ptr(q), _ptr(t), _ptr(dist), _ptr(cnt), _ptr(ws), nbytes, _stream(d1)),
+                       "mp_match_split_f32")
+        return q, t, dist, cnt
     with torch.cuda.device(dev):
         _lib.check(lib.mp_match_f32(_ptr(d1), _ptr(n1), N1, _ptr(d2), _ptr(n2), N2, P, D, METRIC[metric], ALGO[algo],
                                     {'mutual': 0, 'ratio': 1}[kind], int(bool(cross_check)), float(threshold), float(ratio),

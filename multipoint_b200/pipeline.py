@@ -37,8 +37,16 @@ class KeypointPipeline:
         dense, kp, scores, counts = ops.box_nms(prob.reshape(B, H, W), self.nms, self.thr, iou=self.iou,
                                                 keep_top_k=self.topk, want_keypoints=True, kp_cap=self.topk,
                                                 want_dense=self.dense_nms_map)
-        desc = ops.sample_descriptors(kp, desc_nhwc, H, W, counts=counts, channels_last=True)
+        split = None
+        if raw_desc.shape[1] in (64, 128, 256):
+            # the sampler also writes the rows as the tensor-core matcher wants them (bf16 planes + squared norms):
+            # match() then needs no pass of its own over the descriptors
+            desc, split = ops.sample_descriptors(kp, desc_nhwc, H, W, counts=counts, channels_last=True, split=True)
+        else:
+            desc = ops.sample_descriptors(kp, desc_nhwc, H, W, counts=counts, channels_last=True)
         out = {'prob': prob, 'keypoints': kp, 'scores': scores, 'counts': counts, 'desc': desc}
+        if split is not None:
+            out.update(desc_hi=split['hi'], desc_mid=split['mid'], desc_sq_norms=split['sq_norms'], desc_max_norm=split['max_norm'])
         if dense is not None:
             out['prob_nms'] = dense.reshape(B, 1, H, W)
         return out
@@ -51,9 +59,13 @@ class KeypointPipeline:
 
     @torch.no_grad()
     def match(self, ext_a, ext_b):
+        def split_of(e):
+            if 'desc_hi' not in e:
+                return None
+            return {'hi': e['desc_hi'], 'mid': e['desc_mid'], 'sq_norms': e['desc_sq_norms'], 'max_norm': e['desc_max_norm']}
         q, t, d, c = ops.match(ext_a['desc'], ext_b['desc'], metric=self.metric, algo=self.algo, kind='mutual',
                                cross_check=self.cross_check, threshold=self.match_threshold,
-                               n1=ext_a['counts'], n2=ext_b['counts'])
+                               n1=ext_a['counts'], n2=ext_b['counts'], split1=split_of(ext_a), split2=split_of(ext_b))
         return {'query': q, 'train': t, 'distance': d, 'counts': c}
 
     def stream(self, host_batches, device):

@@ -117,9 +117,9 @@ def main():
             fl = 2.0 * N * N * D
             it = 20 if N <= 4096 else 5
             ms = timed(lambda: ops.match(A, Bm, metric='l2', algo='tensor', kind='mutual', cross_check=True), iters=it)
-            add("match bfmatcher crossCheck N=%d D=%d (prep+2xGEMM+recheck+select)" % (N, D), ms, flops=fl, executed_TFLOPs=round(6 * fl / ms / 1e9, 1))
+            add("match bfmatcher crossCheck N=%d D=%d (prep+GEMM+recheck+select)" % (N, D), ms, flops=fl, executed_TFLOPs=round(3 * fl / ms / 1e9, 1))
             ms = timed(lambda: ops.match(A, Bm, metric='nn', algo='tensor', kind='mutual', cross_check=True, threshold=0.7), iters=it)
-            add("match nnmatcher N=%d D=%d" % (N, D), ms, flops=fl, executed_TFLOPs=round(6 * fl / ms / 1e9, 1))
+            add("match nnmatcher N=%d D=%d" % (N, D), ms, flops=fl, executed_TFLOPs=round(3 * fl / ms / 1e9, 1))
             if N <= 4096:
                 ms = timed(lambda: ops.match(A, Bm, metric='l2', algo='simt', kind='mutual', cross_check=True), iters=3)
                 add("match bfmatcher SIMT reference N=%d D=%d" % (N, D), ms, flops=fl)
@@ -128,7 +128,7 @@ def main():
     b = torch.nn.functional.normalize(a[:, torch.randperm(2048, device=dev)] + 0.05 * torch.randn((64, 2048, 256), generator=g, device=dev) / 16, dim=2)
     fl = 2.0 * 64 * 2048 * 2048 * 256
     ms = timed(lambda: ops.match(a, b, metric='l2', algo='tensor', kind='mutual', cross_check=True))
-    add("match bfmatcher crossCheck 64 pairs x 2048 x 256", ms, flops=fl, executed_TFLOPs=round(6 * fl / ms / 1e9, 1))
+    add("match bfmatcher crossCheck 64 pairs x 2048 x 256", ms, flops=fl, executed_TFLOPs=round(3 * fl / ms / 1e9, 1))
 
     # config 4: homographic adaptation kernels, 100 homographies per image, one pair
     n, Bp = 99, 1
