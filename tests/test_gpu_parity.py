@@ -435,6 +435,35 @@ def test_column_side_equals_row_side_of_the_swapped_problem(ops):
                 assert float((ab["best21"][p, :k2] - ba["best12"][p, :k2]).abs().max()) < 1e-4
 
 
+def test_sampler_split_operands_equal_the_matchers_own_prep(ops):
+    """mp_sample_descriptors_split_f32 also writes the rows as the tensor-core matcher consumes them; matching from
+    those operands (mp_match_split_f32, what KeypointPipeline does) gives the same match list as mp_match_f32, which
+    splits the fp32 rows itself."""
+    g = torch.Generator(device="cuda").manual_seed(5)
+    for D in (64, 256):
+        B, K, Hc, Wc, H, W = 6, 700, 32, 40, 256, 320
+        desc = torch.nn.functional.normalize(torch.randn((B, Hc, Wc, D), generator=g, device="cuda"), dim=3)
+        kp = torch.stack([torch.randint(0, H, (B, K), generator=g, device="cuda"), torch.randint(0, W, (B, K), generator=g, device="cuda")], dim=2)
+        cnt = torch.tensor([700, 650, 0, 700, 33, 512], dtype=torch.int32, device="cuda")
+        plain = ops.sample_descriptors(kp, desc, H, W, counts=cnt, channels_last=True)
+        out, sp = ops.sample_descriptors(kp, desc, H, W, counts=cnt, channels_last=True, split=True)
+        assert torch.equal(out, plain)
+        hi = out.to(torch.bfloat16)
+        assert torch.equal(sp['hi'], hi) and torch.equal(sp['mid'], (out - hi.float()).to(torch.bfloat16))
+        torch.testing.assert_close(sp['sq_norms'], (out * out).sum(2), rtol=1e-6, atol=1e-7)
+        P = B // 2
+        half = lambda d, lo: {k: v[lo:lo + P] for k, v in d.items()}   # noqa: E731
+        for metric, thr in (("l2", -1.0), ("nn", 0.9)):
+            want = ops.match(out[:P], out[P:], metric=metric, kind='mutual', cross_check=True, threshold=thr, n1=cnt[:P], n2=cnt[P:])
+            got = ops.match(out[:P], out[P:], metric=metric, kind='mutual', cross_check=True, threshold=thr, n1=cnt[:P], n2=cnt[P:],
+                            split1=half(sp, 0), split2=half(sp, P))
+            assert torch.equal(got[3], want[3])
+            for p in range(P):
+                n = int(want[3][p])
+                assert torch.equal(got[0][p, :n], want[0][p, :n]) and torch.equal(got[1][p, :n], want[1][p, :n])
+                assert torch.equal(got[2][p, :n], want[2][p, :n])
+
+
 def test_get_matches_dropin(utils):
     import cv2
     g = load_golden("matching")
