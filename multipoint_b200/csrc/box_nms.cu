@@ -21,9 +21,10 @@
 //                        are written as -score and queued on a per-image worklist.
 //   2. nms_fixup_kernel  one CTA per image; resolves the worklist against the dense map in L2.
 //                        Exits immediately when the list is empty.
-//  sparse top-k path (keep_top_k > 0, the shipped configuration; see the comment above nms_candidates_kernel)
-//   1'. nms_candidates_kernel  streams the heatmap once: zero-fills the dense map, lists the candidates and
-//                        histograms their scores.
+//  sparse top-k path (keep_top_k > 0; the reference's shipped configs use topk: 0 = the dense path above; see the
+//  comment above nms_candidates_kernel)
+//   1'. nms_candidates_kernel  streams the heatmap once: lists the candidates and histograms their scores (and
+//                        zero-fills the dense map when the caller wants it).
 //   2'. nms_sparse2_kernel one CTA per image settles only the candidates that can reach the top k, cuts to k and emits.
 //  both
 //   3. nms_select_kernel one CTA per image; optional top-k by radix select on (score desc, index

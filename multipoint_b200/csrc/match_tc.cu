@@ -33,7 +33,6 @@
 namespace mp {
 
 constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 64;  // BK bf16 = one 128 B swizzle row
-constexpr int TC_ACC_STAGES = 4;                     // 4 x 128 fp32 columns = all 512 TMEM columns
 constexpr int TC_EPI_WARPS = 8;                      // two per TMEM lane quarter, alternating 32-column chunks
 constexpr int TC_THREADS = 32 * (2 + TC_EPI_WARPS);  // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
 constexpr uint32_t TC_TILE_BYTES = TC_BM * TC_BK * 2;  // 16 KB: one (128 x 64) bf16 block
@@ -55,15 +54,6 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
 }
 // A operand from tensor memory (cute SM100_MMA_F16BF16_TS)
 __device__ __forceinline__ void tc_mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
@@ -148,20 +138,19 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-// ATM = A operand in tensor memory: the CTA's 128 rows of A_hi / A_mid (D/2 32-bit columns each, two
+// The A operand lives in tensor memory: the CTA's 128 rows of A_hi / A_mid (D/2 32-bit columns each, two
 // bf16 per column, row r in TMEM lane r) are written once with tcgen05.st and every MMA reads A from
 // TMEM (tcgen05.mma ... [d], [a], b_desc).  Shared memory then only holds the B ring (six 32 KB
-// stages instead of three) and serves half the operand bytes per MMA: with both operands in shared
-// memory an M=128, N=128 MMA needs 8 KB per 64 cycles -- all of the 128 B/cycle an SM has -- on top
-// of the TMA fills.  TMEM: accumulators in columns [0, ACC*128), A in the last 64*KB columns.
-template <int KB, bool ATM>
+// stages) and serves half the operand bytes per MMA: with both operands in shared memory an M=128, N=128
+// MMA needs 8 KB per 64 cycles -- all of the 128 B/cycle an SM has -- on top of the TMA fills (that variant
+// was measured in round 1 and removed).  TMEM: accumulators in columns [0, ACC*128), A in the last 64*KB columns.
+template <int KB>
 struct TcSmem {
-    static constexpr int B_STAGES = ATM ? 6 : (KB >= 4 ? 3 : 4);
-    static constexpr int ACC_STAGES = ATM ? (512 - 64 * KB) / TC_BN : TC_ACC_STAGES;
-    static constexpr uint32_t A_COL0 = 512 - 64 * KB;   // ATM only
-    static constexpr uint32_t A_BYTES = ATM ? 0u : 2u * KB * TC_TILE_BYTES;
+    static constexpr int B_STAGES = 6;
+    static constexpr int ACC_STAGES = (512 - 64 * KB) / TC_BN;
+    static constexpr uint32_t A_COL0 = 512 - 64 * KB;
     static constexpr uint32_t B_STAGE_BYTES = 2u * TC_TILE_BYTES;
-    static constexpr uint32_t B_OFF = A_BYTES;
+    static constexpr uint32_t B_OFF = 0;
     static constexpr uint32_t BAR_OFF = B_OFF + B_STAGES * B_STAGE_BYTES;  // multiple of 1024
     static constexpr int NUM_BARS = 1 + 2 * B_STAGES + 2 * ACC_STAGES;
     static constexpr uint32_t BIAS_OFF = (BAR_OFF + NUM_BARS * 8 + 16 + 15) & ~15u;  // after the barriers and the tmem pointer
@@ -171,16 +160,15 @@ struct TcSmem {
     static constexpr uint32_t TOTAL = BIAS_OFF + BIAS_BYTES + 1024;        // + alignment slack
 };
 
-template <int KB, bool ATM, bool COLS, bool BIAS>
+template <int KB, bool COLS, bool BIAS>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 match_top2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_mid,
                      const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_mid,
-                     const __nv_bfloat16 *__restrict__ a_hi_ptr, const __nv_bfloat16 *__restrict__ a_mid_ptr,
                      const int32_t *__restrict__ na, int NA, const int32_t *__restrict__ nb, int NB,
                      const float *__restrict__ norms_a, const float *__restrict__ norms_b,
                      const unsigned *__restrict__ max_a, const unsigned *__restrict__ max_b, Top2 *__restrict__ top,
                      uint2 *__restrict__ colpart, int RC, int NBP) {
-    using L = TcSmem<KB, ATM>;
+    using L = TcSmem<KB>;
     constexpr int S = L::B_STAGES;
     constexpr int ACC = L::ACC_STAGES;
     extern __shared__ uint8_t smem_raw[];
@@ -197,7 +185,7 @@ match_top2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
     }
 
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // 128B swizzle needs 1024 B alignment
-    const uint32_t smem_a = base, smem_b = base + L::B_OFF, bars = base + L::BAR_OFF;
+    const uint32_t smem_b = base + L::B_OFF, bars = base + L::BAR_OFF;
     const uint32_t bar_a_full = bars;
     auto bar_b_full = [&](int s) { return bars + 8u * (1 + s); };
     auto bar_b_empty = [&](int s) { return bars + 8u * (1 + S + s); };
@@ -209,7 +197,7 @@ match_top2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
     const int n_tiles = (n_b + TC_BN - 1) / TC_BN;
 
     if (warp == 0 && lane == 0) {
-        mbar_init(bar_a_full, ATM ? TC_EPI_WARPS : 1);
+        mbar_init(bar_a_full, TC_EPI_WARPS);
         for (int s = 0; s < S; ++s) { mbar_init(bar_b_full(s), 1); mbar_init(bar_b_empty(s), 1); }
         for (int t = 0; t < ACC; ++t) { mbar_init(bar_acc_full(t), 1); mbar_init(bar_acc_empty(t), TC_EPI_WARPS); }
         mbar_fence_init();
@@ -226,24 +214,15 @@ match_top2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (elect_one()) {
-            if (!ATM) {
-                mbar_expect_tx(bar_a_full, L::A_BYTES);
-                for (int kb = 0; kb < KB; ++kb) {
-                    tma_load_3d(smem_a + (0 * KB + kb) * TC_TILE_BYTES, &map_a_hi, bar_a_full, kb * TC_BK, m0, p);
-                    tma_load_3d(smem_a + (1 * KB + kb) * TC_TILE_BYTES, &map_a_mid, bar_a_full, kb * TC_BK, m0, p);
-                }
-            }
             int it = 0;
-            if (ATM) {
-                // ring items 0..KB-1 are this CTA's own rows of A (hi + mid block per k-block, the same 32 KB stage
-                // layout as B): the epilogue warps move them from shared to tensor memory.  Pulling A in with
-                // per-thread global loads took 6 us per CTA (43 us per launch) in front of the first MMA.
-                for (int kb = 0; kb < KB; ++kb, ++it) {
-                    mbar_expect_tx(bar_b_full(kb), L::B_STAGE_BYTES);
-                    const uint32_t dst = smem_b + kb * L::B_STAGE_BYTES;
-                    tma_load_3d(dst, &map_a_hi, bar_b_full(kb), kb * TC_BK, m0, p);
-                    tma_load_3d(dst + TC_TILE_BYTES, &map_a_mid, bar_b_full(kb), kb * TC_BK, m0, p);
-                }
+            // ring items 0..KB-1 are this CTA's own rows of A (hi + mid block per k-block, the same 32 KB stage
+            // layout as B): the epilogue warps move them from shared to tensor memory.  Pulling A in with
+            // per-thread global loads took 6 us per CTA (43 us per launch) in front of the first MMA.
+            for (int kb = 0; kb < KB; ++kb, ++it) {
+                mbar_expect_tx(bar_b_full(kb), L::B_STAGE_BYTES);
+                const uint32_t dst = smem_b + kb * L::B_STAGE_BYTES;
+                tma_load_3d(dst, &map_a_hi, bar_b_full(kb), kb * TC_BK, m0, p);
+                tma_load_3d(dst + TC_TILE_BYTES, &map_a_mid, bar_b_full(kb), kb * TC_BK, m0, p);
             }
             for (int nt = 0; nt < n_tiles; ++nt) {
                 for (int kb = 0; kb < KB; ++kb, ++it) {
@@ -263,9 +242,8 @@ match_top2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
             mbar_wait(bar_a_full, 0);
             tc_fence_after();
             int it = 0;
-            if (ATM) {  // A has left the ring stages it arrived in: hand them back to the producer
-                for (int kb = 0; kb < KB; ++kb, ++it) mbar_arrive(bar_b_empty(kb));
-            }
+            // A has left the ring stages it arrived in: hand them back to the producer
+            for (int kb = 0; kb < KB; ++kb, ++it) mbar_arrive(bar_b_empty(kb));
             for (int nt = 0; nt < n_tiles; ++nt) {
                 const int t = nt % ACC;
                 mbar_wait(bar_acc_empty(t), ((nt / ACC) & 1) ^ 1);
@@ -280,20 +258,12 @@ match_top2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
                     for (int k = 0; k < TC_BK / 16; ++k) {
                         const uint32_t ko = k * 32;  // 16 bf16 = 32 B inside the 128 B swizzle row
                         const uint64_t db_hi = umma_desc_sw128(b_hi + ko), db_mid = umma_desc_sw128(b_mid + ko);
-                        if (ATM) {
-                            // 16 bf16 of a row = 8 TMEM columns; plane offset 32*KB columns
-                            const uint32_t ta_hi = tmem_base + L::A_COL0 + (uint32_t)(kb * 32 + k * 8);
-                            const uint32_t ta_mid = ta_hi + 32u * KB;
-                            tc_mma_f16_ts(d_tmem, ta_mid, db_hi, idesc, (kb | k) != 0);  // small terms first
-                            tc_mma_f16_ts(d_tmem, ta_hi, db_mid, idesc, 1);
-                            tc_mma_f16_ts(d_tmem, ta_hi, db_hi, idesc, 1);
-                        } else {
-                            const uint32_t a_hi = smem_a + (0 * KB + kb) * TC_TILE_BYTES, a_mid = smem_a + (1 * KB + kb) * TC_TILE_BYTES;
-                            const uint64_t da_hi = umma_desc_sw128(a_hi + ko), da_mid = umma_desc_sw128(a_mid + ko);
-                            tc_mma_f16(d_tmem, da_mid, db_hi, idesc, (kb | k) != 0);  // small terms first
-                            tc_mma_f16(d_tmem, da_hi, db_mid, idesc, 1);
-                            tc_mma_f16(d_tmem, da_hi, db_hi, idesc, 1);
-                        }
+                        // 16 bf16 of a row = 8 TMEM columns; plane offset 32*KB columns
+                        const uint32_t ta_hi = tmem_base + L::A_COL0 + (uint32_t)(kb * 32 + k * 8);
+                        const uint32_t ta_mid = ta_hi + 32u * KB;
+                        tc_mma_f16_ts(d_tmem, ta_mid, db_hi, idesc, (kb | k) != 0);  // small terms first
+                        tc_mma_f16_ts(d_tmem, ta_hi, db_mid, idesc, 1);
+                        tc_mma_f16_ts(d_tmem, ta_hi, db_hi, idesc, 1);
                     }
                     tc_commit(bar_b_empty(s));  // smem stage free once these MMAs have read it
                 }
@@ -301,18 +271,17 @@ match_top2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
             }
         }
     } else {
-        // ===================== epilogue: running arg-top-2 per row =====================
-        // Keys are made positive (key + C > 0) so their fp32 bit patterns order like unsigned
-        // integers, and the column's position inside its 32-column chunk replaces the 5 lowest
-        // mantissa bits: one integer max then carries value and index together.  Truncation costs
-        // 2^-18 relative (included in MATCH_EPS_TENSOR); equal packed keys prefer the lower column.
+        // ===================== epilogue: running arg-top-3 per row, nearest row per column =====================
+        // Every accumulator value becomes one 32-bit integer key (match_internal.cuh: KeyScale) whose low 5 bits are the
+        // column's position inside its 32-column chunk (row side) or the row's inside its 32-row chunk (column side):
+        // one integer max then carries value and index together; equal keys prefer the lower index.
         // Two warps share each TMEM lane quarter and take alternate chunks, so every scheduler has
         // two epilogue warps to hide the tcgen05.ld latency (with one, ncu showed 3.4 stall cycles
         // per issued instruction and the epilogue, not the MMAs, set the tile time).
         const int quarter = warp & 3;  // TMEM lane quarter this warp may access
         const int half = (warp - 2) >> 2;
         const int row = quarter * 32 + lane;
-        if (ATM) {
+        {
             // stage this CTA's rows of A into tensor memory: warps with half 0 write the hi plane,
             // half 1 the mid plane; each thread owns one row (= one TMEM lane)
             const uint32_t col = L::A_COL0 + (uint32_t)(half * 32 * KB);
@@ -571,15 +540,15 @@ match_colmerge_kernel(const uint2 *__restrict__ colpart, int RC, int NBP, const 
     top_cols[(size_t)p * NB + j] = out;
 }
 
-template <int KB, bool ATM, bool COLS, bool BIAS>
+template <int KB, bool COLS, bool BIAS>
 static int launch_tc(const CUtensorMap &ah, const CUtensorMap &am, const CUtensorMap &bh, const CUtensorMap &bm,
                      const __nv_bfloat16 *a_hi, const __nv_bfloat16 *a_mid, const int32_t *na, int NA,
                      const int32_t *nb, int NB, int P, const float *norms_a, const float *norms_b,
                      const unsigned *max_a, const unsigned *max_b, Top2 *top, uint2 *colpart, int RC, int NBP, cudaStream_t s) {
-    auto k = match_top2_tc_kernel<KB, ATM, COLS, BIAS>;
-    MP_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcSmem<KB, ATM>::TOTAL));
+    auto k = match_top2_tc_kernel<KB, COLS, BIAS>;
+    MP_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcSmem<KB>::TOTAL));
     dim3 grid((NA + TC_BM - 1) / TC_BM, P);
-    k<<<grid, TC_THREADS, TcSmem<KB, ATM>::TOTAL, s>>>(ah, am, bh, bm, a_hi, a_mid, na, NA, nb, NB, norms_a, norms_b,
+    k<<<grid, TC_THREADS, TcSmem<KB>::TOTAL, s>>>(ah, am, bh, bm, na, NA, nb, NB, norms_a, norms_b,
                                                         max_a, max_b, top, colpart, RC, NBP);
     MP_LAUNCH_OK_S("match_top2_tc_kernel", s);
     return MP_OK;
@@ -613,8 +582,8 @@ int match_top2_tensor(const __nv_bfloat16 *a_hi, const __nv_bfloat16 *a_mid, con
     }
 #define MP_TC_ARGS ah, am, bh, bm, a_hi, a_mid, na, NA, nb, NB, P, norms_a, norms_b, max_a, max_b, top, cp, RC, NBP, stream
 #define MP_TC_LAUNCH(KB)                                                                             \
-    rc = cols ? (use_bias ? launch_tc<KB, true, true, true>(MP_TC_ARGS) : launch_tc<KB, true, true, false>(MP_TC_ARGS))     \
-              : (use_bias ? launch_tc<KB, true, false, true>(MP_TC_ARGS) : launch_tc<KB, true, false, false>(MP_TC_ARGS));  \
+    rc = cols ? (use_bias ? launch_tc<KB, true, true>(MP_TC_ARGS) : launch_tc<KB, true, false>(MP_TC_ARGS))     \
+              : (use_bias ? launch_tc<KB, false, true>(MP_TC_ARGS) : launch_tc<KB, false, false>(MP_TC_ARGS));  \
     break
     switch (D / 64) {
         case 1: MP_TC_LAUNCH(1);
