@@ -877,10 +877,10 @@ __device__ void emit_from_bitmap(const uint32_t *bitmap, int words, int W, const
 //     in one CTA, so no apron and no fix-up; candidate bitmap, ranks and signed state all in shared
 //     memory -- lowers the threshold and repeats while fewer than k survive, then cuts to k and
 //     emits the keypoints in row-major order itself (nms_select_kernel only serves redone images).
-// An image that does not fit (more than SP_CAND_CAP candidates, or more than SP2_CAP needed)
+// An image that does not fit (a chunk with more than SP_SEG_CAP candidates, or more than SP2_CAP needed)
 // raises its flag and is redone by the tile + fix-up kernels, which otherwise exit at once.
 constexpr int SP_BINS = 128;
-constexpr int SP_CAND_CAP = 1 << 16;  // candidates listed per image
+constexpr int SP_SEG_CAP = 1536;      // candidates listed per SP_CHUNK pixels (37.5 %); a denser chunk sends the image to the tile kernels
 constexpr int SP_CHUNK = 4096;        // pixels per CTA of the candidates kernel
 constexpr int SP_PAD = 3;             // footprint reach handled here
 
@@ -891,15 +891,16 @@ __device__ __forceinline__ int sp_bin(uint32_t bits) {  // monotone in the (posi
 template <bool VEC, bool ZERO>   // ZERO: also zero-fill the dense output map (only when the caller asked for it)
 __global__ void __launch_bounds__(NMS_THREADS)  // 71 registers, 3 CTAs/SM; capping at 48 (5 CTAs/SM) measured the same 81 us
 nms_candidates_kernel(const float *__restrict__ prob, float *__restrict__ out, int W, int HW, float thr,
-                      uint2 *__restrict__ cands, int *__restrict__ cand_count, int *__restrict__ hist) {
+                      uint2 *__restrict__ cands, int *__restrict__ seg_count, int *__restrict__ hist) {
     // One histogram per warp: the scores cluster in a few bins just above the threshold, and a single shared histogram
-    // serialised its atomics there (ncu: 465 k bank conflicts per launch).  One global atomic per CTA reserves its run
-    // of the image's candidate list (per-warp reservations were measured at 109 us against 65: the L2 serialises the
-    // 640 atomics an image then sends to one address).  List entry: (pixel index, score bits) -- splitting the index
-    // into (y, x) here costs a division per candidate (86 us against 65); the sparse kernel does it for the admitted 8 %.
+    // serialised its atomics there (ncu: 465 k bank conflicts per launch).  Every CTA owns a fixed segment of the
+    // image's candidate list and stores its count: reserving a run of one shared list with a returning atomic put an L2
+    // round trip into every CTA's critical path (per-warp reservations were even measured at 109 us against 65: the L2
+    // serialises the 640 atomics an image then sends to one address).  List entry: (pixel index, score bits) --
+    // splitting the index into (y, x) here costs a division per candidate (86 us against 65); the sparse kernel does it
+    // for the admitted 8 %.
     __shared__ int sh_hist[NMS_THREADS / 32][SP_BINS];
     __shared__ int warp_sums[NMS_THREADS / 32];
-    __shared__ int sh_base;
     const int b = blockIdx.y, tid = threadIdx.x;
     const int p0 = blockIdx.x * SP_CHUNK;
     const float *img = prob + (size_t)b * HW;
@@ -927,28 +928,43 @@ nms_candidates_kernel(const float *__restrict__ prob, float *__restrict__ out, i
         }
     }
     __syncthreads();
-    int mine = 0;
-    int *my_hist = sh_hist[tid >> 5];
+    // Warp-cooperative compaction (the per-thread count / block scan / branchy second pass it replaces made the kernel
+    // instruction-bound: 38 instructions per pixel, issue active 78 %, DRAM 35 %): one ballot per pixel slot gives every
+    // lane the warp's candidate pattern, a popcount its position.
+    const int lane = tid & 31, warp = tid >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    int *my_hist = sh_hist[warp];
+    uint32_t bal[PER];
+    int wtotal = 0;
 #pragma unroll
-    for (int k = 0; k < PER; ++k)
-        if (v[k] > thr) {  // strict, fp32 (utils.py:97); NaN is not a candidate
-            ++mine;
-            atomicAdd(&my_hist[sp_bin(__float_as_uint(v[k]))], 1);
-        }
-    int total;
-    const int off = block_exclusive_scan(mine, warp_sums, total);
-    if (tid == 0) sh_base = total ? atomicAdd(cand_count + b, total) : 0;
+    for (int k = 0; k < PER; ++k) {
+        const bool c = v[k] > thr;  // strict, fp32 (utils.py:97); NaN is not a candidate
+        bal[k] = __ballot_sync(0xffffffffu, c);
+        wtotal += __popc(bal[k]);
+        if (c) atomicAdd(&my_hist[sp_bin(__float_as_uint(v[k]))], 1);
+    }
+    if (lane == 0) warp_sums[warp] = wtotal;
     __syncthreads();
-    if (mine) {
-        int slot = sh_base + off;
-        uint2 *list = cands + (size_t)b * SP_CAND_CAP;
+    int run = 0, total = 0;
 #pragma unroll
-        for (int k = 0; k < PER; ++k)
-            if (v[k] > thr) {
+    for (int w = 0; w < NMS_THREADS / 32; ++w) {
+        const int t = warp_sums[w];
+        if (w < warp) run += t;
+        total += t;
+    }
+    if (tid == 0) seg_count[(size_t)b * gridDim.x + blockIdx.x] = total;   // may exceed SP_SEG_CAP: the sparse kernel then gives the image up
+    if (wtotal) {
+        uint2 *list = cands + ((size_t)b * gridDim.x + blockIdx.x) * SP_SEG_CAP;
+#pragma unroll
+        for (int k = 0; k < PER; ++k) {
+            const uint32_t bk = bal[k];
+            if (bk & (1u << lane)) {
+                const int slot = run + __popc(bk & lt_mask);
                 const int i = VEC ? p0 + 4 * (tid + (k >> 2) * NMS_THREADS) + (k & 3) : p0 + tid + k * NMS_THREADS;
-                if (slot < SP_CAND_CAP) list[slot] = make_uint2((uint32_t)i, __float_as_uint(v[k]));
-                ++slot;
+                if (slot < SP_SEG_CAP) list[slot] = make_uint2((uint32_t)i, __float_as_uint(v[k]));
             }
+            run += __popc(bk);
+        }
     }
     if (tid < SP_BINS) {
         int t = 0;
@@ -1017,7 +1033,7 @@ struct Sp2Layout {
 
 __global__ void __launch_bounds__(1024, 1)
 nms_sparse2_kernel(const float *__restrict__ prob, float *__restrict__ dense, int H, int W, int keep_top_k, const NmsFootprint fp,
-                   const uint2 *__restrict__ cands, const int *__restrict__ cand_count, const int *__restrict__ hist,
+                   const uint2 *__restrict__ cands, const int *__restrict__ seg_count, const int *__restrict__ hist,
                    int64_t *__restrict__ keypoints, float *__restrict__ kp_scores, int32_t *__restrict__ kp_counts, int kp_cap,
                    int *__restrict__ surv_count, int *__restrict__ redo_flags) {
     extern __shared__ __align__(16) uint8_t sp_smem[];
@@ -1037,12 +1053,17 @@ nms_sparse2_kernel(const float *__restrict__ prob, float *__restrict__ dense, in
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.x;
     const float *img = prob + (size_t)b * H * W;
-    const int n_all = cand_count[b];
-    if (n_all > SP_CAND_CAP) {  // list truncated: the dense kernels redo this image (block-uniform)
-        if (tid == 0) { redo_flags[b] = 1; surv_count[b] = 0; }
-        return;
+    const int nseg = (H * W + SP_CHUNK - 1) / SP_CHUNK;
+    const int *segc = seg_count + (size_t)b * nseg;
+    const uint2 *list = cands + (size_t)b * nseg * SP_SEG_CAP;
+    {
+        bool over = false;
+        for (int sg = tid; sg < nseg; sg += 1024) over |= segc[sg] > SP_SEG_CAP;
+        if (__syncthreads_or(over)) {  // a chunk's list is truncated: the dense kernels redo this image (block-uniform)
+            if (tid == 0) { redo_flags[b] = 1; surv_count[b] = 0; }
+            return;
+        }
     }
-    const uint2 *list = cands + (size_t)b * SP_CAND_CAP;
     if (tid < SP_BINS) sh_hist[tid] = hist[b * SP_BINS + tid];
     if (tid < 7) {
         const int dy = tid - SP_PAD;
@@ -1091,27 +1112,32 @@ nms_sparse2_kernel(const float *__restrict__ prob, float *__restrict__ dense, in
             if (tid == 0) { redo_flags[b] = 1; surv_count[b] = 0; }
             return;
         }
-        // ---- pass 1 over the whole candidate list: set the bitmap bit of every admitted candidate (eight loads in flight)
+        // ---- pass 1 over the candidate lists (a warp per chunk segment, eight loads per lane in flight): set the bitmap bit
+        //      of every admitted candidate
         constexpr int SCAN = 8;
-        for (int i0 = 0; i0 < n_all; i0 += 1024 * SCAN) {
-            uint2 c[SCAN];
+        for (int sg = warp; sg < nseg; sg += 32) {
+            const int n = segc[sg];
+            const uint2 *seg = list + (size_t)sg * SP_SEG_CAP;
+            for (int i0 = 0; i0 < n; i0 += 32 * SCAN) {
+                uint2 c[SCAN];
 #pragma unroll
-            for (int u = 0; u < SCAN; ++u) {
-                const int i = i0 + u * 1024 + tid;
-                c[u] = i < n_all ? __ldg(list + i) : make_uint2(0u, 0u);
-            }
-#pragma unroll
-            for (int u = 0; u < SCAN; ++u)
-                if ((i0 + u * 1024 + tid) < n_all && sp_bin(c[u].y) >= tb) {
-                    // pixel index -> (y, x) without an integer division: H * W < 2^24 here (the bitmap fits shared memory),
-                    // so the float quotient is within one of the row and two compares settle it
-                    const int e = (int)c[u].x;
-                    int y = (int)((float)e * inv_w);
-                    y -= (y * W > e) ? 1 : 0;
-                    y += ((y + 1) * W <= e) ? 1 : 0;
-                    const int x = e - y * W;
-                    atomicOr(&bm[(y + SP_PAD) * BWR + ((x + 32) >> 5)], 1u << ((x + 32) & 31));
+                for (int u = 0; u < SCAN; ++u) {
+                    const int i = i0 + u * 32 + lane;
+                    c[u] = i < n ? __ldg(seg + i) : make_uint2(0u, 0u);
                 }
+#pragma unroll
+                for (int u = 0; u < SCAN; ++u)
+                    if ((i0 + u * 32 + lane) < n && sp_bin(c[u].y) >= tb) {
+                        // pixel index -> (y, x) without an integer division: H * W < 2^24 here (the bitmap fits shared memory),
+                        // so the float quotient is within one of the row and two compares settle it
+                        const int e = (int)c[u].x;
+                        int y = (int)((float)e * inv_w);
+                        y -= (y * W > e) ? 1 : 0;
+                        y += ((y + 1) * W <= e) ? 1 : 0;
+                        const int x = e - y * W;
+                        atomicOr(&bm[(y + SP_PAD) * BWR + ((x + 32) >> 5)], 1u << ((x + 32) & 31));
+                    }
+            }
         }
         __syncthreads();
         // ---- ranks: candidates before each bitmap word (row-major), then id -> (pixel, -score)
@@ -1453,15 +1479,17 @@ static bool footprint_hit(double size, double iou, int dy, int dx) {
 
 struct NmsLayout {
     int cap, words;
-    size_t survivors, worklist, counts, counts_bytes, bitmaps, cands, dense_scratch, total;
+    size_t survivors, worklist, counts, counts_bytes, bitmaps, cands, segcnt, dense_scratch, total;
     NmsLayout(int B, int H, int W) {
         cap = H * W;
         words = (H * W + 31) / 32;
         size_t off = 0;
-        // ints: surv_count[B] work_count[B] cand_count[B] redo_flags[B] hist[B][SP_BINS]
+        // ints: surv_count[B] work_count[B] (unused)[B] redo_flags[B] hist[B][SP_BINS]; seg_count[B][nseg] lives with the lists
         counts_bytes = sizeof(int) * (4 + SP_BINS) * (size_t)B;
         counts = off;    off = align_up(off + counts_bytes, 256);
-        cands = off;     off = align_up(off + sizeof(uint2) * (size_t)B * SP_CAND_CAP, 256);
+        const size_t nseg = ((size_t)H * W + SP_CHUNK - 1) / SP_CHUNK;
+        segcnt = off;    off = align_up(off + sizeof(int) * (size_t)B * nseg, 256);
+        cands = off;     off = align_up(off + sizeof(uint2) * (size_t)B * nseg * SP_SEG_CAP, 256);
         survivors = off; off = align_up(off + sizeof(uint2) * (size_t)B * cap, 256);
         worklist = off;  off = align_up(off + sizeof(uint32_t) * (size_t)B * cap, 256);
         bitmaps = off;   off = align_up(off + sizeof(uint32_t) * (size_t)B * words, 256);
@@ -1597,7 +1625,7 @@ extern "C" int mp_box_nms_f32(const float *prob, int B, int H, int W, double siz
     uint32_t *bitmaps = (uint32_t *)(ws + L.bitmaps);
     cudaStream_t s = (cudaStream_t)stream;
     MP_CUDA_OK(cudaMemsetAsync(counts, 0, L.counts_bytes, s));
-    int *cand_count = counts + 2 * B, *redo_flags = counts + 3 * B, *hist = counts + 4 * B;
+    int *seg_count = (int *)(ws + L.segcnt), *redo_flags = counts + 3 * B, *hist = counts + 4 * B;
     uint2 *cands = (uint2 *)(ws + L.cands);
 
     const float thr = (float)min_prob;
@@ -1616,13 +1644,13 @@ extern "C" int mp_box_nms_f32(const float *prob, int B, int H, int W, double siz
         dim3 cgrid((unsigned)((HW + SP_CHUNK - 1) / SP_CHUNK), (unsigned)B);
         const bool cvec = (HW % 4 == 0) && (((uintptr_t)prob & 15) == 0) && (((uintptr_t)prob_nms & 15) == 0);
         // the dense map is zero-filled only when the caller asked for it: the sparse kernel keeps its state in shared memory
-        if (cvec && want_dense) nms_candidates_kernel<true, true><<<cgrid, NMS_THREADS, 0, s>>>(prob, prob_nms, W, HW, thr, cands, cand_count, hist);
-        else if (cvec) nms_candidates_kernel<true, false><<<cgrid, NMS_THREADS, 0, s>>>(prob, prob_nms, W, HW, thr, cands, cand_count, hist);
-        else if (want_dense) nms_candidates_kernel<false, true><<<cgrid, NMS_THREADS, 0, s>>>(prob, prob_nms, W, HW, thr, cands, cand_count, hist);
-        else nms_candidates_kernel<false, false><<<cgrid, NMS_THREADS, 0, s>>>(prob, prob_nms, W, HW, thr, cands, cand_count, hist);
+        if (cvec && want_dense) nms_candidates_kernel<true, true><<<cgrid, NMS_THREADS, 0, s>>>(prob, prob_nms, W, HW, thr, cands, seg_count, hist);
+        else if (cvec) nms_candidates_kernel<true, false><<<cgrid, NMS_THREADS, 0, s>>>(prob, prob_nms, W, HW, thr, cands, seg_count, hist);
+        else if (want_dense) nms_candidates_kernel<false, true><<<cgrid, NMS_THREADS, 0, s>>>(prob, prob_nms, W, HW, thr, cands, seg_count, hist);
+        else nms_candidates_kernel<false, false><<<cgrid, NMS_THREADS, 0, s>>>(prob, prob_nms, W, HW, thr, cands, seg_count, hist);
         MP_LAUNCH_OK_S("nms_candidates_kernel", s);
         MP_CUDA_OK(cudaFuncSetAttribute(nms_sparse2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp_smem));
-        nms_sparse2_kernel<<<B, 1024, sp_smem, s>>>(prob, want_dense ? prob_nms : nullptr, H, W, keep_top_k, fp, cands, cand_count, hist,
+        nms_sparse2_kernel<<<B, 1024, sp_smem, s>>>(prob, want_dense ? prob_nms : nullptr, H, W, keep_top_k, fp, cands, seg_count, hist,
                                                     keypoints, kp_scores, kp_counts, kp_cap, surv_count, redo_flags);
         MP_LAUNCH_OK_S("nms_sparse_kernel", s);
         only_flagged = redo_flags;  // the dense kernels below only redo images the sparse path gave up on
