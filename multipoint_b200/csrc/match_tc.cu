@@ -381,11 +381,20 @@ match_top2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
             if (second != old_second) second_chunk = (second == old_best && best != old_best) ? best_chunk : chunk;
             if (best != old_best) best_chunk = chunk;
         };
+        // the raw |b_j|^2 of the two columns this lane stages for tile nt; the -|b_j|^2/2 + C arithmetic happens when the
+        // value is stored a tile later (next to the load it would wait for the whole global-memory latency)
         auto fetch_terms = [&](int nt, float &a0, float &a1) {
             const int ca = nt * TC_BN + half * 32 + lane, cb_ = ca + 64;
             a0 = 0.f; a1 = 0.f;
-            if (ca < n_b) a0 = BIAS ? fmaf(-0.5f, __ldg(bias + ca), kr.C) : kr.C;
-            if (cb_ < n_b) a1 = BIAS ? fmaf(-0.5f, __ldg(bias + cb_), kr.C) : kr.C;
+            if (BIAS) {
+                if (ca < n_b) a0 = __ldg(bias + ca);
+                if (cb_ < n_b) a1 = __ldg(bias + cb_);
+            }
+        };
+        auto store_terms = [&](int nt, float a0, float a1, float *dst) {
+            const int ca = nt * TC_BN + half * 32 + lane, cb_ = ca + 64;
+            dst[lane] = ca < n_b ? (BIAS ? fmaf(-0.5f, a0, kr.C) : kr.C) : 0.f;
+            dst[32 + lane] = cb_ < n_b ? (BIAS ? fmaf(-0.5f, a1, kr.C) : kr.C) : 0.f;
         };
         // Software pipeline over the 2 * n_tiles chunks of this warp: the tcgen05.ld of chunk s+1 is in flight while chunk s
         // is processed (tcgen05.wait::ld waits for every outstanding load, so it is issued right after the wait for chunk s).
@@ -394,7 +403,7 @@ match_top2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
         uint32_t va[32], vb[32];
         float a0n, a1n;
         fetch_terms(0, a0n, a1n);
-        sbias[lane] = a0n; sbias[32 + lane] = a1n;
+        store_terms(0, a0n, a1n, sbias);
         if (n_tiles > 1) fetch_terms(1, a0n, a1n);
         mbar_wait(bar_acc_full(0), 0);
         tc_fence_after();
@@ -414,8 +423,7 @@ match_top2_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_acc_empty(t));
             if (nt + 1 < n_tiles) {
-                float *dst = sbias + ((nt + 1) & 1) * 64;      // last read two tiles ago
-                dst[lane] = a0n; dst[32 + lane] = a1n;
+                store_terms(nt + 1, a0n, a1n, sbias + ((nt + 1) & 1) * 64);      // last read two tiles ago
                 if (nt + 2 < n_tiles) fetch_terms(nt + 2, a0n, a1n);
                 const int t1 = (nt + 1) % ACC;
                 mbar_wait(bar_acc_full(t1), ((nt + 1) / ACC) & 1);
