@@ -192,6 +192,16 @@ MP_API int mp_match_threshold_f32(const float *d1, int N1, const float *d2, int 
 MP_API int mp_warp_f32(const float *src, int N, int n_mats, int H, int W, const float *A,
                        const float *xs, const float *ys, int mode, int padding, float *out,
                        mp_stream_t stream);
+/* The same warp with the N planes split into N / group groups that each get their own output block:
+ * out (N / group, n_mats, group, H, W).  The adaptation of an image PAIR warps both spectra by the same matrices
+ * (homographies.py:86 with the `H` of :81 for the optical and the thermal batch): one call with group = B shares the
+ * per-pixel coordinate arithmetic between them and still hands each network a contiguous (n_mats * B, 1, H, W) batch.
+ * With four or more matrices in bilinear mode the planes are first copied into a block-linear CUDA array owned by the
+ * library (one per device, stream and width, kept for the life of the process) and interior footprints are fetched
+ * with one tex2Dgather each; the values and the blend are the direct path's, bit for bit. */
+MP_API int mp_warp_groups_f32(const float *src, int N, int group, int n_mats, int H, int W, const float *A,
+                              const float *xs, const float *ys, int mode, int padding, float *out,
+                              mp_stream_t stream);
 
 /* mp_ha_aggregate_f32 = the unwarp + accumulate + finish of homographic_adaptation (:162-187)
  * and homographic_adaptation_multispectral (:77-126) over n pre-computed samples:

@@ -39,6 +39,7 @@ SIGNATURES = {
                                 _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "mp_match_threshold_f32": (_i, [_vp, _i, _vp, _i, _i, _d, _vp, _vp, _vp, _i64, _c.POINTER(_i64), _vp, _sz, _vp]),
     "mp_warp_f32": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _vp]),
+    "mp_warp_groups_f32": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _vp]),
     "mp_valid_mask_u8": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "mp_warp_keypoints_i64": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
     "mp_points_min_dist2_i64": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),

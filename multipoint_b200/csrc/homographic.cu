@@ -20,6 +20,9 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
+#include <vector>
+
 #include "mp_common.cuh"
 #include "mp_tma.cuh"
 
@@ -97,9 +100,17 @@ __device__ __forceinline__ void patch_pixel(int &x, int &y) {
     y = blockIdx.y * 8 + (w >> 2) * 4 + (l >> 3);
 }
 
-// grid (ceil(W/32), ceil(H/8), n_mats); each thread one destination pixel, all N planes
-__global__ void __launch_bounds__(256)
-warp_kernel(const float *__restrict__ src, int N, int H, int W, const float *__restrict__ A,
+// grid (ceil(W/32), ceil(H/8), n_mats); each thread one destination pixel, all N planes.
+// GATHER: the N source planes also sit, stacked vertically, in a block-linear CUDA array, and the four taps of an
+// interior pixel come back from ONE tex2Dgather (texels (x0,y0+1), (x1,y0+1), (x1,y0), (x0,y0) in .x .y .z .w, measured
+// by tools/microbench/tex_gather.cu) fetched at the corner the four texels share -- half a texel away from every
+// footprint boundary, so the unit's fixed-point coordinate rounding cannot pick another footprint.  The values are the
+// stored fp32 texels (point sampling, no filtering hardware in the arithmetic); the blend is the same un-fused
+// sequence, so the result is bit-identical to the direct path.  Four separate gathers of a rotated 8 x 4 patch cost
+// ~30 L1 wavefronts per warp and plane, the texture unit 16 cycles (microbenchmark: 230 -> 119 us for 198 planes).
+template <bool GATHER>
+__global__ void __launch_bounds__(256, GATHER ? 5 : 6)
+warp_kernel(const float *__restrict__ src, cudaTextureObject_t tex, int N, int G, int H, int W, const float *__restrict__ A,
             const float *__restrict__ xs, const float *__restrict__ ys, int mode, int padding,
             float *__restrict__ out) {
     __shared__ float As[9];
@@ -113,19 +124,99 @@ warp_kernel(const float *__restrict__ src, int N, int H, int W, const float *__r
     src_coord(As, xs[x], ys[y], W, H, ix, iy);
     if (padding == MP_PAD_REFLECTION) { ix = reflect_coord(ix, W); iy = reflect_coord(iy, H); }
     const size_t HW = (size_t)H * W;
-    float *o = out + (size_t)m * N * HW + (size_t)y * W + x;
+    // plane n = group n / G, member n % G; out (N / G, n_mats, G, H, W): every group gets its own (n_mats, G, H, W) block.
+    // One flat loop over the planes; the output pointer jumps to the next group's block after every G planes.
+    float *o = out + (size_t)m * G * HW + (size_t)y * W + x;
+    const size_t group_jump = ((size_t)gridDim.z - 1) * G * HW;   // from the end of one group's G planes to the next group's first
+    int k = G;
     if (mode == MP_NEAREST) {
         const float rx = rintf(ix), ry = rintf(iy);
         const bool ok = rx >= 0.f && rx < (float)W && ry >= 0.f && ry < (float)H;
-        const int off = ok ? (int)ry * W + (int)rx : 0;
-        for (int n = 0; n < N; ++n) o[n * HW] = ok ? __ldg(src + n * HW + off) : 0.f;
+        const float *pl = src + (ok ? (int)ry * W + (int)rx : 0);
+        for (int n = 0; n < N; ++n, pl += HW, o += HW) {
+            *o = ok ? __ldg(pl) : 0.f;
+            if (--k == 0) { k = G; o += group_jump; }
+        }
     } else {
         const Bilinear q = bilinear_setup(ix, iy, W, H);
-        for (int n = 0; n < N; ++n) {
-            const float *pl = src + n * HW;
-            o[n * HW] = bilinear_apply(q, W, [&](int off) { return __ldg(pl + off); });
+        if (GATHER && q.any && q.vx0 && q.vx1 && q.vy0 && q.vy1) {
+            const float u = (float)(q.x0 + 1), fh = (float)H;
+            float v0 = (float)(q.y0 + 1);   // exact: plane rows stay below 2^24
+            for (int n = 0; n < N; ++n, v0 += fh, o += HW) {
+                const float4 g = tex2Dgather<float4>(tex, u, v0, 0);
+                float v = __fadd_rn(0.f, __fmul_rn(g.w, q.nw));
+                v = __fadd_rn(v, __fmul_rn(g.z, q.ne));
+                v = __fadd_rn(v, __fmul_rn(g.x, q.sw));
+                *o = __fadd_rn(v, __fmul_rn(g.y, q.se));
+                if (--k == 0) { k = G; o += group_jump; }
+            }
+            return;
+        }
+        const float *pl = src;
+        for (int n = 0; n < N; ++n, pl += HW, o += HW) {
+            *o = bilinear_apply(q, W, [&](int off) { return __ldg(pl + off); });
+            if (--k == 0) { k = G; o += group_jump; }
         }
     }
+}
+
+// The library's own gather arrays (not caller-visible memory): one per (device, stream, width), grown on demand and
+// kept for the life of the process, so that calls on one stream reuse theirs in stream order and calls on different
+// streams or devices (nn.DataParallel: one thread per GPU) never share one.
+struct GatherArray {
+    int dev;
+    cudaStream_t stream;
+    int W, rows;
+    cudaArray_t arr;
+    cudaTextureObject_t tex;
+};
+static std::mutex g_gather_mutex;
+static std::vector<GatherArray> g_gather;
+
+// 0 = ok, 1 = not available for this shape (caller uses the direct path), < 0 = error
+static int gather_array_for(int W, int rows, cudaStream_t s, cudaTextureObject_t *tex, cudaArray_t *arr) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 1;
+    int maxw = 0, maxh = 0;
+    cudaDeviceGetAttribute(&maxw, cudaDevAttrMaxTexture2DGatherWidth, dev);
+    cudaDeviceGetAttribute(&maxh, cudaDevAttrMaxTexture2DGatherHeight, dev);
+    if (W > maxw || rows > maxh) return 1;
+    std::lock_guard<std::mutex> lock(g_gather_mutex);
+    for (GatherArray &g : g_gather) {
+        if (g.dev != dev || g.stream != s || g.W != W) continue;
+        if (g.rows >= rows) { *tex = g.tex; *arr = g.arr; return 0; }
+        // too small: replace (the frees synchronise; this happens once per shape)
+        cudaDestroyTextureObject(g.tex);
+        cudaFreeArray(g.arr);
+        g = g_gather.back();
+        g_gather.pop_back();
+        break;
+    }
+    GatherArray g{dev, s, W, rows, nullptr, 0};
+    const cudaChannelFormatDesc cd = cudaCreateChannelDesc<float>();
+    if (cudaMallocArray(&g.arr, &cd, (size_t)W, (size_t)rows, cudaArrayTextureGather) != cudaSuccess) {
+        cudaGetLastError();
+        return 1;
+    }
+    cudaResourceDesc rd;
+    memset(&rd, 0, sizeof(rd));
+    rd.resType = cudaResourceTypeArray;
+    rd.res.array.array = g.arr;
+    cudaTextureDesc td;
+    memset(&td, 0, sizeof(td));
+    td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
+    td.filterMode = cudaFilterModePoint;
+    td.readMode = cudaReadModeElementType;
+    td.normalizedCoords = 0;
+    if (cudaCreateTextureObject(&g.tex, &rd, &td, nullptr) != cudaSuccess) {
+        cudaGetLastError();
+        cudaFreeArray(g.arr);
+        return 1;
+    }
+    g_gather.push_back(g);
+    *tex = g.tex;
+    *arr = g.arr;
+    return 0;
 }
 
 // grid (ceil(W/32), ceil(H/8), B); dynamic smem: n*9 floats
@@ -401,20 +492,39 @@ static int make_window_map(CUtensorMap *map, const void *ptr, CUtensorMapDataTyp
 
 }  // namespace mp
 
-extern "C" int mp_warp_f32(const float *src, int N, int n_mats, int H, int W, const float *A,
-                           const float *xs, const float *ys, int mode, int padding, float *out,
-                           mp_stream_t stream) {
+extern "C" int mp_warp_groups_f32(const float *src, int N, int group, int n_mats, int H, int W, const float *A,
+                                  const float *xs, const float *ys, int mode, int padding, float *out,
+                                  mp_stream_t stream) {
     mp::prof_entry((cudaStream_t)stream);
     MP_CHECK_ARG(N >= 0 && n_mats >= 0 && H > 0 && W > 0, "mp_warp_f32: bad shape");
     MP_CHECK_ARG(mode == MP_BILINEAR || mode == MP_NEAREST, "mp_warp_f32: bad mode %d", mode);
     MP_CHECK_ARG(padding == MP_PAD_ZEROS || padding == MP_PAD_REFLECTION, "mp_warp_f32: bad padding %d", padding);
     MP_CHECK_ARG(n_mats <= 65535, "mp_warp_f32: at most 65535 matrices per call");
     if (N == 0 || n_mats == 0) return MP_OK;
+    MP_CHECK_ARG(group > 0 && N % group == 0, "mp_warp_groups_f32: group %d does not divide the %d planes", group, N);
     MP_CHECK_ARG(src && A && xs && ys && out, "mp_warp_f32: null pointer");
     dim3 grid((W + 31) / 32, (H + 7) / 8, n_mats), block(32, 8);
-    mp::warp_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(src, N, H, W, A, xs, ys, mode, padding, out);
-    MP_LAUNCH_OK_S("warp_kernel", (cudaStream_t)stream);
+    cudaStream_t s = (cudaStream_t)stream;
+    // many matrices over few planes (the adaptation loop's image warp): stage the planes in a gather array first
+    static const bool no_gather = getenv("MP_WARP_NO_GATHER") != nullptr;   // tuning aid
+    cudaTextureObject_t tex = 0;
+    cudaArray_t arr = nullptr;
+    if (!no_gather && mode == MP_BILINEAR && n_mats >= 4 && (long long)N * H < (1ll << 24) &&
+        mp::gather_array_for(W, N * H, s, &tex, &arr) == 0) {
+        MP_CUDA_OK(cudaMemcpy2DToArrayAsync(arr, 0, 0, src, (size_t)W * sizeof(float), (size_t)W * sizeof(float), (size_t)N * H,
+                                            cudaMemcpyDeviceToDevice, s));
+        mp::warp_kernel<true><<<grid, block, 0, s>>>(src, tex, N, group, H, W, A, xs, ys, mode, padding, out);
+    } else {
+        mp::warp_kernel<false><<<grid, block, 0, s>>>(src, 0, N, group, H, W, A, xs, ys, mode, padding, out);
+    }
+    MP_LAUNCH_OK_S("warp_kernel", s);
     return MP_OK;
+}
+
+extern "C" int mp_warp_f32(const float *src, int N, int n_mats, int H, int W, const float *A,
+                           const float *xs, const float *ys, int mode, int padding, float *out,
+                           mp_stream_t stream) {
+    return mp_warp_groups_f32(src, N, N > 0 ? N : 1, n_mats, H, W, A, xs, ys, mode, padding, out, stream);
 }
 
 extern "C" int mp_ha_aggregate_f32(const float *prob0, const float *probw_a, const float *probw_b,

@@ -317,18 +317,23 @@ def linspace_tables(H, W, device):
     return torch.from_numpy(_linspace_f32(W)).to(device), torch.from_numpy(_linspace_f32(H)).to(device)
 
 
-def warp(src, A, mode='bilinear', padding='zeros', tables=None):
-    """src (N,H,W) planes shared by all matrices; A (n,3,3) normalised dst->src; out (n,N,H,W)."""
+def warp(src, A, mode='bilinear', padding='zeros', tables=None, groups=1):
+    """src (N,H,W) planes shared by all matrices; A (n,3,3) normalised dst->src; out (n,N,H,W).
+    ``groups`` > 1 splits the planes into that many equal groups, each with an output block of its own:
+    out (groups, n, N // groups, H, W) -- one launch (one pass of coordinate arithmetic) for both spectra of a pair."""
     src = _cuda(src, torch.float32, "src")
     A = _cuda(A, torch.float32, "A")
     N, H, W = src.shape
     n = A.shape[0]
+    if groups < 1 or N % groups:
+        raise ValueError("warp: {} planes do not split into {} groups".format(N, groups))
+    G = N // groups if N else 1
     xs, ys = tables if tables is not None else linspace_tables(H, W, src.device)
-    out = torch.empty((n, N, H, W), dtype=torch.float32, device=src.device)
+    out = torch.empty((n, N, H, W) if groups == 1 else (groups, n, G, H, W), dtype=torch.float32, device=src.device)
     with torch.cuda.device(src.device):
-        _lib.check(_lib.load().mp_warp_f32(_ptr(src), N, n, H, W, _ptr(A), _ptr(xs), _ptr(ys),
-                                           {'bilinear': 0, 'nearest': 1}[mode], {'zeros': 0, 'reflection': 1}[padding],
-                                           _ptr(out), _stream(src)), "mp_warp_f32")
+        _lib.check(_lib.load().mp_warp_groups_f32(_ptr(src), N, max(G, 1), n, H, W, _ptr(A), _ptr(xs), _ptr(ys),
+                                                  {'bilinear': 0, 'nearest': 1}[mode], {'zeros': 0, 'reflection': 1}[padding],
+                                                  _ptr(out), _stream(src)), "mp_warp_groups_f32")
     return out
 
 

@@ -583,15 +583,19 @@ def _adaptation_core(images, is_optical, net, config, second, homographies, mask
     # summation order (MP_HA_INIT on the first chunk, MP_HA_FINISH on the last), so the result does not depend on it.
     chunk = max(1, int(config.get('sample_chunk', 0)) or max(1, 64 // max(B, 1)))
     prob_acc = count_acc = out = None
+    both_spectra = torch.cat([images[:, 0], img_b[:, 0]]) if second is not None else None
     for c0 in range(0, n, chunk):
         c1 = min(n, c0 + chunk)
         nc = c1 - c0
-        warped = ops.warp(images[:, 0], A_warp[c0:c1], 'bilinear', 'reflection', tables).reshape(nc * B, 1, H, W)  # :86 / :171
-        pw_a = run(warped, is_optical).reshape(nc, B, H, W).contiguous()
         pw_b = None
-        if second is not None:
-            warped = ops.warp(img_b[:, 0], A_warp[c0:c1], 'bilinear', 'reflection', tables).reshape(nc * B, 1, H, W)
-            pw_b = run(warped, opt_b).reshape(nc, B, H, W).contiguous()
+        if second is None:
+            warped = ops.warp(images[:, 0], A_warp[c0:c1], 'bilinear', 'reflection', tables).reshape(nc * B, 1, H, W)  # :171
+            pw_a = run(warped, is_optical).reshape(nc, B, H, W).contiguous()
+        else:
+            # both spectra are warped by the same matrices (:81, :86): one launch computes every sampling position once
+            warped = ops.warp(both_spectra, A_warp[c0:c1], 'bilinear', 'reflection', tables, groups=2)
+            pw_a = run(warped[0].reshape(nc * B, 1, H, W), is_optical).reshape(nc, B, H, W).contiguous()
+            pw_b = run(warped[1].reshape(nc * B, 1, H, W), opt_b).reshape(nc, B, H, W).contiguous()
         del warped
         first, last = c0 == 0, c1 == n
         res = ops.ha_aggregate(prob0 if first else None, pw_a, pw_b, mk[c0:c1], A_unwarp[c0:c1], agg, config['min_count'],

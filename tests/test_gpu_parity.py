@@ -518,6 +518,40 @@ def test_warp_vs_oracle_and_restatement(ops, utils, oracle):
     np.testing.assert_array_equal(ys.cpu().numpy(), oracle.linspace_table(H))
 
 
+def test_warp_gather_array_path_is_bit_identical(ops, oracle):
+    """Four or more matrices per call stage the planes in a CUDA array and fetch interior footprints with tex2Dgather
+    (homographic.cu: warp_kernel<true>); one matrix per call takes the direct gathers.  Same bits, and the oracle's."""
+    g = load_golden("adaptation")
+    img = cu(g["img_o"][:, 0])
+    for A_all, pad in [(g["A_warp"], 'reflection'), (g["A_unwarp"], 'zeros')]:
+        A = cu(np.ascontiguousarray(A_all))
+        assert A.shape[0] >= 4
+        got = ops.warp(img, A, 'bilinear', pad)
+        for i in range(A.shape[0]):
+            one = ops.warp(img, A[i:i + 1], 'bilinear', pad)[0]
+            assert torch.equal(got[i], one), (pad, i)
+        np.testing.assert_allclose(got[0].cpu().numpy(), oracle.warp(g["img_o"][:, 0], A_all[0], 'bilinear', pad), rtol=1e-6, atol=1e-7)
+    # full-size planes, the reference's homography distribution (rotations up to 180 degrees), NaN-free and bit-equal
+    from multipoint_b200 import utils as U
+    np.random.seed(11)
+    H, W = 512, 640
+    cfg = U._check_ha_config({'num': 9})
+    Hs, _ = U.sample_adaptation_homographies((H, W), cfg, with_masks=False)
+    A_w = U.normalized_warp_matrix(torch.from_numpy(Hs), (H, W), (H, W)).cuda()
+    src = torch.rand((3, H, W), device="cuda")
+    got = ops.warp(src, A_w, 'bilinear', 'reflection')
+    for i in range(A_w.shape[0]):
+        assert torch.equal(got[i], ops.warp(src, A_w[i:i + 1], 'bilinear', 'reflection')[0]), i
+    # both spectra of a pair in one launch: groups of planes with an output block each
+    src4 = torch.rand((4, H, W), device="cuda")
+    for mode, pad in (('bilinear', 'reflection'), ('nearest', 'zeros')):
+        both = ops.warp(src4, A_w, mode, pad, groups=2)
+        assert both.shape == (2, A_w.shape[0], 2, H, W)
+        assert torch.equal(both[0], ops.warp(src4[:2], A_w, mode, pad)) and torch.equal(both[1], ops.warp(src4[2:], A_w, mode, pad))
+    with pytest.raises(ValueError):
+        ops.warp(src, A_w, groups=2)
+
+
 def _stub(g):
     conv = torch.nn.Conv2d(1, 65, 8, stride=8).cuda()
     conv.weight.data = cu(g["stub_w"])

@@ -75,7 +75,10 @@ def main():
         r["frac_of_hbm"] = round(r["bytes"] / r["us"] / 1e3 / hbm, 4)
         print(json.dumps(r), flush=True)
     # the two aggregate flavours separately (events around single calls)
-    for name, fn in (("ha_aggregate prod (pairs)", lambda: ops.ha_aggregate(p0, pa, pb, masks, A_unwarp, 'prod', cfg['min_count'], tables=tables)),
+    img2 = torch.cat([img, torch.rand((B, H, W), generator=g, device=dev)])
+    for name, fn in (("warp, both spectra of the pairs in one launch (n=%d, %d planes in 2 groups)" % (n, 2 * B),
+                      lambda: ops.warp(img2, A_warp, 'bilinear', 'reflection', tables, groups=2)),
+                     ("ha_aggregate prod (pairs)", lambda: ops.ha_aggregate(p0, pa, pb, masks, A_unwarp, 'prod', cfg['min_count'], tables=tables)),
                      ("ha_aggregate single", lambda: ops.ha_aggregate(p0, pa, None, masks, A_unwarp, 'none', cfg['min_count'], tables=tables)),
                      ("ha_aggregate prod (pairs), TMA-staged variant", lambda: ops.ha_aggregate(p0, pa, pb, masks, A_unwarp, 'prod', cfg['min_count'], tables=tables, staged=True)),
                      ("ha_aggregate single, TMA-staged variant", lambda: ops.ha_aggregate(p0, pa, None, masks, A_unwarp, 'none', cfg['min_count'], tables=tables, staged=True))):
@@ -87,6 +90,8 @@ def main():
         torch.cuda.synchronize()
         us = e0.elapsed_time(e1) * 1e3 / args.iters
         nb = n * ((2 if 'prod' in name else 1) * B * HW * 4 + HW) + 2 * B * HW * 4
+        if name.startswith("warp"):
+            nb = n * 2 * B * 2 * HW * 4
         r = {"kernel": name, "us": round(us, 1), "bytes": nb, "GBps": round(nb / us / 1e3, 1), "frac_of_hbm": round(nb / us / 1e3 / hbm, 4)}
         rows.append(r)
         print(json.dumps(r), flush=True)

@@ -27,7 +27,17 @@ __device__ __forceinline__ void coords(const float *A, int x, int y, float &ix, 
     iy = A[3] * x + A[4] * y + A[5];
 }
 
-template <bool TEX>
+// quad-expanded source: element (y, x) = (v[y][x], v[y][x+1], v[y+1][x], v[y+1][x+1])
+__global__ void expand_kernel(const float *__restrict__ src, float4 *__restrict__ quads) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= NP * H * W) return;
+    const int x = i % W, y = (i / W) % H;
+    const bool xr = x + 1 < W, yd = y + 1 < H;
+    quads[i] = make_float4(src[i], xr ? src[i + 1] : 0.f, yd ? src[i + W] : 0.f, xr && yd ? src[i + W + 1] : 0.f);
+}
+
+// TEX: 0 = four __ldg, 1 = tex2Dgather (CUDA array), 2 = one 128-bit __ldg from the quad-expanded source, 3 = four tex2D point fetches (pitch-linear)
+template <int TEX>
 __global__ void __launch_bounds__(256) warp_kernel(cudaTextureObject_t tex, const float *__restrict__ src, const float *__restrict__ A, float *__restrict__ out) {
     __shared__ float As[6];
     const int m = blockIdx.z;
@@ -44,9 +54,15 @@ __global__ void __launch_bounds__(256) warp_kernel(cudaTextureObject_t tex, cons
     const float ax = ix - fx, ay = iy - fy;
     for (int n = 0; n < NP; ++n) {
         float a, b, c, d;
-        if (TEX) {
+        if (TEX == 1) {
             const float4 g = tex2Dgather<float4>(tex, (float)(x0 + 1), (float)(y0 + 1 + n * H), 0);
             a = g.w; b = g.z; c = g.x; d = g.y;
+        } else if (TEX == 2) {
+            const float4 g = __ldg(reinterpret_cast<const float4 *>(src) + (size_t)n * H * W + y0 * W + x0);
+            a = g.x; b = g.y; c = g.z; d = g.w;
+        } else if (TEX == 3) {
+            const float u = x0 + 0.5f, v = y0 + n * H + 0.5f;
+            a = tex2D<float>(tex, u, v); b = tex2D<float>(tex, u + 1, v); c = tex2D<float>(tex, u, v + 1); d = tex2D<float>(tex, u + 1, v + 1);
         } else {
             const float *p = src + (size_t)n * H * W + y0 * W + x0;
             a = __ldg(p); b = __ldg(p + 1); c = __ldg(p + W); d = __ldg(p + W + 1);
@@ -100,22 +116,38 @@ int main() {
 
     dim3 grid(W / 32, H / 8, NM), block(256);
     std::vector<float> r0((size_t)NM * NP * H * W), r1(r0.size());
-    for (int variant = 0; variant < 2; ++variant) {
+    float4 *quads;
+    CK(cudaMalloc(&quads, h.size() * 16));
+    CK(cudaEventRecord(e0));
+    for (int i = 0; i < 20; ++i) expand_kernel<<<(NP * H * W + 255) / 256, 256>>>(src, quads);
+    CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1)); CK(cudaEventElapsedTime(&ms, e0, e1));
+    printf("quad expansion of %d planes: %.2f us\n", NP, ms * 1000 / 20);
+    cudaResourceDesc rp = {};
+    rp.resType = cudaResourceTypePitch2D; rp.res.pitch2D.devPtr = src; rp.res.pitch2D.desc = cd;
+    rp.res.pitch2D.width = W; rp.res.pitch2D.height = NP * H; rp.res.pitch2D.pitchInBytes = W * 4;
+    cudaTextureObject_t texp;
+    CK(cudaCreateTextureObject(&texp, &rp, &td, nullptr));
+    const char *names[4] = {"4 x ldg", "tex2Dgather", "quad ldg.128", "4 x tex2D pitch2D"};
+    for (int variant = 0; variant < 4; ++variant) {
         for (int rep = 0; rep < 3; ++rep) {
             CK(cudaEventRecord(e0));
             for (int i = 0; i < 10; ++i) {
-                if (variant) warp_kernel<true><<<grid, block>>>(tex, src, A, out);
-                else warp_kernel<false><<<grid, block>>>(tex, src, A, out);
+                if (variant == 1) warp_kernel<1><<<grid, block>>>(tex, src, A, out);
+                else if (variant == 2) warp_kernel<2><<<grid, block>>>(tex, reinterpret_cast<const float *>(quads), A, out);
+                else if (variant == 3) warp_kernel<3><<<grid, block>>>(texp, src, A, out);
+                else warp_kernel<0><<<grid, block>>>(tex, src, A, out);
             }
             CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1)); CK(cudaEventElapsedTime(&ms, e0, e1));
         }
         CK(cudaGetLastError());
-        printf("%s: %.1f us per launch (%d planes of %dx%d), %.0f GB/s written\n", variant ? "tex2Dgather" : "4 x ldg", ms * 100, NM * NP, W, H,
+        printf("%s: %.1f us per launch (%d planes of %dx%d), %.0f GB/s written\n", names[variant], ms * 100, NM * NP, W, H,
                (double)NM * NP * H * W * 4 / (ms * 1e-4) / 1e9);
         CK(cudaMemcpy((variant ? r1 : r0).data(), out, r0.size() * 4, cudaMemcpyDeviceToHost));
+        if (variant) {
+            size_t diff = 0;
+            for (size_t i = 0; i < r0.size(); ++i) diff += r0[i] != r1[i];
+            printf("  elements that differ from the ldg variant: %zu of %zu\n", diff, r0.size());
+        }
     }
-    size_t diff = 0;
-    for (size_t i = 0; i < r0.size(); ++i) diff += r0[i] != r1[i];
-    printf("elements that differ between the two variants: %zu of %zu\n", diff, r0.size());
     return 0;
 }
