@@ -19,7 +19,9 @@ FULL_COLS = ['Kernel Name', 'gpu__time_duration.sum', 'dram__bytes_read.sum', 'd
              'l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed', 'sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active',
              'sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active', 'smsp__inst_executed.sum',
              'smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio',
-             'smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio']
+             'smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio',
+             'sm__cycles_elapsed.avg.per_second', 'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed',
+             'l1tex__data_pipe_tex_wavefronts.avg.pct_of_peak_sustained_elapsed']
 
 
 def _us(value, unit):
