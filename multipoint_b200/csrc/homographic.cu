@@ -181,10 +181,15 @@ static int gather_array_for(int W, int rows, cudaStream_t s, cudaTextureObject_t
     cudaDeviceGetAttribute(&maxw, cudaDevAttrMaxTexture2DGatherWidth, dev);
     cudaDeviceGetAttribute(&maxh, cudaDevAttrMaxTexture2DGatherHeight, dev);
     if (W > maxw || rows > maxh) return 1;
+    // allocating (or freeing) an array is not a stream operation: while the stream is being captured into a graph only
+    // an array that already exists may be used
+    cudaStreamCaptureStatus capturing = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(s, &capturing) != cudaSuccess) { cudaGetLastError(); return 1; }
     std::lock_guard<std::mutex> lock(g_gather_mutex);
     for (GatherArray &g : g_gather) {
         if (g.dev != dev || g.stream != s || g.W != W) continue;
         if (g.rows >= rows) { *tex = g.tex; *arr = g.arr; return 0; }
+        if (capturing != cudaStreamCaptureStatusNone) return 1;
         // too small: replace (the frees synchronise; this happens once per shape)
         cudaDestroyTextureObject(g.tex);
         cudaFreeArray(g.arr);
@@ -192,6 +197,7 @@ static int gather_array_for(int W, int rows, cudaStream_t s, cudaTextureObject_t
         g_gather.pop_back();
         break;
     }
+    if (capturing != cudaStreamCaptureStatusNone) return 1;
     GatherArray g{dev, s, W, rows, nullptr, 0};
     const cudaChannelFormatDesc cd = cudaCreateChannelDesc<float>();
     if (cudaMallocArray(&g.arr, &cd, (size_t)W, (size_t)rows, cudaArrayTextureGather) != cudaSuccess) {
