@@ -216,3 +216,24 @@ def test_fuzz_homographic_adaptation(utils, ops, oracle):
             want = oracle.homographic_adaptation(img_o[:, 0], net_prob, Hs, masks.astype(np.float32), cfg['min_count'], images_b=img_t[:, 0],
                                                  aggregation=agg, A_warp=A_w, A_unwarp=A_u)
         np.testing.assert_allclose(got[:, 0].cpu().numpy(), want, rtol=1e-5, atol=1e-7, err_msg=tag)
+
+
+def test_larger_than_benchmark_shapes(utils, ops, oracle):
+    """Images larger than 512 x 640 (the sparse top-k kernel's whole-image bitmap no longer fits shared memory: the tile
+    kernels take over), more keypoints than the benchmark's 2048, and a matching problem with ragged tile edges."""
+    for seed, H, W in ((9001, 1030, 1284), (9002, 777, 1001)):
+        hm = syn.heatmap(seed, 2, H, W)
+        for topk in (0, 3000):
+            want = oracle.box_nms(hm, 4, 0.015, keep_top_k=topk)
+            dense, kp, sc, cnt = ops.box_nms(cu(hm[:, 0]), 4, 0.015, keep_top_k=topk, want_keypoints=True, kp_cap=(topk or 200000))
+            np.testing.assert_array_equal(dense.cpu().numpy(), want[:, 0])
+            for b in range(2):
+                ref = oracle.extract_keypoints(want[b, 0], 0.0)
+                assert int(cnt[b]) == len(ref)
+                np.testing.assert_array_equal(kp[b, :len(ref)].cpu().numpy(), ref)
+    rng = np.random.RandomState(9003)
+    a, b = _sets(rng, 3001, 2777, 256, ties=True)
+    got = ops.nearest(cu(a), cu(b), metric='l2', algo='tensor', want_scores=False)
+    want = oracle.nearest(a, b, mode='bf', f64=True)
+    np.testing.assert_array_equal(got['idx12'][0].cpu().numpy(), want['idx12'])
+    np.testing.assert_array_equal(got['idx21'][0].cpu().numpy(), want['idx21'])
