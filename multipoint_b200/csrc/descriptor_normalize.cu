@@ -51,9 +51,7 @@ normalize_desc_kernel(const float *__restrict__ x, float *__restrict__ out_nchw,
         float tot = 0.f;
 #pragma unroll
         for (int w = 0; w < DN_WARPS; ++w) tot += smem[(m * DN_WARPS + w) * 32 + lane];
-        const float denom = fmaxf(sqrtf(tot), 1e-12f);
-#pragma unroll
-        for (int k = 0; k < CPT; ++k) v[m][k] = v[m][k] / denom;
+        divide_all(v[m], fmaxf(sqrtf(tot), 1e-12f));   // x / max(|x|, eps), one reciprocal per cell
     }
 
     if (out_nchw != nullptr) {

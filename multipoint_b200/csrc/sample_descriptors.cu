@@ -145,9 +145,12 @@ sample_descriptors_nhwc_vec_kernel(const int64_t *__restrict__ kp, const int32_t
     for (int s = LPK / 2; s > 0; s >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, s);
     if (!SPLIT && !in_range) return;   // (SPLIT: the lanes still take part in the norm reduction below)
     if (live) {
-        const float denom = fmaxf(sqrtf(ss), 1e-12f);
+        float e[4 * NV];
 #pragma unroll
-        for (int j = 0; j < NV; ++j) { v[j].x = v[j].x / denom; v[j].y = v[j].y / denom; v[j].z = v[j].z / denom; v[j].w = v[j].w / denom; }
+        for (int j = 0; j < NV; ++j) { e[4 * j] = v[j].x; e[4 * j + 1] = v[j].y; e[4 * j + 2] = v[j].z; e[4 * j + 3] = v[j].w; }
+        divide_all(e, fmaxf(sqrtf(ss), 1e-12f));
+#pragma unroll
+        for (int j = 0; j < NV; ++j) v[j] = make_float4(e[4 * j], e[4 * j + 1], e[4 * j + 2], e[4 * j + 3]);
     }
     if (in_range) {
         float4 *o = reinterpret_cast<float4 *>(out + (size_t)item * D);
