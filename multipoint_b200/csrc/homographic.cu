@@ -32,7 +32,7 @@ __device__ __forceinline__ void src_coord(const float *A, float xs, float ys, in
     const float X = __fadd_rn(__fadd_rn(__fmul_rn(A[0], xs), __fmul_rn(A[1], ys)), A[2]);
     const float Y = __fadd_rn(__fadd_rn(__fmul_rn(A[3], xs), __fmul_rn(A[4], ys)), A[5]);
     const float Z = __fadd_rn(__fadd_rn(__fmul_rn(A[6], xs), __fmul_rn(A[7], ys)), A[8]);
-    const float sc = fabsf(Z) > 1e-8f ? __fdiv_rn(1.0f, Z) : 1.0f;
+    const float sc = fabsf(Z) > 1e-8f ? __frcp_rn(Z) : 1.0f;   // the correctly rounded 1 / Z, i.e. the same bits as the division
     // (.. + 1) / 2 as a multiplication by 0.5: the same bits as the division for every finite input
     ix = __fmul_rn(__fmul_rn(__fadd_rn(__fmul_rn(X, sc), 1.f), 0.5f), (float)(Ws - 1));
     iy = __fmul_rn(__fmul_rn(__fadd_rn(__fmul_rn(Y, sc), 1.f), 0.5f), (float)(Hs - 1));

@@ -5,7 +5,8 @@
 //
 // The sampling coordinate follows the reference's fp32 operation order exactly:
 //   y_n = y / (H*0.5) - 1            (utils.py:162-163; note H/2, not (H-1)/2)
-//   iy  = ((y_n + 1) / 2) * (Hc - 1) (ATen grid_sampler unnormalize, align_corners=True)
+//   iy  = ((y_n + 1) / 2) * (Hc - 1) (ATen grid_sampler unnormalize, align_corners=True; the halving is
+//         a multiplication by 0.5 here: the same bits)
 // zero padding: a corner outside the map contributes 0.
 //
 // HBM-bound gather: one warp per keypoint, lanes across channels.  With the channels-last map
@@ -38,8 +39,8 @@ sample_descriptors_kernel(const int64_t *__restrict__ kp, const int32_t *__restr
     const float y = (float)kp[2 * item], x = (float)kp[2 * item + 1];
     const float yn = __fsub_rn(__fdiv_rn(y, half_h), 1.0f);
     const float xn = __fsub_rn(__fdiv_rn(x, half_w), 1.0f);
-    const float iy = __fmul_rn(__fdiv_rn(__fadd_rn(yn, 1.0f), 2.0f), (float)(Hc - 1));
-    const float ix = __fmul_rn(__fdiv_rn(__fadd_rn(xn, 1.0f), 2.0f), (float)(Wc - 1));
+    const float iy = __fmul_rn(__fmul_rn(__fadd_rn(yn, 1.0f), 0.5f), (float)(Hc - 1));
+    const float ix = __fmul_rn(__fmul_rn(__fadd_rn(xn, 1.0f), 0.5f), (float)(Wc - 1));
     const float fx = floorf(ix), fy = floorf(iy);
     const int x0 = (int)fx, y0 = (int)fy, x1 = x0 + 1, y1 = y0 + 1;
     const float nw = __fmul_rn((float)x1 - ix, (float)y1 - iy);
@@ -109,8 +110,8 @@ sample_descriptors_nhwc_vec_kernel(const int64_t *__restrict__ kp, const int32_t
         const float y = (float)kp[2 * item], x = (float)kp[2 * item + 1];
         const float yn = __fsub_rn(__fdiv_rn(y, half_h), 1.0f);
         const float xn = __fsub_rn(__fdiv_rn(x, half_w), 1.0f);
-        const float iy = __fmul_rn(__fdiv_rn(__fadd_rn(yn, 1.0f), 2.0f), (float)(Hc - 1));
-        const float ix = __fmul_rn(__fdiv_rn(__fadd_rn(xn, 1.0f), 2.0f), (float)(Wc - 1));
+        const float iy = __fmul_rn(__fmul_rn(__fadd_rn(yn, 1.0f), 0.5f), (float)(Hc - 1));
+        const float ix = __fmul_rn(__fmul_rn(__fadd_rn(xn, 1.0f), 0.5f), (float)(Wc - 1));
         const float fx = floorf(ix), fy = floorf(iy);
         const int x0 = (int)fx, y0 = (int)fy, x1 = x0 + 1, y1 = y0 + 1;
         const float w4[4] = {__fmul_rn((float)x1 - ix, (float)y1 - iy), __fmul_rn(ix - (float)x0, (float)y1 - iy),
