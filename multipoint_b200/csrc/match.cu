@@ -183,25 +183,33 @@ match_top2_simt_kernel(const float *__restrict__ a, const int32_t *__restrict__ 
 //               the true nearest neighbour: two exact keys settle it (match_recheck_pair_kernel)
 //   full list : three or more candidates within the bound (or the NN metric's clip plateau) ->
 //               exact rescan of the whole other set (match_recheck_kernel)
-__global__ void match_flag_kernel(const Top2 *__restrict__ top, int N, int P, const unsigned *__restrict__ max_a,
-                                  const unsigned *__restrict__ max_b, int metric, float eps_rel, float pack_rel, int side,
-                                  int32_t *__restrict__ idx_out, int32_t *__restrict__ flagged, int *__restrict__ n_flagged,
-                                  int32_t *__restrict__ pairs, int *__restrict__ n_pairs) {
+struct FlagSide {
+    const Top2 *top;
+    int N;
+    const unsigned *max_a, *max_b;
+    int32_t *idx_out, *flagged, *pairs;
+};
+// grid (ceil(max(N1, N2) * P / 256), 2): blockIdx.y = side (0: rows of set 1 against set 2, 1: the other way round)
+__global__ void match_flag_kernel(const FlagSide side0, const FlagSide side1, int P, int metric, float eps_rel, float pack_rel,
+                                  int *__restrict__ n_flagged, int *__restrict__ n_pairs) {
+    const int side = blockIdx.y;
+    const FlagSide &S = side == 0 ? side0 : side1;
+    const int N = S.N;
     const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= (long long)P * N) return;
     const int p = (int)(g / N);
-    const Top2 t = top[g];
-    idx_out[g] = t.best_idx;
+    const Top2 t = S.top[g];
+    S.idx_out[g] = t.best_idx;
     if (t.best_idx < 0 || t.second_idx < 0) return;
-    const float ma = __uint_as_float(max_a[p]), mb = __uint_as_float(max_b[p]);
+    const float ma = __uint_as_float(S.max_a[p]), mb = __uint_as_float(S.max_b[p]);
     const float eps = eps_rel * fmaxf(ma * mb, 1e-30f) +
                       pack_rel * 2.f * (1.002f * ma * mb + (metric == MP_METRIC_L2 ? 0.5f * mb * mb : 0.f));
     const bool close2 = !(t.best - t.second >= 2.f * eps);  // also catches NaN keys
     const bool close3 = !(t.best - t.third >= 2.f * eps);
     const bool plateau = metric == MP_METRIC_NN && t.best >= 1.f - eps;  // clip(.,-1,1) can tie many columns
     const int row = (int)(g - (long long)p * N);
-    if (plateau || (close2 && close3)) flagged[(size_t)p * N + atomicAdd(n_flagged + 2 * p + side, 1)] = row;
-    else if (close2) pairs[(size_t)p * N + atomicAdd(n_pairs + 2 * p + side, 1)] = row;
+    if (plateau || (close2 && close3)) S.flagged[(size_t)p * N + atomicAdd(n_flagged + 2 * p + side, 1)] = row;
+    else if (close2) S.pairs[(size_t)p * N + atomicAdd(n_pairs + 2 * p + side, 1)] = row;
 }
 
 // exact fp64 key of one (a, b) pair, lanes striding over D; result in every lane
@@ -890,10 +898,12 @@ static int run_nearest(const float *d1, const int32_t *n1, int N1, const float *
         MP_LAUNCH_OK_S("match_top2_simt_kernel", s);
     }
     const float eps_rel = tensor ? MATCH_EPS_TENSOR : MATCH_EPS_SIMT, pack_rel = tensor ? MATCH_PACK_REL : 0.f;
-    match_flag_kernel<<<(unsigned)((r1 + 255) / 256), 256, 0, s>>>(top12, N1, P, max1, max2, metric, eps_rel, pack_rel, 0, idx12, flagged1, n_flagged, pairs1, n_pairs);
-    MP_LAUNCH_OK_S("match_flag_kernel", s);
-    match_flag_kernel<<<(unsigned)((r2 + 255) / 256), 256, 0, s>>>(top21, N2, P, max2, max1, metric, eps_rel, pack_rel, 1, idx21, flagged2, n_flagged, pairs2, n_pairs);
-    MP_LAUNCH_OK_S("match_flag_kernel", s);
+    {   // both directions in one launch
+        const FlagSide f0{top12, N1, max1, max2, idx12, flagged1, pairs1}, f1{top21, N2, max2, max1, idx21, flagged2, pairs2};
+        const long long rmax = r1 > r2 ? r1 : r2;
+        match_flag_kernel<<<dim3((unsigned)((rmax + 255) / 256), 2), 256, 0, s>>>(f0, f1, P, metric, eps_rel, pack_rel, n_flagged, n_pairs);
+        MP_LAUNCH_OK_S("match_flag_kernel", s);
+    }
     {
         dim3 grid(2 * P, RP_Y);
         match_recheck_pair_kernel<<<grid, 256, 0, s>>>(d1, N1, d2, N2, D, metric, top12, top21, pairs1, pairs2, n_pairs, idx12, idx21);
