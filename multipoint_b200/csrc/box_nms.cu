@@ -19,7 +19,7 @@
 //                        shared memory; iterates to the local fixed point over candidate lists, writes the
 //                        dense result once.  Pixels whose dependency chain leaves the apron (<0.1 % at E=8)
 //                        are written as -score and queued on a per-image worklist.
-//   2. nms_fixup_kernel  one CTA per image; resolves the worklist against the dense map in L2.
+//   2. nms_fixup_select_kernel  one CTA per image; first resolves the worklist against the dense map in L2 (nms_fixup_body),
 //                        Exits immediately when the list is empty.
 //  sparse top-k path (keep_top_k > 0; the reference's shipped configs use topk: 0 = the dense path above; see the
 //  comment above nms_candidates_kernel)
@@ -27,7 +27,7 @@
 //                        zero-fills the dense map when the caller wants it).
 //   2'. nms_sparse2_kernel one CTA per image settles only the candidates that can reach the top k, cuts to k and emits.
 //  both
-//   3. nms_select_kernel one CTA per image; optional top-k by radix select on (score desc, index
+//   3. then, in the same launch (nms_select_body): optional top-k by radix select on (score desc, index
 //                        asc), then ordered (row-major) compaction of the survivors through a
 //                        bitmap into int64 (y,x) keypoints.
 #include <math.h>
@@ -779,10 +779,10 @@ nms_tile_fast_redo_kernel(const float *__restrict__ prob, float *__restrict__ ou
 // One CTA per image: resolve the pixels whose dependency chain left their tile's apron.
 // One warp per queued pixel: the lanes fetch the (2R+1)^2 window from the dense map (L2) in
 // parallel and vote, so a round costs one L2 round trip instead of one per neighbour.
-__global__ void __launch_bounds__(1024)
-nms_fixup_kernel(float *__restrict__ out, int H, int W, const NmsFootprint fp, uint2 *__restrict__ survivors,
-                 int *__restrict__ surv_count, const uint32_t *__restrict__ worklist,
-                 const int *__restrict__ work_count, int cap) {
+__device__ __forceinline__ void
+nms_fixup_body(float *__restrict__ out, int H, int W, const NmsFootprint &fp, uint2 *survivors,
+               int *surv_count, const uint32_t *__restrict__ worklist,
+               const int *__restrict__ work_count, int cap) {
     const int b = blockIdx.x;
     const int n = work_count[b];  // 0 for images the sparse top-k path settled
     if (n == 0) return;
@@ -876,7 +876,7 @@ __device__ void emit_from_bitmap(const uint32_t *bitmap, int words, int W, const
 //     candidates, settles exactly those with the same fixed point as the tile kernel -- whole image
 //     in one CTA, so no apron and no fix-up; candidate bitmap, ranks and signed state all in shared
 //     memory -- lowers the threshold and repeats while fewer than k survive, then cuts to k and
-//     emits the keypoints in row-major order itself (nms_select_kernel only serves redone images).
+//     emits the keypoints in row-major order itself (the select step of nms_fixup_select_kernel only serves redone images).
 // An image that does not fit (a chunk with more than SP_SEG_CAP candidates, or more than SP2_CAP needed)
 // raises its flag and is redone by the tile + fix-up kernels, which otherwise exit at once.
 constexpr int SP_BINS = 128;
@@ -1360,16 +1360,16 @@ nms_sparse2_kernel(const float *__restrict__ prob, float *__restrict__ dense, in
     }
 }
 
-__global__ void __launch_bounds__(1024)
-nms_select_kernel(float *__restrict__ out, int H, int W, int keep_top_k, const uint2 *__restrict__ survivors,
-                  const int *__restrict__ surv_count, int cap, uint32_t *__restrict__ bitmaps, int words,
-                  int64_t *__restrict__ keypoints, float *__restrict__ kp_scores, int32_t *__restrict__ kp_counts,
-                  int kp_cap) {
+__device__ __forceinline__ void
+nms_select_body(float *out, int H, int W, int keep_top_k, const uint2 *survivors,
+                const int *surv_count, int cap, uint32_t *__restrict__ bitmaps, int words,
+                int64_t *__restrict__ keypoints, float *__restrict__ kp_scores, int32_t *__restrict__ kp_counts,
+                int kp_cap) {
     __shared__ int hist[SEL_BINS];
     __shared__ int warp_sums[32];
     __shared__ int sel_bin, sel_remaining;
     const int b = blockIdx.x, tid = threadIdx.x;
-    const int n = surv_count[b];
+    const int n = *reinterpret_cast<const volatile int *>(surv_count + b);   // the fix-up in front of this may just have raised it
     if (n < 0) return;   // settled, cut and emitted by nms_sparse2_kernel
     const uint2 *surv = survivors + (size_t)b * cap;
     float *img = out + (size_t)b * H * W;
@@ -1449,6 +1449,22 @@ nms_select_kernel(float *__restrict__ out, int H, int W, int keep_top_k, const u
     emit_from_bitmap(bitmap, words, W, img, keypoints ? keypoints + (size_t)b * kp_cap * 2 : nullptr,
                      kp_scores ? kp_scores + (size_t)b * kp_cap : nullptr, kp_counts ? kp_counts + b : nullptr,
                      kp_cap, warp_sums);
+}
+
+// One CTA per image, one launch for both steps: the fix-up of the pixels whose dependency chain left their tile's apron,
+// then (optionally) the top-k cut and the ordered keypoint emission.  Both only touch their own image, so the order
+// inside the CTA is all the synchronisation they need; on the sparse top-k path both return at once for every image the
+// sparse kernel settled (one ~3 us launch instead of two).
+__global__ void __launch_bounds__(1024)
+nms_fixup_select_kernel(float *out, int H, int W, const NmsFootprint fp, uint2 *survivors, int *surv_count,
+                        const uint32_t *__restrict__ worklist, const int *__restrict__ work_count, int cap, int do_select,
+                        int keep_top_k, uint32_t *__restrict__ bitmaps, int words, int64_t *__restrict__ keypoints,
+                        float *__restrict__ kp_scores, int32_t *__restrict__ kp_counts, int kp_cap) {
+    nms_fixup_body(out, H, W, fp, survivors, surv_count, worklist, work_count, cap);
+    if (!do_select) return;
+    __threadfence_block();
+    __syncthreads();
+    nms_select_body(out, H, W, keep_top_k, survivors, surv_count, cap, bitmaps, words, keypoints, kp_scores, kp_counts, kp_cap);
 }
 
 // ---- row 4b: torch.nonzero((p > thr).float() [* mask]) ----
@@ -1683,14 +1699,10 @@ extern "C" int mp_box_nms_f32(const float *prob, int B, int H, int W, double siz
         rc = launch_tile<32, 128, 16>(prob, prob_nms, B, H, W, thr, fp, surv, surv_count, work, work_count, L.cap, vec, s);
     if (rc != MP_OK) return rc;
 
-    nms_fixup_kernel<<<B, 1024, 0, s>>>(prob_nms, H, W, fp, surv, surv_count, work, work_count, L.cap);
-    MP_LAUNCH_OK_S("nms_fixup_kernel", s);
-
-    if (keep_top_k > 0 || keypoints != nullptr || kp_counts != nullptr) {
-        nms_select_kernel<<<B, 1024, 0, s>>>(prob_nms, H, W, keep_top_k, surv, surv_count, L.cap, bitmaps, L.words,
-                                             keypoints, kp_scores, kp_counts, kp_cap);
-        MP_LAUNCH_OK_S("nms_select_kernel", s);
-    }
+    const int do_select = (keep_top_k > 0 || keypoints != nullptr || kp_counts != nullptr) ? 1 : 0;
+    nms_fixup_select_kernel<<<B, 1024, 0, s>>>(prob_nms, H, W, fp, surv, surv_count, work, work_count, L.cap, do_select, keep_top_k,
+                                               bitmaps, L.words, keypoints, kp_scores, kp_counts, kp_cap);
+    MP_LAUNCH_OK_S("nms_fixup_select_kernel", s);
     return MP_OK;
 }
 

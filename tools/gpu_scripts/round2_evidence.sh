@@ -14,10 +14,10 @@ timeout -k 10 900 python tools/bench_kernels.py --out gpurun_out/r2_kernels.json
 # launch list of the hot path at the full batch size (cold-cache, serialised: compare shares)
 timeout -k 10 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r2_launches_hot.csv \
     python bench.py --only-hot --steps 2 --warmup 3 > gpurun_out/r2_ncu_launch_hot.log 2>&1
-# full capture of one warm hot-path step (every kernel of this library): 16 launches per step, 3 warm-up steps
+# full capture of one warm hot-path step (every kernel of this library): 15 launches per step, 3 warm-up steps
 timeout -k 10 900 ncu --set full --clock-control none --import-source on \
     -k regex:"nms_|detector_head_kernel|normalize_desc|sample_descriptors|match_" \
-    -s 48 -c 16 -o gpurun_out/r2_prof_hot python bench.py --only-hot --steps 1 --warmup 3 > gpurun_out/r2_ncu_full.log 2>&1
+    -s 45 -c 15 -o gpurun_out/r2_prof_hot python bench.py --only-hot --steps 1 --warmup 3 > gpurun_out/r2_ncu_full.log 2>&1
 # adaptation kernels on the reference's homography distribution
 timeout -k 10 600 ncu --set full --clock-control none --import-source on -k regex:"warp_kernel|ha_aggregate|valid_mask" -s 12 -c 4 \
     -o gpurun_out/r2_prof_adapt python tools/bench_adapt.py --iters 2 > gpurun_out/r2_ncu_adapt.log 2>&1
