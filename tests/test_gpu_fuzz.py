@@ -237,3 +237,60 @@ def test_larger_than_benchmark_shapes(utils, ops, oracle):
     want = oracle.nearest(a, b, mode='bf', f64=True)
     np.testing.assert_array_equal(got['idx12'][0].cpu().numpy(), want['idx12'])
     np.testing.assert_array_equal(got['idx21'][0].cpu().numpy(), want['idx21'])
+
+
+def test_fuzz_glue_and_magicleap(ops, oracle):
+    """The fused backbone glue (any C, H, W incl. the scalar path for W % 4 != 0) against the torch module sequence, and
+    the MagicLeap heatmap arithmetic against the oracle, on random shapes."""
+    rng = np.random.RandomState(1007)
+    torch.manual_seed(7)
+    for it in range(ITERS):
+        B, C = int(rng.randint(1, 4)), int(rng.randint(1, 40))
+        H, W = int(rng.randint(2, 50)), int(rng.randint(2, 70))
+        pool = bool(rng.rand() < 0.5)
+        if pool:
+            H, W = 2 * H, 2 * W
+        x = torch.randn(B, C, H, W, device="cuda") * 2
+        bn = torch.nn.BatchNorm2d(C).cuda().eval()
+        with torch.no_grad():
+            bn.weight.uniform_(-1.5, 1.5); bn.bias.normal_(); bn.running_mean.normal_(); bn.running_var.uniform_(0.2, 3.0)
+            scale = bn.weight / torch.sqrt(bn.running_var + bn.eps)
+            shift = bn.bias - bn.running_mean * scale
+            bn_first, pad, reflect = bool(rng.rand() < 0.5), int(rng.randint(0, 2)), bool(rng.rand() < 0.5)
+            cbias = torch.randn(C, device="cuda") if rng.rand() < 0.5 else None
+            xb = x if cbias is None else x + cbias[None, :, None, None]
+            ref = torch.relu(bn(xb)) if bn_first else bn(torch.relu(xb))
+            if pool:
+                ref = torch.nn.functional.max_pool2d(ref, 2, 2)
+            if pad:
+                ref = (torch.nn.ReflectionPad2d(1) if reflect else torch.nn.ZeroPad2d(1))(ref)
+            got = ops.relu_bn_pad(x, scale, shift, bn_first=bn_first, pool=pool, pad=pad, reflect=reflect, conv_bias=cbias)
+            torch.testing.assert_close(got, ref, rtol=2e-6, atol=2e-6, msg=str((B, C, H, W, pool, bn_first, pad, reflect)))
+            # first encoder layer
+            img = torch.rand(B, 1, H, W, device="cuda")
+            conv = torch.nn.Conv2d(1, C, 3).cuda()
+            in_reflect = bool(rng.rand() < 0.5)
+            y = conv((torch.nn.ReflectionPad2d(1) if in_reflect else torch.nn.ZeroPad2d(1))(img))
+            ref = torch.relu(bn(y)) if bn_first else bn(torch.relu(y))
+            if pad:
+                ref = (torch.nn.ReflectionPad2d(1) if reflect else torch.nn.ZeroPad2d(1))(ref)
+            got = ops.conv1_relu_bn_pad(img, conv.weight, conv.bias, scale, shift, bn_first=bn_first, in_reflect=in_reflect,
+                                        pad=pad, out_reflect=reflect)
+            torch.testing.assert_close(got, ref, rtol=1e-5, atol=1e-5, msg=str((B, C, H, W, bn_first, in_reflect, pad, reflect)))
+        lg = syn.logits(9100 + it, B, int(rng.randint(1, 30)), int(rng.randint(1, 30)), sigma=float(rng.choice([0.5, 3.0])), bias=float(rng.choice([0.0, 6.0])))
+        np.testing.assert_allclose(ops.heatmap_magicleap(cu(lg)).cpu().numpy(), oracle.heatmap_magicleap(lg), rtol=1e-5, atol=1e-12)
+
+
+def test_fuzz_evaluation_points(ops, oracle):
+    rng = np.random.RandomState(1008)
+    for it in range(ITERS):
+        H, W = int(rng.randint(8, 300)), int(rng.randint(8, 400))
+        nq, nt = int(rng.randint(1, 400)), int(rng.randint(1, 400))
+        q = rng.randint(-10, max(H, W) + 10, (1, nq, 2)).astype(np.int64)
+        t = np.stack([rng.randint(0, H, (1, nt)), rng.randint(0, W, (1, nt))], axis=2).astype(np.int64)
+        got = ops.points_min_dist2(cu(q), cu(t), H, W)[0].cpu().numpy()
+        np.testing.assert_array_equal(got, oracle.points_min_dist2(q[0], t[0], H, W), err_msg=str((H, W, nq, nt)))
+        qw = q[0].astype(np.float64) + rng.rand(nq, 2)
+        thr = float(rng.choice([1.0, 4.0, 6.0]))
+        ra, _ = ops.points_correct(cu(qw[None]), cu(t), thr)
+        np.testing.assert_array_equal(ra[0].cpu().numpy(), oracle.points_correct(qw, t[0], thr)[0], err_msg=str((H, W, nq, nt, thr)))
