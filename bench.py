@@ -354,7 +354,7 @@ def adaptation_bench(net, dev, rank, world, hbm_peak, n_pairs=2, num=100, steps=
         torch.cuda.synchronize()
         iso = torch.tensor([c0.elapsed_time(c1) / 10 * 2], dtype=torch.float64, device=dev)
         dist.all_reduce(iso, op=dist.ReduceOp.MAX)
-        res["sharded"] = {"what": "one batch, %d homography samples split round-robin over %d ranks; NCCL all-reduce(SUM) of prob and count" % (n, world),
+        res["sharded"] = {"what": "one batch, identity pass + %d homography samples split round-robin over %d ranks (the identity pass counts as rank 0's first unit); NCCL all-reduce(SUM) of prob and count" % (n, world),
                           "all_reduce_ms_isolated": round(float(iso[0]), 4),
                           "all_reduce_note": "all_reduce_ms is measured inside the batch and includes waiting for the slowest rank; "
                                              "all_reduce_ms_isolated is the same two collectives with the ranks aligned",

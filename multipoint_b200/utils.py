@@ -557,7 +557,9 @@ def _adaptation_core(images, is_optical, net, config, second, homographies, mask
 
     if homographies is None:
         homographies, masks = sample_adaptation_homographies((H, W), config, with_masks=False)
-    mine = list(range(rank, n_total, world))
+    # round-robin over num units, unit 0 being the identity pass (rank 0's) and unit i + 1 sample i: rank 0 then gets one
+    # sample fewer than the busiest rank instead of the identity pass on top of a full share
+    mine = [i for i in range(n_total) if (i + 1) % world == rank]
     tables = ops.linspace_tables(H, W, dev)
     n = len(mine)
     empty = torch.zeros((0, B, H, W), device=dev)
