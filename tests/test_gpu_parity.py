@@ -550,6 +550,11 @@ def test_warp_gather_array_path_is_bit_identical(ops, oracle):
         assert torch.equal(both[0], ops.warp(src4[:2], A_w, mode, pad)) and torch.equal(both[1], ops.warp(src4[2:], A_w, mode, pad))
     with pytest.raises(ValueError):
         ops.warp(src, A_w, groups=2)
+    # the cached gather array is reused by later calls of the same width: new contents must be seen (no stale texels)
+    for seed in range(4):
+        fresh = torch.rand((3, H, W), device="cuda", generator=torch.Generator(device="cuda").manual_seed(100 + seed))
+        got = ops.warp(fresh, A_w, 'bilinear', 'zeros')
+        assert torch.equal(got[2], ops.warp(fresh, A_w[2:3], 'bilinear', 'zeros')[0]), seed
 
 
 def _stub(g):
